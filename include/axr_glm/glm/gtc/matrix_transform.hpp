@@ -1,0 +1,3 @@
+// axr mini-glm forwarding header (see ../glm.hpp)
+#pragma once
+#include "../glm.hpp"
