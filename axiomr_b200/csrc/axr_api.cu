@@ -1,0 +1,630 @@
+// libaxr_b200.so — context management and the C ABI declared in include/axr_b200.h.
+// Host-side restatement of the bookkeeping in TiledPipeline::drawMesh (reference src/tiled_pipeline.cpp:143-322):
+// uniforms, per-draw buffers sized from counts (instead of the fixed 32 MB arenas, include/tiled_pipeline.hpp:98-107),
+// kernel sequencing on one CUDA stream (instead of ThreadPool futures, :183-248, :281-308).
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/axr_b200.h"
+#include "axr_kernels.cuh"
+
+using namespace axr;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DeviceMesh {
+	bool live = false;
+	float4* pos = nullptr;
+	VAttr* attr = nullptr;
+	unsigned* idx = nullptr;
+	float4* sv = nullptr;  // per-draw screen-space vertex records (16 B each)
+	unsigned long long n_verts = 0, n_faces = 0;
+	std::vector<unsigned long long> group_first;  // n_groups + 1
+	std::vector<Material> materials;              // host copy
+	Material* d_materials = nullptr;
+	unsigned long long* d_group_first = nullptr;
+	bool materials_dirty = true;
+};
+
+struct DeviceTexture {
+	bool live = false;
+	uchar4* data = nullptr;
+	int w = 0, h = 0;
+};
+
+struct PendingDraw {
+	bool valid = false;
+	axr_mesh mesh = -1;
+	float model[16];
+	int redo_depth = 0;
+};
+
+}  // namespace
+
+struct axr_ctx {
+	int device = 0;
+	FrameParams fp{};
+	int sampler = 0;
+	cudaStream_t stream = nullptr;
+	bool own_stream = false;
+	std::string error;
+
+	// framebuffer (full-frame pitch; only the band rows are touched)
+	unsigned* color = nullptr;
+	float* depth = nullptr;
+	unsigned* out_color = nullptr;  // where the resolve stores go (own buffers unless axr_set_output redirected them)
+	float* out_depth = nullptr;
+
+	// per-frame state
+	float view_proj[16];
+	float viewport[16];
+	float cam_pos[3];
+	int shader_kind = AXR_SHADER_FLAT;
+	axr_shader_params shader_params{};
+
+	// raster state
+	unsigned long long* vis = nullptr;
+	unsigned* tile_touched = nullptr;
+	unsigned* tile_count = nullptr;
+	unsigned* bin_start = nullptr;
+	unsigned* items = nullptr;
+	unsigned ref_cap = 0;
+	TriRecord* records = nullptr;
+	unsigned rec_cap = 0;
+	unsigned* n_records = nullptr;
+	DrawStatus* d_status = nullptr;
+	DrawStatus* h_status = nullptr;  // pinned
+	cudaEvent_t status_event = nullptr;
+	PendingDraw pending;
+	axr_stats stats{};
+
+	std::vector<DeviceMesh> meshes;
+	std::vector<DeviceTexture> textures;
+	std::vector<void*> ipc_opened;
+};
+
+namespace {
+
+int fail(axr_ctx* ctx, int code, const char* fmt, ...) {
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	if (ctx) ctx->error = buf; else g_create_error = buf;
+	return code;
+}
+
+#define CU(call)                                                                                          \
+	do {                                                                                                  \
+		cudaError_t e_ = (call);                                                                          \
+		if (e_ != cudaSuccess) return fail(ctx, AXR_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+inline int grid_for(size_t n, int block, int cap = 148 * 16) {
+	size_t g = (n + block - 1) / block;
+	if (g < 1) g = 1;
+	if (g > (size_t)cap) g = cap;
+	return (int)g;
+}
+
+int n_tiles(const axr_ctx* c) { return c->fp.ntx * c->fp.nty; }
+
+int reset_raster_state(axr_ctx* ctx) {
+	size_t npx = (size_t)ctx->fp.W * ctx->fp.H;
+	k_fill_u64<<<grid_for(npx, 256), 256, 0, ctx->stream>>>(ctx->vis, KEY_EMPTY, npx);
+	k_fill_u32<<<grid_for(n_tiles(ctx), 256), 256, 0, ctx->stream>>>(ctx->tile_touched, 0u, (size_t)n_tiles(ctx));
+	k_fill_u32<<<grid_for(n_tiles(ctx), 256), 256, 0, ctx->stream>>>(ctx->tile_count, 0u, (size_t)n_tiles(ctx));
+	CU(cudaGetLastError());
+	return AXR_OK;
+}
+
+int ensure_bins(axr_ctx* ctx, unsigned want_rec, unsigned want_ref) {
+	if (want_rec > ctx->rec_cap) {
+		if (ctx->records) CU(cudaFree(ctx->records));
+		ctx->records = nullptr;
+		unsigned cap = want_rec + want_rec / 8 + 1024;
+		CU(cudaMalloc(&ctx->records, (size_t)cap * sizeof(TriRecord)));
+		ctx->rec_cap = cap;
+	}
+	if (want_ref > ctx->ref_cap) {
+		if (ctx->items) CU(cudaFree(ctx->items));
+		ctx->items = nullptr;
+		unsigned cap = want_ref + want_ref / 8 + 4096;
+		CU(cudaMalloc(&ctx->items, (size_t)cap * sizeof(unsigned)));
+		ctx->ref_cap = cap;
+	}
+	return AXR_OK;
+}
+
+int sync_materials(axr_ctx* ctx, DeviceMesh& m) {
+	if (!m.materials_dirty) return AXR_OK;
+	CU(cudaMemcpyAsync(m.d_materials, m.materials.data(), m.materials.size() * sizeof(Material), cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));  // the host vector may change right after
+	m.materials_dirty = false;
+	return AXR_OK;
+}
+
+int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model);
+
+// Inspect the status of the draw issued last; if its bins overflowed (its tile kernel then did nothing), grow and re-issue.
+int check_pending(axr_ctx* ctx) {
+	if (!ctx->pending.valid) return AXR_OK;
+	CU(cudaEventSynchronize(ctx->status_event));
+	PendingDraw p = ctx->pending;
+	ctx->pending.valid = false;
+	const DrawStatus st = *ctx->h_status;
+	ctx->stats.clipped_faces = st.clipped_faces;
+	ctx->stats.triangles = st.triangles;
+	ctx->stats.small_triangles = st.small_triangles;
+	ctx->stats.binned_triangles = st.binned_triangles;
+	ctx->stats.bin_refs = st.bin_refs;
+	if (!st.overflow) return AXR_OK;
+	if (p.redo_depth >= 2) return fail(ctx, AXR_ERR_CAPACITY, "bin capacity still exceeded after regrowing (records %llu refs %llu)",
+	                                   (unsigned long long)st.binned_triangles, (unsigned long long)st.bin_refs);
+	CU(cudaStreamSynchronize(ctx->stream));
+	int rc = ensure_bins(ctx, (unsigned)st.binned_triangles, (unsigned)st.bin_refs);
+	if (rc) return rc;
+	rc = reset_raster_state(ctx);
+	if (rc) return rc;
+	rc = issue_draw(ctx, p.mesh, p.model);
+	if (rc) return rc;
+	ctx->pending.redo_depth = p.redo_depth + 1;
+	ctx->stats.redo = 1;
+	return check_pending(ctx);
+}
+
+template <typename Shader>
+void launch_tile(axr_ctx* ctx, const MeshView& mv, const Uniforms& u, const TileIn& in) {
+	dim3 grid(ctx->fp.ntx, ctx->fp.ty_hi - ctx->fp.ty_lo);
+	k_tile_shade<Shader><<<grid, TILE_THREADS, 0, ctx->stream>>>(mv, u, ctx->fp, in);
+}
+
+int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model) {
+	DeviceMesh& m = ctx->meshes[mh];
+	int rc = sync_materials(ctx, m);
+	if (rc) return rc;
+	// shader / material validation (the reference dereferences null textures, include/shaders/shaders.hpp:178,210)
+	for (const Material& mat : m.materials) {
+		if (ctx->shader_kind >= AXR_SHADER_PHONG && (!mat.tex[0].data || !mat.tex[1].data))
+			return fail(ctx, AXR_ERR_MATERIAL, "shader needs diffuse + bump textures on every material group");
+		if (ctx->shader_kind == AXR_SHADER_PBR && (!mat.tex[2].data || !mat.tex[3].data || !mat.tex[4].data))
+			return fail(ctx, AXR_ERR_MATERIAL, "PBRShader needs metallic, roughness and ao textures on every material group");
+	}
+	Uniforms u;
+	u.model = load_m4(model);
+	u.mvp = mul(load_m4(ctx->view_proj), u.model);  // reference src/tiled_pipeline.cpp:149
+	m4 inv = inverse(u.model);
+	u.normal_mat.c[0] = V3(inv.c[0].x, inv.c[1].x, inv.c[2].x);  // mat3(transpose(inverse(model)))
+	u.normal_mat.c[1] = V3(inv.c[0].y, inv.c[1].y, inv.c[2].y);
+	u.normal_mat.c[2] = V3(inv.c[0].z, inv.c[1].z, inv.c[2].z);
+	u.cam_pos = V3(ctx->cam_pos[0], ctx->cam_pos[1], ctx->cam_pos[2]);
+	u.light_dir = V3(ctx->shader_params.light_dir[0], ctx->shader_params.light_dir[1], ctx->shader_params.light_dir[2]);
+	u.light_color = V3(ctx->shader_params.light_color[0], ctx->shader_params.light_color[1], ctx->shader_params.light_color[2]);
+	u.sampler = ctx->sampler;
+
+	MeshView mv;
+	mv.pos = m.pos; mv.attr = m.attr; mv.idx = m.idx;
+	mv.n_verts = m.n_verts; mv.n_faces = m.n_faces;
+	mv.materials = m.d_materials;
+	mv.group_first = m.d_group_first;
+	mv.n_groups = (int)m.materials.size();
+
+	cudaStream_t s = ctx->stream;
+	uint64_t launches = 0;
+	CU(cudaMemsetAsync(ctx->d_status, 0, sizeof(DrawStatus), s));
+	CU(cudaMemsetAsync(ctx->n_records, 0, sizeof(unsigned), s));
+	if (m.n_verts) {
+		k_vertex_xform<<<(unsigned)((m.n_verts + 255) / 256), 256, 0, s>>>(m.pos, m.n_verts, u.mvp, (float)ctx->fp.W, (float)ctx->fp.H, m.sv);
+		++launches;
+	}
+	SetupOut so;
+	so.vis = ctx->vis; so.tile_touched = ctx->tile_touched; so.tile_count = ctx->tile_count;
+	so.records = ctx->records; so.rec_cap = ctx->rec_cap; so.n_records = ctx->n_records; so.status = ctx->d_status;
+	if (m.n_faces) {
+		k_setup_raster<<<(unsigned)((m.n_faces + 255) / 256), 256, 0, s>>>(mv, m.sv, u.mvp, ctx->fp, so);
+		++launches;
+	}
+	k_scan_tiles<<<1, 1024, 0, s>>>(ctx->tile_count, ctx->bin_start, n_tiles(ctx), ctx->ref_cap, ctx->n_records, ctx->rec_cap, ctx->d_status);
+	++launches;
+	CU(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(DrawStatus), cudaMemcpyDeviceToHost, s));
+	CU(cudaEventRecord(ctx->status_event, s));
+	k_bin_scatter<<<148 * 4, 256, 0, s>>>(ctx->records, ctx->n_records, ctx->fp, ctx->bin_start, ctx->tile_count, ctx->items, ctx->d_status);
+	++launches;
+	TileIn in;
+	in.vis = ctx->vis; in.tile_touched = ctx->tile_touched; in.tile_cursor = ctx->tile_count; in.bin_start = ctx->bin_start;
+	in.items = ctx->items; in.records = ctx->records; in.n_records = ctx->n_records; in.status = ctx->d_status; in.sv = m.sv;
+	in.color = ctx->out_color; in.depth = ctx->out_depth;
+	switch (ctx->shader_kind) {
+	case AXR_SHADER_FLAT: launch_tile<FlatShader>(ctx, mv, u, in); break;
+	case AXR_SHADER_PHONG: launch_tile<PhongShader>(ctx, mv, u, in); break;
+	case AXR_SHADER_PBR: launch_tile<PBRShader>(ctx, mv, u, in); break;
+	default: return fail(ctx, AXR_ERR_UNSUPPORTED, "unknown shader kind %d", ctx->shader_kind);
+	}
+	++launches;
+	CU(cudaGetLastError());
+	ctx->stats.faces = m.n_faces;
+	ctx->stats.kernel_launches = launches;
+	ctx->stats.redo = 0;
+	ctx->pending.valid = true;
+	ctx->pending.mesh = mh;
+	memcpy(ctx->pending.model, model, sizeof(float) * 16);
+	ctx->pending.redo_depth = 0;
+	return AXR_OK;
+}
+
+bool valid_mesh(const axr_ctx* ctx, axr_mesh m) { return m >= 0 && (size_t)m < ctx->meshes.size() && ctx->meshes[m].live; }
+bool valid_tex(const axr_ctx* ctx, axr_tex t) { return t >= 0 && (size_t)t < ctx->textures.size() && ctx->textures[t].live; }
+
+}  // namespace
+
+extern "C" {
+
+int axr_abi_version(void) { return AXR_ABI_VERSION; }
+
+const char* axr_last_error(const axr_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int axr_create(const axr_config* cfg, axr_ctx** out) {
+	axr_ctx* ctx = nullptr;  // for the CU/fail macros: errors land in g_create_error
+	if (!cfg || !out) return fail(ctx, AXR_ERR_INVALID, "axr_create: null argument");
+	*out = nullptr;
+	if (cfg->width <= 0 || cfg->height <= 0 || cfg->width > 65536 || cfg->height > 65536)
+		return fail(ctx, AXR_ERR_INVALID, "axr_create: bad framebuffer size %dx%d", cfg->width, cfg->height);
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+		return fail(ctx, AXR_ERR_NO_DEVICE, "axr_create: no CUDA device (this library has no CPU path)");
+	if (cfg->device < 0 || cfg->device >= ndev) return fail(ctx, AXR_ERR_INVALID, "axr_create: device %d of %d", cfg->device, ndev);
+	cudaDeviceProp prop;
+	CU(cudaGetDeviceProperties(&prop, cfg->device));
+	if (prop.major != 10) return fail(ctx, AXR_ERR_NO_DEVICE, "axr_create: device %d is sm_%d%d, kernels are built for sm_100a only", cfg->device, prop.major, prop.minor);
+	int y0 = cfg->band_y0, y1 = cfg->band_y1;
+	if (y0 == 0 && y1 == 0) y1 = cfg->height;
+	if (y0 < 0 || y1 > cfg->height || y0 >= y1 || (y0 % REF_TILE) != 0)
+		return fail(ctx, AXR_ERR_INVALID, "axr_create: bad band [%d,%d) (start must be a multiple of %d)", y0, y1, REF_TILE);
+	CU(cudaSetDevice(cfg->device));
+	axr_ctx* c = new axr_ctx();
+	ctx = c;
+	c->device = cfg->device;
+	c->fp.W = cfg->width; c->fp.H = cfg->height;
+	c->fp.y_lo = y0; c->fp.y_hi = y1;
+	c->fp.ntx = (cfg->width + GT - 1) / GT;
+	c->fp.nty = (cfg->height + GT - 1) / GT;
+	c->fp.ty_lo = y0 / GT;
+	c->fp.ty_hi = (y1 + GT - 1) / GT;
+	c->sampler = cfg->sampler ? 1 : 0;
+	// identity uniforms until axr_set_uniforms
+	memset(c->view_proj, 0, sizeof c->view_proj);
+	memset(c->viewport, 0, sizeof c->viewport);
+	for (int i = 0; i < 4; ++i) c->view_proj[i * 5] = c->viewport[i * 5] = 1.0f;
+	c->cam_pos[0] = c->cam_pos[1] = c->cam_pos[2] = 0.f;
+	c->shader_params.light_dir[1] = -1.0f;
+	c->shader_params.light_color[0] = c->shader_params.light_color[1] = c->shader_params.light_color[2] = 1.0f;
+#define CUC(call)                                                                              \
+	do {                                                                                       \
+		cudaError_t e_ = (call);                                                               \
+		if (e_ != cudaSuccess) {                                                               \
+			int rc_ = fail(nullptr, AXR_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));    \
+			axr_destroy(c);                                                                    \
+			return rc_;                                                                        \
+		}                                                                                      \
+	} while (0)
+	if (cfg->stream) { c->stream = (cudaStream_t)cfg->stream; c->own_stream = false; }
+	else { CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+	const size_t npx = (size_t)cfg->width * cfg->height;
+	const size_t nt = (size_t)c->fp.ntx * c->fp.nty;
+	CUC(cudaMalloc(&c->color, npx * 4));
+	CUC(cudaMalloc(&c->depth, npx * 4));
+	c->out_color = c->color; c->out_depth = c->depth;
+	CUC(cudaMalloc(&c->vis, npx * 8));
+	CUC(cudaMalloc(&c->tile_touched, nt * 4));
+	CUC(cudaMalloc(&c->tile_count, nt * 4));
+	CUC(cudaMalloc(&c->bin_start, (nt + 1) * 4));
+	CUC(cudaMalloc(&c->n_records, 4));
+	CUC(cudaMalloc(&c->d_status, sizeof(DrawStatus)));
+	CUC(cudaMallocHost(&c->h_status, sizeof(DrawStatus)));
+	CUC(cudaEventCreateWithFlags(&c->status_event, cudaEventDisableTiming));
+	c->rec_cap = 1u << 18; c->ref_cap = 1u << 20;
+	CUC(cudaMalloc(&c->records, (size_t)c->rec_cap * sizeof(TriRecord)));
+	CUC(cudaMalloc(&c->items, (size_t)c->ref_cap * 4));
+	if (reset_raster_state(c) != AXR_OK) { g_create_error = c->error; axr_destroy(c); return AXR_ERR_CUDA; }
+	k_clear<<<grid_for(npx, 256), 256, 0, c->stream>>>(c->color, c->depth, 0u, INFINITY, 0, npx);  // Framebuffer ctor: colour 0, depth +inf
+	CUC(cudaStreamSynchronize(c->stream));
+#undef CUC
+	*out = c;
+	return AXR_OK;
+}
+
+void axr_destroy(axr_ctx* ctx) {
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+	for (auto& m : ctx->meshes) if (m.live) { cudaFree(m.pos); cudaFree(m.attr); cudaFree(m.idx); cudaFree(m.sv); cudaFree(m.d_materials); cudaFree(m.d_group_first); }
+	for (auto& t : ctx->textures) if (t.live) cudaFree(t.data);
+	for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
+	cudaFree(ctx->color); cudaFree(ctx->depth); cudaFree(ctx->vis); cudaFree(ctx->tile_touched); cudaFree(ctx->tile_count);
+	cudaFree(ctx->bin_start); cudaFree(ctx->items); cudaFree(ctx->records); cudaFree(ctx->n_records); cudaFree(ctx->d_status);
+	if (ctx->h_status) cudaFreeHost(ctx->h_status);
+	if (ctx->status_event) cudaEventDestroy(ctx->status_event);
+	if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+int axr_upload_mesh(axr_ctx* ctx, const float* vertices, uint64_t n_verts, const uint32_t* indices, uint64_t n_faces,
+                    const axr_group* groups, uint32_t n_groups, axr_mesh* out) {
+	if (!ctx) return AXR_ERR_INVALID;
+	if (!out || (n_verts && !vertices) || (n_faces && !indices)) return fail(ctx, AXR_ERR_INVALID, "axr_upload_mesh: null argument");
+	if (n_faces >= (1ull << 29)) return fail(ctx, AXR_ERR_CAPACITY, "axr_upload_mesh: %llu faces exceed the 2^29 ordinal range", (unsigned long long)n_faces);
+	if (n_verts >= (1ull << 32)) return fail(ctx, AXR_ERR_CAPACITY, "axr_upload_mesh: %llu vertices exceed 32-bit indices", (unsigned long long)n_verts);
+	for (uint64_t i = 0; i < n_faces * 3; ++i)
+		if (indices[i] >= n_verts) return fail(ctx, AXR_ERR_INVALID, "axr_upload_mesh: index %u out of range at face %llu", indices[i], (unsigned long long)(i / 3));
+	CU(cudaSetDevice(ctx->device));
+	int rc = check_pending(ctx);
+	if (rc) return rc;
+	DeviceMesh m;
+	m.n_verts = n_verts; m.n_faces = n_faces;
+	// material groups: contiguous ascending face ranges (reference src/mesh.cpp:336-346)
+	if (!groups || n_groups == 0) {
+		m.group_first = {0ull, (unsigned long long)n_faces};
+	} else {
+		unsigned long long expect = 0;
+		for (uint32_t g = 0; g < n_groups; ++g) {
+			if (groups[g].first_face != expect) return fail(ctx, AXR_ERR_INVALID, "axr_upload_mesh: group %u does not start where group %u ends", g, g ? g - 1 : 0);
+			m.group_first.push_back(groups[g].first_face);
+			expect += groups[g].face_count;
+		}
+		if (expect != n_faces) return fail(ctx, AXR_ERR_INVALID, "axr_upload_mesh: groups cover %llu of %llu faces", expect, (unsigned long long)n_faces);
+		m.group_first.push_back(expect);
+	}
+	const size_t ng = m.group_first.size() - 1;
+	m.materials.assign(ng, Material{});
+	const size_t nv = n_verts ? n_verts : 1, nf = n_faces ? n_faces : 1;
+	float* raw = nullptr;
+	CU(cudaMalloc(&m.pos, nv * sizeof(float4)));
+	CU(cudaMalloc(&m.attr, nv * sizeof(VAttr)));
+	CU(cudaMalloc(&m.sv, nv * sizeof(float4)));
+	CU(cudaMalloc(&m.idx, nf * 3 * sizeof(unsigned)));
+	CU(cudaMalloc(&m.d_materials, ng * sizeof(Material)));
+	CU(cudaMalloc(&m.d_group_first, (ng + 1) * sizeof(unsigned long long)));
+	if (n_verts) {
+		CU(cudaMalloc(&raw, n_verts * 14 * sizeof(float)));
+		CU(cudaMemcpyAsync(raw, vertices, n_verts * 14 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+		k_split_vertices<<<(unsigned)((n_verts + 255) / 256), 256, 0, ctx->stream>>>(raw, n_verts, m.pos, m.attr);
+	}
+	if (n_faces) CU(cudaMemcpyAsync(m.idx, indices, n_faces * 3 * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaMemcpyAsync(m.d_group_first, m.group_first.data(), (ng + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	if (raw) CU(cudaFree(raw));
+	m.live = true;
+	m.materials_dirty = true;
+	size_t slot = ctx->meshes.size();
+	for (size_t i = 0; i < ctx->meshes.size(); ++i) if (!ctx->meshes[i].live) { slot = i; break; }
+	if (slot == ctx->meshes.size()) ctx->meshes.push_back(std::move(m)); else ctx->meshes[slot] = std::move(m);
+	*out = (axr_mesh)slot;
+	return AXR_OK;
+}
+
+int axr_free_mesh(axr_ctx* ctx, axr_mesh mh) {
+	if (!ctx) return AXR_ERR_INVALID;
+	if (!valid_mesh(ctx, mh)) return fail(ctx, AXR_ERR_INVALID, "axr_free_mesh: bad handle %d", mh);
+	CU(cudaSetDevice(ctx->device));
+	int rc = check_pending(ctx);
+	if (rc) return rc;
+	CU(cudaStreamSynchronize(ctx->stream));
+	DeviceMesh& m = ctx->meshes[mh];
+	cudaFree(m.pos); cudaFree(m.attr); cudaFree(m.idx); cudaFree(m.sv); cudaFree(m.d_materials); cudaFree(m.d_group_first);
+	m = DeviceMesh();
+	return AXR_OK;
+}
+
+int axr_upload_texture(axr_ctx* ctx, const uint8_t* rgba, int w, int h, axr_tex* out) {
+	if (!ctx) return AXR_ERR_INVALID;
+	if (!rgba || !out || w <= 0 || h <= 0) return fail(ctx, AXR_ERR_INVALID, "axr_upload_texture: bad argument");
+	CU(cudaSetDevice(ctx->device));
+	DeviceTexture t;
+	t.w = w; t.h = h;
+	CU(cudaMalloc(&t.data, (size_t)w * h * 4));
+	CU(cudaMemcpyAsync(t.data, rgba, (size_t)w * h * 4, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	t.live = true;
+	size_t slot = ctx->textures.size();
+	for (size_t i = 0; i < ctx->textures.size(); ++i) if (!ctx->textures[i].live) { slot = i; break; }
+	if (slot == ctx->textures.size()) ctx->textures.push_back(t); else ctx->textures[slot] = t;
+	*out = (axr_tex)slot;
+	return AXR_OK;
+}
+
+int axr_free_texture(axr_ctx* ctx, axr_tex th) {
+	if (!ctx) return AXR_ERR_INVALID;
+	if (!valid_tex(ctx, th)) return fail(ctx, AXR_ERR_INVALID, "axr_free_texture: bad handle %d", th);
+	CU(cudaSetDevice(ctx->device));
+	int rc = check_pending(ctx);
+	if (rc) return rc;
+	CU(cudaStreamSynchronize(ctx->stream));
+	const uchar4* gone = ctx->textures[th].data;
+	cudaFree(ctx->textures[th].data);
+	ctx->textures[th] = DeviceTexture();
+	for (auto& m : ctx->meshes)  // materials that referenced the texture lose it (a later draw then reports AXR_ERR_MATERIAL)
+		if (m.live)
+			for (auto& mat : m.materials)
+				for (auto& tr : mat.tex)
+					if (tr.data == gone) { tr = TexRef{nullptr, 0, 0}; m.materials_dirty = true; }
+	return AXR_OK;
+}
+
+int axr_set_material(axr_ctx* ctx, axr_mesh mh, uint32_t group, axr_tex diffuse, axr_tex bump, axr_tex metallic, axr_tex roughness,
+                     axr_tex ao, float specular_exponent) {
+	if (!ctx) return AXR_ERR_INVALID;
+	if (!valid_mesh(ctx, mh)) return fail(ctx, AXR_ERR_INVALID, "axr_set_material: bad mesh handle %d", mh);
+	DeviceMesh& m = ctx->meshes[mh];
+	if (group >= m.materials.size()) return fail(ctx, AXR_ERR_INVALID, "axr_set_material: group %u of %zu", group, m.materials.size());
+	const axr_tex th[5] = {diffuse, bump, metallic, roughness, ao};
+	Material mat{};
+	for (int i = 0; i < 5; ++i) {
+		if (th[i] == AXR_NO_TEXTURE) { mat.tex[i] = TexRef{nullptr, 0, 0}; continue; }
+		if (!valid_tex(ctx, th[i])) return fail(ctx, AXR_ERR_INVALID, "axr_set_material: bad texture handle %d", th[i]);
+		const DeviceTexture& t = ctx->textures[th[i]];
+		mat.tex[i] = TexRef{t.data, t.w, t.h};
+	}
+	mat.specular_exponent = specular_exponent;
+	int rc = check_pending(ctx);
+	if (rc) return rc;
+	m.materials[group] = mat;
+	m.materials_dirty = true;
+	return AXR_OK;
+}
+
+int axr_set_uniforms(axr_ctx* ctx, const float view_proj[16], const float viewport[16], const float cam_pos[3]) {
+	if (!ctx) return AXR_ERR_INVALID;
+	if (!view_proj || !cam_pos) return fail(ctx, AXR_ERR_INVALID, "axr_set_uniforms: null argument");
+	memcpy(ctx->view_proj, view_proj, sizeof ctx->view_proj);
+	if (viewport) memcpy(ctx->viewport, viewport, sizeof ctx->viewport);
+	memcpy(ctx->cam_pos, cam_pos, sizeof ctx->cam_pos);
+	return AXR_OK;
+}
+
+int axr_set_shader(axr_ctx* ctx, int kind, const axr_shader_params* params, size_t params_size) {
+	if (!ctx) return AXR_ERR_INVALID;
+	if (kind != AXR_SHADER_FLAT && kind != AXR_SHADER_PHONG && kind != AXR_SHADER_PBR)
+		return fail(ctx, AXR_ERR_UNSUPPORTED, "axr_set_shader: no device functor for shader kind %d", kind);
+	if (!params || params_size != sizeof(axr_shader_params)) return fail(ctx, AXR_ERR_INVALID, "axr_set_shader: bad params");
+	ctx->shader_kind = kind;
+	ctx->shader_params = *params;
+	return AXR_OK;
+}
+
+int axr_set_sampler(axr_ctx* ctx, int sampler) {
+	if (!ctx) return AXR_ERR_INVALID;
+	if (sampler != AXR_SAMPLER_NEAREST && sampler != AXR_SAMPLER_BILINEAR) return fail(ctx, AXR_ERR_INVALID, "axr_set_sampler: %d", sampler);
+	ctx->sampler = sampler;
+	return AXR_OK;
+}
+
+int axr_clear(axr_ctx* ctx, uint32_t packed_argb, float depth) {
+	if (!ctx) return AXR_ERR_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	int rc = check_pending(ctx);
+	if (rc) return rc;
+	const size_t first = (size_t)ctx->fp.y_lo * ctx->fp.W, n = (size_t)(ctx->fp.y_hi - ctx->fp.y_lo) * ctx->fp.W;
+	k_clear<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->out_color, ctx->out_depth, packed_argb, depth, first, n);
+	CU(cudaGetLastError());
+	return AXR_OK;
+}
+
+int axr_upload_framebuffer(axr_ctx* ctx, const uint8_t* bgra, const float* depth) {
+	if (!ctx) return AXR_ERR_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	int rc = check_pending(ctx);
+	if (rc) return rc;
+	const size_t first = (size_t)ctx->fp.y_lo * ctx->fp.W, n = (size_t)(ctx->fp.y_hi - ctx->fp.y_lo) * ctx->fp.W;
+	if (bgra) CU(cudaMemcpyAsync(ctx->out_color + first, bgra + first * 4, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+	if (depth) CU(cudaMemcpyAsync(ctx->out_depth + first, depth + first, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return AXR_OK;
+}
+
+int axr_resolve(axr_ctx* ctx, uint8_t* bgra_out, float* depth_out) {
+	if (!ctx) return AXR_ERR_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	int rc = check_pending(ctx);
+	if (rc) return rc;
+	const size_t first = (size_t)ctx->fp.y_lo * ctx->fp.W, n = (size_t)(ctx->fp.y_hi - ctx->fp.y_lo) * ctx->fp.W;
+	if (bgra_out) CU(cudaMemcpyAsync(bgra_out + first * 4, ctx->out_color + first, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (depth_out) CU(cudaMemcpyAsync(depth_out + first, ctx->out_depth + first, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return AXR_OK;
+}
+
+int axr_draw_mesh(axr_ctx* ctx, axr_mesh mh, const float model[16]) {
+	if (!ctx) return AXR_ERR_INVALID;
+	if (!valid_mesh(ctx, mh) || !model) return fail(ctx, AXR_ERR_INVALID, "axr_draw_mesh: bad mesh handle %d or null model", mh);
+	CU(cudaSetDevice(ctx->device));
+	int rc = check_pending(ctx);
+	if (rc) return rc;
+	return issue_draw(ctx, mh, model);
+}
+
+int axr_sync(axr_ctx* ctx) {
+	if (!ctx) return AXR_ERR_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	int rc = check_pending(ctx);
+	if (rc) return rc;
+	CU(cudaStreamSynchronize(ctx->stream));
+	return AXR_OK;
+}
+
+int axr_get_stats(axr_ctx* ctx, axr_stats* out) {
+	if (!ctx || !out) return AXR_ERR_INVALID;
+	int rc = check_pending(ctx);
+	if (rc) return rc;
+	*out = ctx->stats;
+	return AXR_OK;
+}
+
+void* axr_host_alloc(size_t bytes) {
+	void* p = nullptr;
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+	return p;
+}
+void axr_host_free(void* p) {
+	if (p) cudaFreeHost(p);
+}
+
+void* axr_stream(axr_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int axr_framebuffer_device(axr_ctx* ctx, void** bgra_dev, void** depth_dev) {
+	if (!ctx) return AXR_ERR_INVALID;
+	if (bgra_dev) *bgra_dev = ctx->color;
+	if (depth_dev) *depth_dev = ctx->depth;
+	return AXR_OK;
+}
+
+int axr_set_output(axr_ctx* ctx, void* bgra_dev, void* depth_dev) {
+	if (!ctx) return AXR_ERR_INVALID;
+	int rc = check_pending(ctx);
+	if (rc) return rc;
+	if ((bgra_dev == nullptr) != (depth_dev == nullptr)) return fail(ctx, AXR_ERR_INVALID, "axr_set_output: pass both pointers or neither");
+	ctx->out_color = bgra_dev ? (unsigned*)bgra_dev : ctx->color;
+	ctx->out_depth = depth_dev ? (float*)depth_dev : ctx->depth;
+	return AXR_OK;
+}
+
+int axr_framebuffer_ipc(axr_ctx* ctx, void* color_handle64, void* depth_handle64) {
+	if (!ctx || !color_handle64 || !depth_handle64) return AXR_ERR_INVALID;
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)color_handle64, ctx->color));
+	CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)depth_handle64, ctx->depth));
+	return AXR_OK;
+}
+
+int axr_open_ipc(axr_ctx* ctx, const void* handle64, void** dev_ptr_out) {
+	if (!ctx || !handle64 || !dev_ptr_out) return AXR_ERR_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle64, sizeof h);
+	CU(cudaIpcOpenMemHandle(dev_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+	ctx->ipc_opened.push_back(*dev_ptr_out);
+	return AXR_OK;
+}
+
+int axr_close_ipc(axr_ctx* ctx, void* dev_ptr) {
+	if (!ctx || !dev_ptr) return AXR_ERR_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	for (size_t i = 0; i < ctx->ipc_opened.size(); ++i)
+		if (ctx->ipc_opened[i] == dev_ptr) {
+			CU(cudaStreamSynchronize(ctx->stream));
+			CU(cudaIpcCloseMemHandle(dev_ptr));
+			ctx->ipc_opened.erase(ctx->ipc_opened.begin() + i);
+			return AXR_OK;
+		}
+	return fail(ctx, AXR_ERR_INVALID, "axr_close_ipc: pointer was not opened by this context");
+}
+
+}  // extern "C"

@@ -1,0 +1,439 @@
+// CUDA kernels of the B200 tiled-raster path (sm_100a). One draw =
+//   k_vertex_xform   per unique vertex : mvp transform, clip code, perspective divide -> 16 B screen record
+//   k_setup_raster   per input face    : clip (slow path) / cull / setup; tiny triangles are rasterised right here
+//                                        with 64-bit atomicMin visibility keys, larger ones become 40 B setup records
+//                                        and are counted per 32x32 screen tile (warp-aggregated append)
+//   k_scan_tiles     one CTA           : block-wide exclusive prefix sum of the per-tile counts
+//   k_bin_scatter    per record        : scatter record ids into the per-tile lists
+//   k_tile_shade<S>  one CTA per tile  : tile keys staged in shared memory, binned triangles rasterised with shared
+//                                        atomics, then deferred IShader::vertex x3 + IShader::fragment for the single
+//                                        visible triangle of each pixel, depth test against the framebuffer and one
+//                                        coalesced BGRA8 + f32 store
+// Nothing here is a dense contraction, so there is no tensor-core work; the path is HBM/L2-gather and FP32-issue bound.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "axr_shaders.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace axr {
+
+constexpr int GT = 32;            // GPU tile edge in pixels (a multiple of REF_TILE; keeps rows 128 B wide for the resolve)
+constexpr int GT_PIX = GT * GT;
+constexpr int SMALL_BOX = 4;      // triangles whose pixel box is <= SMALL_BOX x SMALL_BOX are rasterised in k_setup_raster
+constexpr int TILE_THREADS = 256;
+
+// 40-byte setup record of a triangle that goes through the tile bins
+struct __align__(8) TriRecord {
+	float x0, y0, x1, y1, x2, y2, z0, z1, z2;
+	unsigned ordinal;
+};
+
+// Device-side draw status / counters (copied to pinned host memory after the scan)
+struct DrawStatus {
+	unsigned long long clipped_faces, triangles, small_triangles, binned_triangles;  // binned_triangles = records wanted
+	unsigned long long bin_refs;                                                      // refs wanted
+	unsigned overflow;                                                                // 1: records, 2: refs
+	unsigned pad;
+};
+
+struct FrameParams {
+	int W, H;
+	int y_lo, y_hi;      // band rows [y_lo, y_hi)
+	int ntx, nty;        // GPU tiles over the full frame
+	int ty_lo, ty_hi;    // tile rows touched by the band
+};
+
+struct MeshView {
+	const float4* pos;        // x,y,z,1
+	const VAttr* attr;
+	const unsigned* idx;      // 3 per face
+	unsigned long long n_verts, n_faces;
+	const Material* materials;
+	const unsigned long long* group_first;  // n_groups + 1 entries (ascending), only read when n_groups > 1
+	int n_groups;
+};
+
+// ------------------------------------------------------------------------------------------------ utility kernels
+__global__ void k_fill_u64(unsigned long long* p, unsigned long long v, size_t n) {
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (; i < n; i += stride) p[i] = v;
+}
+__global__ void k_fill_u32(unsigned* p, unsigned v, size_t n) {
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (; i < n; i += stride) p[i] = v;
+}
+// Framebuffer::clearColor / clearDepth (reference src/framebuffer.cpp:26-42) over rows [y_lo, y_hi)
+__global__ void k_clear(unsigned* color, float* depth, unsigned packed, float z, size_t first, size_t n) {
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (; i < n; i += stride) { color[first + i] = packed; depth[first + i] = z; }
+}
+// AoS AR::Vertex (56 B) -> position float4 + 48 B attribute record (done once at mesh upload)
+__global__ void k_split_vertices(const float* __restrict__ raw, unsigned long long n, float4* __restrict__ pos, VAttr* __restrict__ attr) {
+	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const float* v = raw + i * 14;
+	pos[i] = make_float4(v[0], v[1], v[2], 1.0f);
+	VAttr a;
+	a.uv[0] = v[3]; a.uv[1] = v[4];
+	a.n[0] = v[5]; a.n[1] = v[6]; a.n[2] = v[7];
+	a.t[0] = v[8]; a.t[1] = v[9]; a.t[2] = v[10];
+	a.b[0] = v[11]; a.b[1] = v[12]; a.b[2] = v[13];
+	a.pad = 0.f;
+	attr[i] = a;
+}
+
+// ------------------------------------------------------------------------------------------------ vertex stage
+// reference src/tiled_pipeline.cpp:210-212 (mvp * vec4(pos,1)) + :57-66 (perspective divide), once per unique vertex
+__global__ void __launch_bounds__(256) k_vertex_xform(const float4* __restrict__ pos, unsigned long long n, m4 mvp, float fW,
+                                                      float fH, float4* __restrict__ sv) {
+	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float4 p = __ldg(pos + i);
+	v4 c = mul(mvp, V4(p.x, p.y, p.z, 1.0f));
+	float sx, sy, z;
+	to_screen(c, fW, fH, sx, sy, z);
+	sv[i] = make_float4(sx, sy, z, __uint_as_float(clip_code(c)));
+}
+
+// ------------------------------------------------------------------------------------------------ setup + small raster
+struct SetupOut {
+	unsigned long long* vis;     // W*H visibility keys
+	unsigned* tile_touched;      // per GPU tile: 1 when the direct path wrote a key into it
+	unsigned* tile_count;        // per GPU tile: binned references
+	TriRecord* records;
+	unsigned rec_cap;
+	unsigned* n_records;         // device counter (also the number wanted when it overflows)
+	DrawStatus* status;
+};
+
+struct EmitCounters { unsigned tris, small, binned; };
+
+__device__ __forceinline__ void emit_triangle(const FrameParams& fp, const SetupOut& o, float x0, float y0, float x1, float y1,
+                                              float x2, float y2, float z0, float z1, float z2, unsigned ordinal, EmitCounters& cnt) {
+	cnt.tris++;
+	Setup s;
+	if (!setup_triangle(x0, y0, x1, y1, x2, y2, z0, z1, z2, fp.W, fp.y_lo, fp.y_hi, s)) return;
+	if (s.X1 - s.X0 <= SMALL_BOX && s.Y1 - s.Y0 <= SMALL_BOX) {
+		cnt.small++;
+		for (int py = s.Y0; py < s.Y1; ++py)
+			for (int px = s.X0; px < s.X1; ++px) {
+				float c0, c1, c2, al, be, ga;
+				if (!coverage(s, px, py, c0, c1, c2)) continue;
+				float z = interp_z(s, c0, c1, c2, al, be, ga);
+				if (!z_draws(z)) continue;
+				unsigned long long key = make_key(z, ordinal);
+				unsigned long long* slot = o.vis + (size_t)py * fp.W + px;
+				if (key < *slot) {  // cheap pre-test; the atomic decides
+					atomicMin(slot, key);
+					o.tile_touched[(py / GT) * fp.ntx + (px / GT)] = 1u;
+				}
+			}
+		return;
+	}
+	cnt.binned++;
+	// warp-aggregated append of the setup record
+	cg::coalesced_group g = cg::coalesced_threads();
+	unsigned base = 0;
+	if (g.thread_rank() == 0) base = atomicAdd(o.n_records, g.size());
+	unsigned slot = g.shfl(base, 0) + g.thread_rank();
+	if (slot < o.rec_cap) {
+		TriRecord r;
+		r.x0 = x0; r.y0 = y0; r.x1 = x1; r.y1 = y1; r.x2 = x2; r.y2 = y2; r.z0 = z0; r.z1 = z1; r.z2 = z2; r.ordinal = ordinal;
+		o.records[slot] = r;
+	}
+	int tx0 = s.X0 / GT, tx1 = (s.X1 - 1) / GT, ty0 = s.Y0 / GT, ty1 = (s.Y1 - 1) / GT;
+	for (int ty = ty0; ty <= ty1; ++ty)
+		for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(o.tile_count + ty * fp.ntx + tx, 1u);
+}
+
+// Clip slow path of one face for the visibility pass (positions only): reference src/tiled_pipeline.cpp:210-234
+__device__ __noinline__ void setup_clipped_face(const FrameParams& fp, const SetupOut& o, const m4& mvp, float4 p0, float4 p1,
+                                                float4 p2, unsigned face, EmitCounters& cnt) {
+	ClipPos a[MAX_CLIPPED_VERTS], b[MAX_CLIPPED_VERTS];
+	a[0].clip = mul(mvp, V4(p0.x, p0.y, p0.z, 1.0f));
+	a[1].clip = mul(mvp, V4(p1.x, p1.y, p1.z, 1.0f));
+	a[2].clip = mul(mvp, V4(p2.x, p2.y, p2.z, 1.0f));
+	ClipPos* out;
+	int n = clip_triangle(a, b, &out);
+	const float fW = (float)fp.W, fH = (float)fp.H;
+	for (int j = 0; j + 2 < n; j += 3) {
+		float x0, y0, z0, x1, y1, z1, x2, y2, z2;
+		to_screen(out[j].clip, fW, fH, x0, y0, z0);
+		to_screen(out[j + 1].clip, fW, fH, x1, y1, z1);
+		to_screen(out[j + 2].clip, fW, fH, x2, y2, z2);
+		if (is_backface(x0, y0, x1, y1, x2, y2)) continue;
+		emit_triangle(fp, o, x0, y0, x1, y1, x2, y2, z0, z1, z2, face * 8u + (unsigned)(j / 3), cnt);
+	}
+}
+
+__global__ void __launch_bounds__(256) k_setup_raster(MeshView mesh, const float4* __restrict__ sv, m4 mvp, FrameParams fp, SetupOut o) {
+	__shared__ unsigned s_cnt[4];
+	if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+	__syncthreads();
+	unsigned long long f = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	EmitCounters cnt = {0, 0, 0};
+	unsigned clipped = 0;
+	if (f < mesh.n_faces) {
+		unsigned i0 = __ldg(mesh.idx + f * 3), i1 = __ldg(mesh.idx + f * 3 + 1), i2 = __ldg(mesh.idx + f * 3 + 2);
+		float4 s0 = __ldg(sv + i0), s1 = __ldg(sv + i1), s2 = __ldg(sv + i2);
+		unsigned code = __float_as_uint(s0.w) | __float_as_uint(s1.w) | __float_as_uint(s2.w);
+		if (code == 0) {
+			// every vertex inside every plane: clipTriangle returns the triangle unchanged (reference src/pipeline.cpp:322-325)
+			if (!is_backface(s0.x, s0.y, s1.x, s1.y, s2.x, s2.y))
+				emit_triangle(fp, o, s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, (unsigned)f * 8u, cnt);
+		} else {
+			clipped = 1;
+			setup_clipped_face(fp, o, mvp, __ldg(mesh.pos + i0), __ldg(mesh.pos + i1), __ldg(mesh.pos + i2), (unsigned)f, cnt);
+		}
+	}
+	// block-level counter reduction: one global atomic per counter per CTA
+	unsigned w0 = __reduce_add_sync(0xffffffffu, clipped), w1 = __reduce_add_sync(0xffffffffu, cnt.tris);
+	unsigned w2 = __reduce_add_sync(0xffffffffu, cnt.small), w3 = __reduce_add_sync(0xffffffffu, cnt.binned);
+	if ((threadIdx.x & 31) == 0) {
+		if (w0) atomicAdd(&s_cnt[0], w0);
+		if (w1) atomicAdd(&s_cnt[1], w1);
+		if (w2) atomicAdd(&s_cnt[2], w2);
+		if (w3) atomicAdd(&s_cnt[3], w3);
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		if (s_cnt[0]) atomicAdd(&o.status->clipped_faces, (unsigned long long)s_cnt[0]);
+		if (s_cnt[1]) atomicAdd(&o.status->triangles, (unsigned long long)s_cnt[1]);
+		if (s_cnt[2]) atomicAdd(&o.status->small_triangles, (unsigned long long)s_cnt[2]);
+		if (s_cnt[3]) atomicAdd(&o.status->binned_triangles, (unsigned long long)s_cnt[3]);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ bins: scan + scatter
+// Block-wide exclusive prefix sum over the per-tile counts (one CTA of 1024 threads, chunked).
+// On exit: bin_start[0..n] holds offsets, tile_count[] is zeroed so k_bin_scatter can reuse it as the fill cursor.
+__global__ void __launch_bounds__(1024) k_scan_tiles(unsigned* tile_count, unsigned* bin_start, int n, unsigned ref_cap,
+                                                     const unsigned* n_records, unsigned rec_cap, DrawStatus* status) {
+	__shared__ unsigned s_warp[32];
+	__shared__ unsigned s_carry;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid == 0) s_carry = 0;
+	__syncthreads();
+	for (int base = 0; base < n; base += 1024) {
+		int i = base + tid;
+		unsigned v = (i < n) ? tile_count[i] : 0u;
+		unsigned x = v;
+		for (int d = 1; d < 32; d <<= 1) {
+			unsigned y = __shfl_up_sync(0xffffffffu, x, d);
+			if (lane >= d) x += y;
+		}
+		if (lane == 31) s_warp[warp] = x;
+		__syncthreads();
+		if (warp == 0) {
+			unsigned w = s_warp[lane];
+			for (int d = 1; d < 32; d <<= 1) {
+				unsigned y = __shfl_up_sync(0xffffffffu, w, d);
+				if (lane >= d) w += y;
+			}
+			s_warp[lane] = w;
+		}
+		__syncthreads();
+		unsigned carry = s_carry;
+		unsigned excl = carry + (warp ? s_warp[warp - 1] : 0u) + (x - v);
+		if (i < n) { bin_start[i] = excl; tile_count[i] = 0u; }
+		__syncthreads();
+		if (tid == 1023) s_carry = carry + s_warp[31];
+		__syncthreads();
+	}
+	if (tid == 0) {
+		unsigned total = s_carry;
+		bin_start[n] = total;
+		status->bin_refs = total;
+		unsigned ovf = 0;
+		if (*n_records > rec_cap) ovf |= 1u;
+		if (total > ref_cap) ovf |= 2u;
+		status->overflow = ovf;
+	}
+}
+
+__global__ void __launch_bounds__(256) k_bin_scatter(const TriRecord* __restrict__ records, const unsigned* __restrict__ n_records,
+                                                     FrameParams fp, const unsigned* __restrict__ bin_start, unsigned* cursor,
+                                                     unsigned* __restrict__ items, const DrawStatus* status) {
+	if (status->overflow) return;
+	unsigned n = *n_records;
+	for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+		TriRecord t = records[r];
+		Setup s;
+		if (!setup_triangle(t.x0, t.y0, t.x1, t.y1, t.x2, t.y2, t.z0, t.z1, t.z2, fp.W, fp.y_lo, fp.y_hi, s)) continue;
+		int tx0 = s.X0 / GT, tx1 = (s.X1 - 1) / GT, ty0 = s.Y0 / GT, ty1 = (s.Y1 - 1) / GT;
+		for (int ty = ty0; ty <= ty1; ++ty)
+			for (int tx = tx0; tx <= tx1; ++tx) {
+				int tile = ty * fp.ntx + tx;
+				unsigned slot = atomicAdd(cursor + tile, 1u);
+				items[bin_start[tile] + slot] = r;
+			}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ per-tile raster + shade + resolve
+struct TileIn {
+	unsigned long long* vis;
+	unsigned* tile_touched;
+	unsigned* tile_cursor;          // == tile_count, reset here for the next draw
+	const unsigned* bin_start;
+	const unsigned* items;
+	const TriRecord* records;
+	const unsigned* n_records;
+	const DrawStatus* status;
+	const float4* sv;
+	unsigned* color;                // BGRA8 as packed words (B | G<<8 | R<<16 | A<<24), full-frame pitch W
+	float* depth;
+};
+
+__device__ __forceinline__ unsigned pack_bgra(v4 c) {
+	// reference src/tiled_pipeline.cpp:579-582 (truncating float->u8 of clamp*255) + the R<->B swizzle of mergeTileResults :1171-1174
+	unsigned r = (unsigned)(unsigned char)cvtt(clampf(c.x, 0.0f, 1.0f) * 255.0f);
+	unsigned g = (unsigned)(unsigned char)cvtt(clampf(c.y, 0.0f, 1.0f) * 255.0f);
+	unsigned b = (unsigned)(unsigned char)cvtt(clampf(c.z, 0.0f, 1.0f) * 255.0f);
+	unsigned a = (unsigned)(unsigned char)cvtt(clampf(c.w, 0.0f, 1.0f) * 255.0f);
+	return b | (g << 8) | (r << 16) | (a << 24);
+}
+
+__device__ __forceinline__ const Material& face_material(const MeshView& mesh, unsigned face) {
+	int g = 0;
+	if (mesh.n_groups > 1) {
+		while (g + 1 < mesh.n_groups && (unsigned long long)face >= mesh.group_first[g + 1]) ++g;
+	}
+	return mesh.materials[g];
+}
+
+struct ShadeVerts { v3 pos[3], n[3], t[3], b[3]; float uv[3][2]; float sx[3], sy[3], z[3]; };
+
+// Re-derive sub-triangle `sub` of a clipped face with full attributes (reference src/pipeline.cpp:176-272)
+__device__ __noinline__ bool reclip_face(const MeshView& mesh, const m4& mvp, const unsigned vi[3], int sub, float fW, float fH,
+                                         ShadeVerts& sv) {
+	ClipFull a[MAX_CLIPPED_VERTS], b[MAX_CLIPPED_VERTS];
+	for (int k = 0; k < 3; ++k) {
+		float4 p = __ldg(mesh.pos + vi[k]);
+		const VAttr at = mesh.attr[vi[k]];
+		a[k].pos = V3(p.x, p.y, p.z);
+		a[k].clip = mul(mvp, V4(p.x, p.y, p.z, 1.0f));
+		a[k].uv[0] = at.uv[0]; a[k].uv[1] = at.uv[1];
+		a[k].n = V3(at.n[0], at.n[1], at.n[2]);
+		a[k].t = V3(at.t[0], at.t[1], at.t[2]);
+		a[k].b = V3(at.b[0], at.b[1], at.b[2]);
+	}
+	ClipFull* out;
+	int n = clip_triangle(a, b, &out);
+	if (sub * 3 + 2 >= n) return false;
+	for (int k = 0; k < 3; ++k) {
+		const ClipFull& c = out[sub * 3 + k];
+		sv.pos[k] = c.pos; sv.n[k] = c.n; sv.t[k] = c.t; sv.b[k] = c.b;
+		sv.uv[k][0] = c.uv[0]; sv.uv[k][1] = c.uv[1];
+		to_screen(c.clip, fW, fH, sv.sx[k], sv.sy[k], sv.z[k]);
+	}
+	return true;
+}
+
+template <typename Shader>
+__device__ __forceinline__ void shade_pixel(const MeshView& mesh, const Uniforms& u, const FrameParams& fp, const TileIn& in,
+                                            unsigned ordinal, int px, int py) {
+	const unsigned face = ordinal >> 3;
+	unsigned vi[3];
+	vi[0] = __ldg(mesh.idx + (size_t)face * 3);
+	vi[1] = __ldg(mesh.idx + (size_t)face * 3 + 1);
+	vi[2] = __ldg(mesh.idx + (size_t)face * 3 + 2);
+	float4 s0 = __ldg(in.sv + vi[0]), s1 = __ldg(in.sv + vi[1]), s2 = __ldg(in.sv + vi[2]);
+	const unsigned code = __float_as_uint(s0.w) | __float_as_uint(s1.w) | __float_as_uint(s2.w);
+	ShadeVerts q;
+	if (code == 0) {
+		q.sx[0] = s0.x; q.sy[0] = s0.y; q.z[0] = s0.z;
+		q.sx[1] = s1.x; q.sy[1] = s1.y; q.z[1] = s1.z;
+		q.sx[2] = s2.x; q.sy[2] = s2.y; q.z[2] = s2.z;
+	} else {
+		if (!reclip_face(mesh, u.mvp, vi, (int)(ordinal & 7u), (float)fp.W, (float)fp.H, q)) return;
+	}
+	Setup s;
+	if (!setup_triangle(q.sx[0], q.sy[0], q.sx[1], q.sy[1], q.sx[2], q.sy[2], q.z[0], q.z[1], q.z[2], fp.W, fp.y_lo, fp.y_hi, s)) return;
+	float c0, c1, c2, al, be, ga;
+	coverage(s, px, py, c0, c1, c2);
+	const float z = interp_z(s, c0, c1, c2, al, be, ga);
+	const size_t gi = (size_t)py * fp.W + px;
+	// mergeTileResults: strict tileZ < fbZ (reference src/tiled_pipeline.cpp:1148-1156)
+	if (!(z < in.depth[gi])) return;
+	typename Shader::VsOut vs[3];
+	if (code == 0) {
+#pragma unroll
+		for (int k = 0; k < 3; ++k) {
+			float4 p = __ldg(mesh.pos + vi[k]);
+			const float4* ap = reinterpret_cast<const float4*>(mesh.attr + vi[k]);
+			float4 a0 = __ldg(ap), a1 = __ldg(ap + 1), a2 = __ldg(ap + 2);
+			float uv[2] = {a0.x, a0.y};
+			Shader::vertex(u, V3(p.x, p.y, p.z), V3(a0.z, a0.w, a1.x), V3(a1.y, a1.z, a1.w), V3(a2.x, a2.y, a2.z), uv, vs[k]);
+		}
+	} else {
+		for (int k = 0; k < 3; ++k) Shader::vertex(u, q.pos[k], q.n[k], q.t[k], q.b[k], q.uv[k], vs[k]);
+	}
+	v4 col;
+	if (Shader::fragment(u, face_material(mesh, face), al, be, ga, vs, col)) return;  // true = discard (none of the shipped shaders does)
+	in.depth[gi] = z;
+	in.color[gi] = pack_bgra(col);
+}
+
+template <typename Shader>
+__global__ void __launch_bounds__(TILE_THREADS) k_tile_shade(MeshView mesh, Uniforms u, FrameParams fp, TileIn in) {
+	__shared__ unsigned long long s_keys[GT_PIX];
+	if (in.status->overflow) return;  // the host grows the bins and re-issues the draw
+	const int tx = blockIdx.x, ty = fp.ty_lo + blockIdx.y;
+	const int tile = ty * fp.ntx + tx;
+	const int x0 = tx * GT, y0 = ty * GT;
+	const unsigned touched = in.tile_touched[tile];
+	const unsigned nrec = *in.n_records;
+	const unsigned b0 = nrec ? in.bin_start[tile] : 0u, b1 = nrec ? in.bin_start[tile + 1] : 0u;
+	if (!touched && b0 == b1) return;
+	const int tid = threadIdx.x;
+	// 1. stage the tile's visibility keys in shared memory (and hand the global buffer back empty for the next draw)
+	for (int p = tid; p < GT_PIX; p += TILE_THREADS) {
+		int px = x0 + (p & (GT - 1)), py = y0 + (p / GT);
+		unsigned long long k = KEY_EMPTY;
+		if (touched && px < fp.W && py >= fp.y_lo && py < fp.y_hi) {
+			unsigned long long* g = in.vis + (size_t)py * fp.W + px;
+			k = *g;
+			if (k != KEY_EMPTY) *g = KEY_EMPTY;
+		}
+		s_keys[p] = k;
+	}
+	__syncthreads();
+	if (tid == 0) { in.tile_touched[tile] = 0u; in.tile_cursor[tile] = 0u; }
+	// 2. binned triangles: one warp per record, 8x4 pixel blocks per step, shared-memory atomicMin
+	if (b1 > b0) {
+		const int warp = tid >> 5, lane = tid & 31;
+		const int lx = lane & 7, ly = lane >> 3;
+		const int yb0 = max(y0, fp.y_lo), yb1 = min(min(y0 + GT, fp.H), fp.y_hi);
+		for (unsigned r = b0 + warp; r < b1; r += TILE_THREADS / 32) {
+			const TriRecord t = in.records[in.items[r]];
+			Setup s;
+			if (!setup_triangle(t.x0, t.y0, t.x1, t.y1, t.x2, t.y2, t.z0, t.z1, t.z2, fp.W, fp.y_lo, fp.y_hi, s)) continue;
+			const int bx0 = max(s.X0, x0), bx1 = min(s.X1, x0 + GT), by0 = max(s.Y0, yb0), by1 = min(s.Y1, yb1);
+			for (int py0 = by0; py0 < by1; py0 += 4)
+				for (int px0 = bx0; px0 < bx1; px0 += 8) {
+					int px = px0 + lx, py = py0 + ly;
+					if (px >= bx1 || py >= by1) continue;
+					float c0, c1, c2, al, be, ga;
+					if (!coverage(s, px, py, c0, c1, c2)) continue;
+					float z = interp_z(s, c0, c1, c2, al, be, ga);
+					if (!z_draws(z)) continue;
+					atomicMin(&s_keys[(py - y0) * GT + (px - x0)], make_key(z, t.ordinal));
+				}
+		}
+		__syncthreads();
+	}
+	// 3. deferred shading of the visible triangle of each pixel + framebuffer resolve (one warp = one 128 B row segment)
+	for (int p = tid; p < GT_PIX; p += TILE_THREADS) {
+		unsigned long long k = s_keys[p];
+		if (k == KEY_EMPTY) continue;
+		shade_pixel<Shader>(mesh, u, fp, in, (unsigned)(k & 0xFFFFFFFFull), x0 + (p & (GT - 1)), y0 + (p / GT));
+	}
+}
+
+}  // namespace axr

@@ -1,0 +1,155 @@
+/* axr_b200 — C ABI of the B200-native tiled rasterisation path (libaxr_b200.so).
+ *
+ * This is the drop-in boundary for AxiomR's hot path, AR::TiledPipeline::drawMesh
+ * (reference src/tiled_pipeline.cpp:143-322) behind AR::Pipeline / AR::IShader
+ * (reference include/pipeline.hpp:18-27, include/IShader.hpp:30-46). The reference has no FFI of
+ * its own (static C++ linkage); each entry point below names the reference interface it replaces.
+ * The C++ adapter that keeps the reference's class names on top of this ABI lives in
+ * axiomr_b200/host/, the binding a maintainer adds is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types; no exceptions cross the boundary.
+ *   - return 0 (AXR_OK) on success, negative axr_status on error; axr_last_error() has the text.
+ *   - matrices are float[16] column-major exactly as glm::mat4 stores them (m[col*4+row]).
+ *   - host buffers passed in are copied before the call returns (caller keeps ownership).
+ *   - one context is used by one host thread at a time (the reference's drawMesh is not re-entrant either).
+ *   - there is NO CPU fallback: every call needs a CUDA device (sm_100a); axr_create fails otherwise.
+ *   - work is enqueued on the context's CUDA stream; axr_sync / axr_resolve are the synchronisation points.
+ */
+#ifndef AXR_B200_H
+#define AXR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AXR_ABI_VERSION 1
+
+typedef enum axr_status {
+	AXR_OK = 0,
+	AXR_ERR_INVALID = -1,     /* bad argument / handle (reference: silent return, src/tiled_pipeline.cpp:146) */
+	AXR_ERR_CUDA = -2,        /* CUDA runtime error, text in axr_last_error */
+	AXR_ERR_NO_DEVICE = -3,   /* no sm_100 device: there is no CPU path */
+	AXR_ERR_CAPACITY = -4,    /* mesh too large for 32-bit ordinals (reference: std::bad_alloc from the 16 MB arena, include/tiled_pipeline.hpp:98-104) */
+	AXR_ERR_MATERIAL = -5,    /* shader needs a texture the material lacks (reference: null unique_ptr deref, include/shaders/shaders.hpp:178,210) */
+	AXR_ERR_UNSUPPORTED = -6  /* unknown shader kind (reference: any IShader subclass; device functors exist for the shipped ones) */
+} axr_status;
+
+/* IShader implementations with a device functor (reference include/shaders/shaders.hpp:19-58, 136-250, 252-423). */
+typedef enum axr_shader_kind { AXR_SHADER_FLAT = 0, AXR_SHADER_PHONG = 1, AXR_SHADER_PBR = 2 } axr_shader_kind;
+
+/* Texture::sample mode. NEAREST is the reference (include/texture.hpp:12-34). BILINEAR is an extension
+ * (BASELINE.json config 3) with no reference counterpart; it is checked against oracle/axr_oracle.c only. */
+typedef enum axr_sampler { AXR_SAMPLER_NEAREST = 0, AXR_SAMPLER_BILINEAR = 1 } axr_sampler;
+
+/* Public shader parameters (FlatShader::lightDirection; PhongShader/PBRShader::lightDirection, lightColor). */
+typedef struct axr_shader_params {
+	float light_dir[3];
+	float light_color[3];
+} axr_shader_params;
+
+typedef struct axr_config {
+	int device;            /* CUDA device ordinal */
+	int width, height;     /* Framebuffer(width, height, useDepth=true), reference include/framebuffer.hpp:12 */
+	int sampler;           /* axr_sampler */
+	/* Multi-GPU screen-space band owned by this context: pixel rows [band_y0, band_y1). 0,0 = whole frame.
+	 * Rows outside the band are never rasterised, shaded or written. band_y0 must be a multiple of 16
+	 * (the reference tile size, include/tiled_pipeline.hpp:28) so per-pixel results do not depend on the split. */
+	int band_y0, band_y1;
+	void* stream;          /* optional cudaStream_t to enqueue on (e.g. the caller's timing stream); NULL = own stream */
+	uint64_t reserved[4];  /* must be zero */
+} axr_config;
+
+typedef struct axr_ctx axr_ctx;
+typedef int32_t axr_mesh;  /* handles are small non-negative integers */
+typedef int32_t axr_tex;
+#define AXR_NO_TEXTURE (-1)
+
+/* MaterialGroup {materialName, startIndex, faceCount} (reference include/mesh.hpp:35-39) without the name. */
+typedef struct axr_group {
+	uint64_t first_face;
+	uint64_t face_count;
+} axr_group;
+
+/* Counters of the most recent draw (diagnostics / tests / bench launch accounting). */
+typedef struct axr_stats {
+	uint64_t faces;            /* input faces */
+	uint64_t clipped_faces;    /* faces that took the clip slow path (some vertex outside some plane) */
+	uint64_t triangles;        /* post-clip, front-facing triangles (|m_Triangles| in the reference) */
+	uint64_t small_triangles;  /* rasterised directly by the setup kernel */
+	uint64_t binned_triangles; /* setup records sent through tile bins */
+	uint64_t bin_refs;         /* (triangle, tile) references written */
+	uint64_t kernel_launches;  /* CUDA kernels launched by this draw */
+	uint64_t redo;             /* 1 if the draw was re-issued after growing bin capacity */
+} axr_stats;
+
+/* ---- lifetime: replaces `new Framebuffer(w,h,true)` + `new TiledPipeline(threads, camera, fb)`
+ *      (reference src/renderer.cpp:66-71). The thread-count argument has no meaning on the GPU. */
+int axr_create(const axr_config* cfg, axr_ctx** out);
+void axr_destroy(axr_ctx* ctx);
+const char* axr_last_error(const axr_ctx* ctx);  /* ctx may be NULL: error of the last failed axr_create */
+int axr_abi_version(void);
+
+/* ---- scene data: replaces Mesh::getVertices()/getFaces()/getMaterialGroups()/getMaterial() consumption
+ *      (reference src/tiled_pipeline.cpp:157-159,176-179) and Texture(path) data (reference src/texture.cpp:21-36).
+ *      vertices: n_verts x 14 f32 in AR::Vertex layout (reference include/mesh.hpp:9-18), 56-byte stride.
+ *      indices: 3 u32 per face (reference asserts triangles, src/tiled_pipeline.cpp:202).
+ *      groups may be NULL: one group covering every face. */
+int axr_upload_mesh(axr_ctx* ctx, const float* vertices, uint64_t n_verts, const uint32_t* indices,
+                    uint64_t n_faces, const axr_group* groups, uint32_t n_groups, axr_mesh* out);
+int axr_free_mesh(axr_ctx* ctx, axr_mesh mesh);
+/* rgba: w*h*4 bytes, row 0 = image top — what stbi_load(..., STBI_rgb_alpha) returns. */
+int axr_upload_texture(axr_ctx* ctx, const uint8_t* rgba, int w, int h, axr_tex* out);
+int axr_free_texture(axr_ctx* ctx, axr_tex tex);
+/* Material of one group: diffuse/bump/metallic/roughness/ao textures + specularExponent ("Ns")
+ * (reference include/mesh.hpp:20-34). Pass AXR_NO_TEXTURE for absent maps. */
+int axr_set_material(axr_ctx* ctx, axr_mesh mesh, uint32_t group, axr_tex diffuse, axr_tex bump, axr_tex metallic,
+                     axr_tex roughness, axr_tex ao, float specular_exponent);
+
+/* ---- per-frame state: replaces Pipeline::setCamera / the uniform writes at src/tiled_pipeline.cpp:148-155.
+ *      view_proj = Camera::getViewProjectionMatrix(), viewport = Camera::getViewportMatrix() (carried, unused by
+ *      the shipped shaders), cam_pos = Camera::getPosition(). mvp = view_proj * model is formed per draw in glm order. */
+int axr_set_uniforms(axr_ctx* ctx, const float view_proj[16], const float viewport[16], const float cam_pos[3]);
+/* replaces Pipeline::setShader(IShader*) (reference src/pipeline.cpp:22-24); params = the shader's public fields. */
+int axr_set_shader(axr_ctx* ctx, int kind, const axr_shader_params* params, size_t params_size);
+int axr_set_sampler(axr_ctx* ctx, int sampler);
+
+/* ---- framebuffer: replaces Framebuffer::clearColor / clearDepth (reference src/framebuffer.cpp:26-42) and the raw
+ *      getColorData()/getDepthData() accessors (reference include/framebuffer.hpp:45-48). Colour bytes are B,G,R,A;
+ *      row 0 is the bottom of the image (y up), depth is f32 NDC z with +inf = empty. */
+int axr_clear(axr_ctx* ctx, uint32_t packed_argb, float depth);
+int axr_upload_framebuffer(axr_ctx* ctx, const uint8_t* bgra, const float* depth);
+/* Device -> host copy of the whole frame (or this context's band rows only, at their place in the full image),
+ * synchronous: on return the draw(s) are complete, like the reference's drawMesh. NULL pointers are skipped. */
+int axr_resolve(axr_ctx* ctx, uint8_t* bgra_out, float* depth_out);
+
+/* ---- the hot path: replaces TiledPipeline::drawMesh(const glm::mat4& model, const Mesh&)
+ *      (reference src/tiled_pipeline.cpp:143-322). Composites onto the current framebuffer contents with the
+ *      reference's strict depth test; never clears. Asynchronous on the context stream. */
+int axr_draw_mesh(axr_ctx* ctx, axr_mesh mesh, const float model[16]);
+int axr_sync(axr_ctx* ctx);
+int axr_get_stats(axr_ctx* ctx, axr_stats* out);
+
+/* ---- pinned host memory for framebuffers / staging (cudaHostAlloc): makes axr_upload_framebuffer / axr_resolve
+ *      run at full PCIe rate. Plain malloc'ed memory works too, just slower. */
+void* axr_host_alloc(size_t bytes);
+void axr_host_free(void* p);
+
+/* ---- interop for callers that keep data on the device (bench timing, NCCL / peer composite) */
+void* axr_stream(axr_ctx* ctx);                                          /* cudaStream_t */
+int axr_framebuffer_device(axr_ctx* ctx, void** bgra_dev, void** depth_dev);  /* full-frame device pointers (W*H*4, W*H*4 bytes) */
+/* Redirect this context's band output into another allocation laid out as a full frame (e.g. GPU 0's framebuffer
+ * mapped through CUDA IPC / peer access): the resolve stores then go straight over NVLink. NULL restores the own buffers. */
+int axr_set_output(axr_ctx* ctx, void* bgra_dev, void* depth_dev);
+/* CUDA IPC handles (64 bytes each) of the own framebuffer allocations, for one-process-per-GPU compositing. */
+int axr_framebuffer_ipc(axr_ctx* ctx, void* color_handle64, void* depth_handle64);
+int axr_open_ipc(axr_ctx* ctx, const void* handle64, void** dev_ptr_out);
+int axr_close_ipc(axr_ctx* ctx, void* dev_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AXR_B200_H */
