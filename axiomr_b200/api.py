@@ -74,8 +74,9 @@ ABI_SYMBOLS = [
     "axr_upload_texture", "axr_free_texture", "axr_set_material", "axr_set_uniforms", "axr_set_shader", "axr_set_sampler",
     "axr_clear", "axr_upload_framebuffer", "axr_resolve", "axr_draw_mesh", "axr_sync", "axr_get_stats", "axr_host_alloc",
     "axr_host_free", "axr_stream", "axr_framebuffer_device", "axr_set_output", "axr_framebuffer_ipc", "axr_open_ipc",
-    "axr_close_ipc",
+    "axr_close_ipc", "axr_set_profiling", "axr_get_kernel_times",
 ]
+STAGES = ["vertex_xform", "setup_raster", "scan_tiles", "bin_scatter", "tile_shade"]
 
 _lib = None
 
@@ -120,6 +121,8 @@ def load_library():
     lib.axr_framebuffer_ipc.argtypes = [vp, C.c_void_p, C.c_void_p]
     lib.axr_open_ipc.argtypes = [vp, C.c_void_p, C.POINTER(vp)]
     lib.axr_close_ipc.argtypes = [vp, vp]
+    lib.axr_set_profiling.argtypes = [vp, C.c_int]
+    lib.axr_get_kernel_times.argtypes = [vp, _f32p, C.POINTER(C.c_uint64)]
     _lib = lib
     return lib
 
@@ -240,6 +243,16 @@ class Device:
         s = Stats()
         self._check(self.lib.axr_get_stats(self.h, C.byref(s)))
         return s.as_dict()
+
+    def set_profiling(self, enabled: bool):
+        self._check(self.lib.axr_set_profiling(self.h, 1 if enabled else 0))
+
+    def kernel_times(self):
+        """(dict stage -> accumulated ms, draws) since profiling was enabled / last read."""
+        ms = (C.c_float * len(STAGES))()
+        n = C.c_uint64(0)
+        self._check(self.lib.axr_get_kernel_times(self.h, ms, C.byref(n)))
+        return {k: float(ms[i]) for i, k in enumerate(STAGES)}, int(n.value)
 
     # --- interop
     @property

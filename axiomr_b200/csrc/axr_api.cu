@@ -85,6 +85,11 @@ struct axr_ctx {
 	PendingDraw pending;
 	axr_stats stats{};
 
+	// optional per-kernel timing
+	bool profiling = false;
+	std::vector<cudaEvent_t> prof_events;  // (AXR_NUM_STAGES + 1) per profiled draw
+	std::vector<cudaEvent_t> prof_pool;
+
 	std::vector<DeviceMesh> meshes;
 	std::vector<DeviceTexture> textures;
 	std::vector<void*> ipc_opened;
@@ -181,6 +186,16 @@ int check_pending(axr_ctx* ctx) {
 	return check_pending(ctx);
 }
 
+cudaEvent_t prof_mark(axr_ctx* ctx) {
+	if (!ctx->profiling) return nullptr;
+	cudaEvent_t e = nullptr;
+	if (!ctx->prof_pool.empty()) { e = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
+	else if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+	cudaEventRecord(e, ctx->stream);
+	ctx->prof_events.push_back(e);
+	return e;
+}
+
 template <typename Shader>
 void launch_tile(axr_ctx* ctx, const MeshView& mv, const Uniforms& u, const TileIn& in) {
 	dim3 grid(ctx->fp.ntx, ctx->fp.ty_hi - ctx->fp.ty_lo);
@@ -221,10 +236,12 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model) {
 	uint64_t launches = 0;
 	CU(cudaMemsetAsync(ctx->d_status, 0, sizeof(DrawStatus), s));
 	CU(cudaMemsetAsync(ctx->n_records, 0, sizeof(unsigned), s));
+	prof_mark(ctx);
 	if (m.n_verts) {
 		k_vertex_xform<<<(unsigned)((m.n_verts + 255) / 256), 256, 0, s>>>(m.pos, m.n_verts, u.mvp, (float)ctx->fp.W, (float)ctx->fp.H, m.sv);
 		++launches;
 	}
+	prof_mark(ctx);
 	SetupOut so;
 	so.vis = ctx->vis; so.tile_touched = ctx->tile_touched; so.tile_count = ctx->tile_count;
 	so.records = ctx->records; so.rec_cap = ctx->rec_cap; so.n_records = ctx->n_records; so.status = ctx->d_status;
@@ -232,12 +249,15 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model) {
 		k_setup_raster<<<(unsigned)((m.n_faces + 255) / 256), 256, 0, s>>>(mv, m.sv, u.mvp, ctx->fp, so);
 		++launches;
 	}
+	prof_mark(ctx);
 	k_scan_tiles<<<1, 1024, 0, s>>>(ctx->tile_count, ctx->bin_start, n_tiles(ctx), ctx->ref_cap, ctx->n_records, ctx->rec_cap, ctx->d_status);
 	++launches;
+	prof_mark(ctx);
 	CU(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(DrawStatus), cudaMemcpyDeviceToHost, s));
 	CU(cudaEventRecord(ctx->status_event, s));
 	k_bin_scatter<<<148 * 4, 256, 0, s>>>(ctx->records, ctx->n_records, ctx->fp, ctx->bin_start, ctx->tile_count, ctx->items, ctx->d_status);
 	++launches;
+	prof_mark(ctx);
 	TileIn in;
 	in.vis = ctx->vis; in.tile_touched = ctx->tile_touched; in.tile_cursor = ctx->tile_count; in.bin_start = ctx->bin_start;
 	in.items = ctx->items; in.records = ctx->records; in.n_records = ctx->n_records; in.status = ctx->d_status; in.sv = m.sv;
@@ -249,6 +269,7 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model) {
 	default: return fail(ctx, AXR_ERR_UNSUPPORTED, "unknown shader kind %d", ctx->shader_kind);
 	}
 	++launches;
+	prof_mark(ctx);
 	CU(cudaGetLastError());
 	ctx->stats.faces = m.n_faces;
 	ctx->stats.kernel_launches = launches;
@@ -352,6 +373,8 @@ void axr_destroy(axr_ctx* ctx) {
 	cudaFree(ctx->bin_start); cudaFree(ctx->items); cudaFree(ctx->records); cudaFree(ctx->n_records); cudaFree(ctx->d_status);
 	if (ctx->h_status) cudaFreeHost(ctx->h_status);
 	if (ctx->status_event) cudaEventDestroy(ctx->status_event);
+	for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+	for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
 	if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -564,6 +587,37 @@ int axr_get_stats(axr_ctx* ctx, axr_stats* out) {
 	int rc = check_pending(ctx);
 	if (rc) return rc;
 	*out = ctx->stats;
+	return AXR_OK;
+}
+
+int axr_set_profiling(axr_ctx* ctx, int enabled) {
+	if (!ctx) return AXR_ERR_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaStreamSynchronize(ctx->stream));
+	for (cudaEvent_t e : ctx->prof_events) ctx->prof_pool.push_back(e);
+	ctx->prof_events.clear();
+	ctx->profiling = enabled != 0;
+	return AXR_OK;
+}
+
+int axr_get_kernel_times(axr_ctx* ctx, float ms_out[AXR_NUM_STAGES], uint64_t* draws_out) {
+	if (!ctx || !ms_out) return AXR_ERR_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	int rc = check_pending(ctx);
+	if (rc) return rc;
+	CU(cudaStreamSynchronize(ctx->stream));
+	const size_t per = AXR_NUM_STAGES + 1;
+	const size_t draws = ctx->prof_events.size() / per;
+	for (int k = 0; k < AXR_NUM_STAGES; ++k) ms_out[k] = 0.f;
+	for (size_t d = 0; d < draws; ++d)
+		for (int k = 0; k < AXR_NUM_STAGES; ++k) {
+			float ms = 0.f;
+			CU(cudaEventElapsedTime(&ms, ctx->prof_events[d * per + k], ctx->prof_events[d * per + k + 1]));
+			ms_out[k] += ms;
+		}
+	for (cudaEvent_t e : ctx->prof_events) ctx->prof_pool.push_back(e);
+	ctx->prof_events.clear();
+	if (draws_out) *draws_out = draws;
 	return AXR_OK;
 }
 

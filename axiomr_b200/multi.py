@@ -1,0 +1,112 @@
+"""Multi-GPU sharding of the raster path: one process per GPU (torch.distributed / NCCL for the plumbing).
+
+Rendering shards without any data-path collective in two ways:
+  * views : every rank renders its own camera view of the replicated scene (weak scaling);
+  * bands : every rank owns a contiguous range of 16-px tile rows of ONE frame, runs the geometry stages over the
+            replicated mesh and rasterises / shades only its rows (strong scaling, Amdahl-limited by the geometry stages).
+The single exchange step is the composite to GPU 0 — a gather of disjoint regions, no reduction:
+  * NCCL grouped send/recv straight out of / into the framebuffer allocations (`Compositor`, mode "nccl"), or
+  * fused: the resolve stores of every rank go directly into GPU 0's framebuffer through a CUDA-IPC peer mapping
+    (`Compositor`, mode "peer"; bands only), so the transfer rides NVLink while the tile kernel is still shading.
+"""
+from __future__ import annotations
+
+REF_TILE = 16  # reference include/tiled_pipeline.hpp:28
+
+
+def band_rows(height: int, world: int):
+    """Split ceil(H/16) reference tile rows into `world` contiguous bands, as evenly as possible
+    (8K: 270 tile rows -> 34,34,34,34,34,34,33,33). Returns [(y0, y1)] in pixels; empty bands are not produced."""
+    rows = (height + REF_TILE - 1) // REF_TILE
+    world = max(1, min(world, rows))
+    base, extra = divmod(rows, world)
+    out, r = [], 0
+    for i in range(world):
+        n = base + (1 if i < extra else 0)
+        out.append((r * REF_TILE, min((r + n) * REF_TILE, height)))
+        r += n
+    return out
+
+
+def views_for_rank(rank: int, world: int, n_views: int):
+    """Round-robin-free contiguous assignment of n_views camera views to ranks."""
+    base, extra = divmod(n_views, world)
+    start = rank * base + min(rank, extra)
+    return list(range(start, start + base + (1 if rank < extra else 0)))
+
+
+class _DevArray:
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+def framebuffer_tensors(dev):
+    """Zero-copy torch views of a Device's framebuffer: (colour as int32 [H,W] = packed BGRA words, depth f32 [H,W])."""
+    import torch
+    c, d = dev.framebuffer_device()
+    dv = torch.device("cuda", torch.cuda.current_device())
+    color = torch.as_tensor(_DevArray(c, (dev.height, dev.width), "<i4"), device=dv)
+    depth = torch.as_tensor(_DevArray(d, (dev.height, dev.width), "<f4"), device=dv)
+    return color, depth
+
+
+class Compositor:
+    """Gathers every rank's finished region to GPU 0 after each frame (the path's one exchange step)."""
+
+    def __init__(self, dev, rank: int, world: int, mode: str, band, stream, transport: str = "nccl"):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.dev, self.rank, self.world, self.mode, self.stream = dev, rank, world, mode, stream
+        self.transport = transport
+        self.launches_per_step = 0
+        self.color, self.depth = framebuffer_tensors(dev)
+        self.slots = None
+        if mode == "views":
+            if rank == 0:  # slot r receives rank r's frame; slot 0 is rank 0's own framebuffer (no copy)
+                self.slots = (torch.empty((world - 1, dev.height, dev.width), dtype=torch.int32, device=self.color.device),
+                              torch.empty((world - 1, dev.height, dev.width), dtype=torch.float32, device=self.color.device))
+        else:
+            self.bands = band_rows(dev.height, world)
+            if transport == "peer":
+                self._setup_peer()
+
+    def _setup_peer(self):
+        """bands + peer: every rank r>0 maps GPU 0's framebuffer (CUDA IPC) and redirects its resolve stores there."""
+        dist = self.dist
+        handles = [None]
+        if self.rank == 0:
+            handles = [self.dev.framebuffer_ipc()]
+        dist.broadcast_object_list(handles, src=0)
+        if self.rank != 0:
+            ch, dh = handles[0]
+            self._peer = (self.dev.open_ipc(ch), self.dev.open_ipc(dh))
+            self.dev.set_output(*self._peer)
+
+    def composite(self):
+        torch, dist = self.torch, self.dist
+        if self.mode == "bands" and self.transport == "peer":
+            return  # the tile kernel already stored this rank's band into GPU 0's framebuffer over NVLink
+        with torch.cuda.stream(self.stream):
+            ops = []
+            if self.mode == "views":
+                if self.rank == 0:
+                    for r in range(1, self.world):
+                        ops.append(dist.P2POp(dist.irecv, self.slots[0][r - 1], r))
+                        ops.append(dist.P2POp(dist.irecv, self.slots[1][r - 1], r))
+                else:
+                    ops.append(dist.P2POp(dist.isend, self.color, 0))
+                    ops.append(dist.P2POp(dist.isend, self.depth, 0))
+            else:
+                if self.rank == 0:
+                    for r in range(1, len(self.bands)):
+                        y0, y1 = self.bands[r]
+                        ops.append(dist.P2POp(dist.irecv, self.color[y0:y1], r))
+                        ops.append(dist.P2POp(dist.irecv, self.depth[y0:y1], r))
+                elif self.rank < len(self.bands):
+                    y0, y1 = self.bands[self.rank]
+                    ops.append(dist.P2POp(dist.isend, self.color[y0:y1], 0))
+                    ops.append(dist.P2POp(dist.isend, self.depth[y0:y1], 0))
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()

@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the B200 tiled-raster path on BASELINE.json's headline workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c3n|c2|c4|c1|c5] [--mode views|bands]
+    python bench.py --impl reference ...      # the reference's own CPU path on the box's host cores
+
+A step is one frame: Framebuffer clear + TiledPipeline::drawMesh of the whole mesh (vertex stage, clip/cull/setup,
+binning, per-tile raster + shading, resolve), with mesh, textures and framebuffer already resident in HBM.
+Prints ONE JSON line (rank 0). See DESIGN.md §Measurement for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from axiomr_b200 import scenes as S  # noqa: E402
+
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def build_workload(name: str) -> S.Scene:
+    if name == "c3":      # BASELINE.json configs[2]: the configuration the headline metric is quoted on
+        return S.config3(sampler=S.SAMPLER_BILINEAR)
+    if name == "c3n":     # same scene, nearest sampling = the reference's own Texture::sample (parity mode)
+        return S.config3(sampler=S.SAMPLER_NEAREST)
+    if name == "c2":
+        return S.config2()
+    if name == "c4":
+        return S.config4()
+    if name == "c1":
+        return S.config1()
+    if name == "c5":      # C3 scene at 8K (bands mode)
+        return S.config3(w=7680, h=4320, sampler=S.SAMPLER_BILINEAR)
+    if name == "tiny":    # CI-sized stand-in
+        return S.config3(n=300, w=1280, h=720, tex=512, sampler=S.SAMPLER_BILINEAR)
+    raise SystemExit(f"unknown workload {name}")
+
+
+def workload_label(name: str, sc: S.Scene) -> str:
+    smp = "bilinear" if sc.sampler else "nearest"
+    shader = ["FlatShader", "PhongShader", "PBRShader"][sc.shader]
+    tex = f", {sc.textures[0].shape[0]}^2 diffuse+normal textures ({smp})" if sc.textures[0] is not None else ", no textures"
+    return f"{name}: {sc.n_faces} tris / {sc.n_verts} verts, {sc.width}x{sc.height}, {shader}{tex}"
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(sc: S.Scene, covered_px: int):
+    """B_alg = 12 T + 56 V + 12 W H + sum_tex min(4 taps P_cov, 4 Wt Ht), split by the stage that owns each term."""
+    taps = 4 if sc.sampler else 1
+    tex = 0
+    n_tex = {0: 0, 1: 2, 2: 5}[sc.shader]
+    for t in sc.textures[:n_tex] if n_tex else []:
+        if t is not None:
+            tex += min(4 * taps * covered_px, 4 * t.shape[0] * t.shape[1])
+    per_stage = {
+        "vertex_xform": 12 * sc.n_verts,                                        # positions
+        "setup_raster": 12 * sc.n_faces,                                        # 3 u32 indices per face
+        "tile_shade": 44 * sc.n_verts + 12 * sc.width * sc.height + tex,        # attributes + depth r/w + colour w + texels
+        "scan_tiles": 0, "bin_scatter": 0,
+    }
+    return sum(per_stage.values()), per_stage
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------- reference / CPU arm
+def cpu_reference_run(sc: S.Scene, seconds_budget: float, threads: int | None = None, steps: int = 1, warmup: int = 0,
+                      thread_sweep: bool = True):
+    """Times the reference's CPU implementation of the path (oracle/_ref = the unmodified sources; else the C port) on a
+    bounded, contiguous face sample of the workload. Returns (Mtri/s, info dict). bench.py is allowed to run oracle/ here only."""
+    from oracle import pyoracle as po
+    use_ref = po.ref_available()
+    cores = os.cpu_count() or 1
+    if threads is None:
+        threads = po.ref_hardware_concurrency() if po.ref_available() else cores
+    # the reference only has nearest sampling; its arm always runs Texture::sample as shipped
+    ref_scene = sc
+    if use_ref and sc.sampler != S.SAMPLER_NEAREST:
+        import copy
+        ref_scene = copy.copy(sc)
+        ref_scene.sampler = S.SAMPLER_NEAREST
+
+    def run(n_faces):
+        if use_ref:
+            _, _, secs = po.ref_render(ref_scene, threads=threads, chunk=30000, n_faces=n_faces)
+        else:
+            po.build(ref=False)
+            _, _, secs = po.oracle_render(sc, threads=threads, n_faces=n_faces)
+        return secs
+
+    # calibrate on a small prefix (also picks the thread count the reference runs fastest with on this box:
+    # its own default is hardware_concurrency, reference src/renderer.cpp:71), then size the sample for the budget
+    n_cal = min(sc.n_faces, 200_000)
+    if thread_sweep and use_ref:
+        best = None
+        for th in sorted({threads, 64, 32, 16, 8}):
+            if th > max(threads, 1):
+                continue
+            threads_try = th
+            t_try = None
+            try:
+                _, _, t_try = po.ref_render(ref_scene, threads=threads_try, chunk=30000, n_faces=n_cal)
+            except Exception:
+                continue
+            if best is None or t_try < best[1]:
+                best = (th, t_try)
+        if best:
+            threads = best[0]
+    t_cal = max(run(n_cal), 1e-6)
+    rate = n_cal / t_cal
+    n = int(min(sc.n_faces, max(n_cal, rate * seconds_budget)))
+    for _ in range(warmup):
+        run(n)
+    times = [run(n) for _ in range(max(1, steps))]
+    t = statistics.median(times)
+    info = {"kind": "reference" if use_ref else "port", "cores": threads, "host_cpus": cores,
+            "sample": f"first {n} of {sc.n_faces} faces of the workload drawn in face order in chunks of 30000 "
+                      f"(TiledPipeline arena limit), full {sc.width}x{sc.height} frame, median of {len(times)} run(s), "
+                      f"{t * 1e3:.1f} ms each" + ("; nearest sampling (the reference has no bilinear mode)" if use_ref and sc.sampler else ""),
+            "ms_per_sample": t * 1e3, "faces": n}
+    return n / t / 1e6, info
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sc = build_workload(args.workload)
+    budget = 8.0
+    v, info = cpu_reference_run(sc, budget, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "Mtri/s (input faces per second through TiledPipeline::drawMesh)", "value": v, "unit": "Mtri/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["ms_per_sample"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_label(args.workload, sc)},
+        "cpu_baseline": {"value": v, "unit": "Mtri/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
+        "e2e": {"value": v, "unit": "Mtri/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "frames_per_s_extrapolated": v * 1e6 / sc.n_faces,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- B200 arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3")
+    ap.add_argument("--mode", default="views", choices=["views", "bands"], help="multi-GPU sharding (N>1)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    from axiomr_b200 import api, multi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the raster path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist = None
+
+    sc = build_workload(args.workload)
+    W, H, T = sc.width, sc.height, sc.n_faces
+    band = None
+    if world > 1 and args.mode == "bands":
+        band = multi.band_rows(H, world)[rank]
+    elif world > 1:
+        sc.view_proj, sc.cam_pos = S.view_matrix_for(rank, max(world, 8), W, H)  # each rank its own camera of the replicated scene
+    dev = api.Device(W, H, device=local, sampler=sc.sampler, band=band)
+    mesh = dev.load_scene(sc)
+    stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local))
+    comp = multi.Compositor(dev, rank, world, args.mode, band, stream) if world > 1 else None
+
+    def step():
+        dev.clear(0xFF000000, float("inf"))
+        dev.draw_mesh(mesh, sc.model)
+        if comp:
+            comp.composite()
+
+    def barrier():
+        dev.sync()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    stats = dev.stats()
+    launches_per_step = int(stats["kernel_launches"]) + 1 + (comp.launches_per_step if comp else 0)
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    dev.set_profiling(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    ktimes, kdraws = dev.kernel_times()
+    dev.set_profiling(False)
+    clk = clocks.stop()
+    ms_step = ms_total / args.steps
+    if dist:
+        t = torch.tensor([ms_step], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item())
+
+    # covered pixels (for the texture term of the algorithmic bytes) — outside the timed region
+    _, depth = dev.resolve()
+    y0, y1 = dev.band
+    covered = int(np.isfinite(depth[y0:y1]).sum())
+
+    units = T * (world if (world > 1 and args.mode == "views") else 1)  # faces processed per step by the whole job
+    value = units / (ms_step * 1e-3) / 1e6
+
+    line = None
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        b_alg, per_stage = algorithmic_bytes(sc, covered)
+        kavg = {k: (v / max(kdraws, 1)) for k, v in ktimes.items()}
+        dom = max(kavg, key=lambda k: kavg[k])
+        dom_ms = kavg[dom]
+        ach = per_stage[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(args.workload, {}).get(dom)
+            except Exception:
+                traffic = None
+        draw_ms = sum(kavg.values())
+        line = {
+            "metric": "Mtri/s (input faces per second through TiledPipeline::drawMesh, 4K 10M-tri textured scene)",
+            "value": value, "unit": "Mtri/s", "frames_per_s": (units / T) / (ms_step * 1e-3),
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak" if args.mode == "views" else "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_label(args.workload, sc),
+                       "step": "axr_clear + axr_draw_mesh (5 kernels) on one stream, all inputs resident in HBM",
+                       "l2": "working set (mesh %.0f MB + textures + 8 B/px keys + framebuffer) exceeds the 126 MB L2; no explicit flush"
+                             % ((sc.vertices.nbytes + sc.indices.nbytes) / 1e6),
+                       "parallelism": ("1 GPU" if world == 1 else f"{args.mode} x{world}: " +
+                                       ("one camera view of the replicated scene per GPU, finished frames gathered to GPU 0 over NCCL"
+                                        if args.mode == "views" else
+                                        "16-px-aligned screen bands of one frame, replicated geometry stages, bands gathered to GPU 0 over NCCL")),
+                       "parity_mode": "nearest sampling == reference; bilinear is an extension checked against oracle/axr_oracle.c"},
+            "gpu_launches": launches_per_step * args.steps,
+            "kernel_ms": kavg, "draw_ms": draw_ms, "draw_stats": stats, "covered_pixels": covered,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": traffic, "algorithmic_bytes": per_stage[dom], "kernel_ms": dom_ms, "peak_source": peak_src},
+            "roofline_frame": {"bound": "hbm", "algorithmic_bytes": b_alg, "achieved": b_alg / (draw_ms * 1e-3) / 1e9,
+                               "peak": peak, "unit": "GB/s", "frac": b_alg / (draw_ms * 1e-3) / 1e9 / peak,
+                               "note": "BASELINE.md §4 figure of record: B_alg / sum of the five draw kernels' event times"},
+            "clocks": clk,
+        }
+
+    # ---- e2e: the reference-facing call (TiledPipeline.drawMesh on a HOST framebuffer) with H2D/D2H inside the timed region
+    if not args.no_e2e:
+        fb = api.Framebuffer(W, H, True)
+        cam = api.Camera()
+        cam.setViewport(0, 0, W, H)
+        cam.setViewProjectionMatrix(sc.view_proj)
+        cam._pos = np.asarray(sc.cam_pos, dtype=np.float32)
+        pipe = api.TiledPipeline(os.cpu_count() or 1, cam, fb, device=local, sampler=sc.sampler)
+        shader = [api.FlatShader(tuple(sc.light_dir)), api.PhongShader(tuple(sc.light_dir), tuple(sc.light_color)),
+                  api.PBRShader(tuple(sc.light_dir), tuple(sc.light_color))][sc.shader]
+        pipe.setShader(shader)
+        tex = [api.Texture(t) if t is not None else None for t in sc.textures]
+        mat = api.Material("m0", tex[0], tex[2], tex[1], tex[3], tex[4], sc.specular_exponent)
+        hmesh = api.Mesh(sc.vertices, sc.indices, {"m0": mat})
+        dev.close()  # free HBM held by the device-resident arm
+        n_e2e = max(3, min(args.steps, 10))
+
+        def e2e_step():
+            fb.clearColor(api.Color(0, 0, 0, 255))
+            fb.clearDepth()
+            pipe.drawMesh(sc.model, hmesh)
+
+        for _ in range(2):
+            e2e_step()  # first call uploads and caches the mesh (the reference reads its host Mesh on every call)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+        if dist:
+            t = torch.tensor([e2e_ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        if rank == 0:
+            line["e2e"] = {"value": units / (e2e_ms * 1e-3) / 1e6, "unit": "Mtri/s", "ms_per_step": e2e_ms, "steps": n_e2e,
+                           "h2d_bytes_per_step": int(pipe.last_h2d_bytes), "d2h_bytes_per_step": int(pipe.last_d2h_bytes),
+                           "call": "TiledPipeline.drawMesh(model, mesh) on a pinned host Framebuffer: host clear, H2D of colour+depth, "
+                                   "draw, D2H of colour+depth, complete on return; mesh/textures cached on the device after the first call",
+                           "mesh_upload_bytes_first_call": int(sc.vertices.nbytes + sc.indices.nbytes)}
+        pipe.device.close()
+    elif rank == 0:
+        line["e2e"] = None
+
+    # ---- CPU baseline (rank 0, N = 1 only): the reference's own thread-pool path on this box's host cores
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            v, info = cpu_reference_run(sc, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": v, "unit": "Mtri/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"],
+                                    "host_cpus": info["host_cpus"]}
+        except Exception as e:  # the checker being absent must not lose the GPU numbers
+            line["cpu_baseline"] = {"value": None, "unit": "Mtri/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -133,6 +133,14 @@ int axr_draw_mesh(axr_ctx* ctx, axr_mesh mesh, const float model[16]);
 int axr_sync(axr_ctx* ctx);
 int axr_get_stats(axr_ctx* ctx, axr_stats* out);
 
+/* ---- per-kernel device timing (CUDA events on the context stream, recorded around each kernel of every draw while
+ *      enabled). Stage order: 0 vertex_xform, 1 setup_raster, 2 scan_tiles, 3 bin_scatter, 4 tile_shade.
+ *      axr_get_kernel_times synchronises, returns the accumulated milliseconds per stage and the number of draws
+ *      accumulated, and resets the accumulators. */
+#define AXR_NUM_STAGES 5
+int axr_set_profiling(axr_ctx* ctx, int enabled);
+int axr_get_kernel_times(axr_ctx* ctx, float ms_out[AXR_NUM_STAGES], uint64_t* draws_out);
+
 /* ---- pinned host memory for framebuffers / staging (cudaHostAlloc): makes axr_upload_framebuffer / axr_resolve
  *      run at full PCIe rate. Plain malloc'ed memory works too, just slower. */
 void* axr_host_alloc(size_t bytes);
