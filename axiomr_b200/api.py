@@ -30,7 +30,7 @@ import numpy as np
 from . import scenes as _scenes
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libaxr_b200.so")
+LIB_PATH = os.environ.get("AXR_B200_LIB") or os.path.join(HERE, "libaxr_b200.so")  # AXR_B200_LIB: tuning variants
 
 SHADER_FLAT, SHADER_PHONG, SHADER_PBR = 0, 1, 2
 SAMPLER_NEAREST, SAMPLER_BILINEAR = 0, 1

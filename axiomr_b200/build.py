@@ -36,16 +36,19 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(d) <= t for d in DEPS if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and up_to_date():
-        return OUT
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    """defines/out: tuning variants (e.g. defines=["AXR_SETUP_FPT=2"], out=".../libaxr_b200_fpt2.so"), selected at run time with
+    the AXR_B200_LIB environment variable. The default build takes the constants in csrc/axr_kernels.cuh."""
+    out = out or OUT
+    if not force and not defines and up_to_date():
+        return out
+    cmd = [nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libaxr_b200.so")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

@@ -246,7 +246,8 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model) {
 	so.vis = ctx->vis; so.tile_touched = ctx->tile_touched; so.tile_count = ctx->tile_count;
 	so.records = ctx->records; so.rec_cap = ctx->rec_cap; so.n_records = ctx->n_records; so.status = ctx->d_status;
 	if (m.n_faces) {
-		k_setup_raster<<<(unsigned)((m.n_faces + 255) / 256), 256, 0, s>>>(mv, m.sv, u.mvp, ctx->fp, so);
+		const unsigned long long per_cta = (unsigned long long)SETUP_THREADS * SETUP_FPT;
+		k_setup_raster<<<(unsigned)((m.n_faces + per_cta - 1) / per_cta), SETUP_THREADS, 0, s>>>(mv, m.sv, u.mvp, ctx->fp, so);
 		++launches;
 	}
 	prof_mark(ctx);

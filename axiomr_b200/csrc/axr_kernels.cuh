@@ -36,7 +36,10 @@ struct DrawStatus {
 	unsigned long long bin_refs;                                                      // refs wanted
 	unsigned overflow;                                                                // 1: records, 2: refs
 	unsigned pad;
+	// per-CTA partial counters are spread over STAT_STRIPES slots (no single hot address); k_scan_tiles folds them
+	unsigned long long stripes[4][32];
 };
+constexpr int STAT_STRIPES = 32;
 
 struct FrameParams {
 	int W, H;
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(256) k_vertex_xform(const float4* __restrict__
 	v4 c = mul(mvp, V4(p.x, p.y, p.z, 1.0f));
 	float sx, sy, z;
 	to_screen(c, fW, fH, sx, sy, z);
-	sv[i] = make_float4(sx, sy, z, __uint_as_float(clip_code(c)));
+	sv[i] = make_float4(sx, sy, z, __uint_as_float(clip_code(c) | (clip_code_safe_out(c) << 8)));
 }
 
 // ------------------------------------------------------------------------------------------------ setup + small raster
@@ -127,11 +130,8 @@ __device__ __forceinline__ void emit_triangle(const FrameParams& fp, const Setup
 				float z = interp_z(s, c0, c1, c2, al, be, ga);
 				if (!z_draws(z)) continue;
 				unsigned long long key = make_key(z, ordinal);
-				unsigned long long* slot = o.vis + (size_t)py * fp.W + px;
-				if (key < *slot) {  // cheap pre-test; the atomic decides
-					atomicMin(slot, key);
-					o.tile_touched[(py / GT) * fp.ntx + (px / GT)] = 1u;
-				}
+				atomicMin(o.vis + (size_t)py * fp.W + px, key);  // result unused -> RED.MIN.64, fire and forget
+				o.tile_touched[(py / GT) * fp.ntx + (px / GT)] = 1u;
 			}
 		return;
 	}
@@ -171,27 +171,59 @@ __device__ __noinline__ void setup_clipped_face(const FrameParams& fp, const Set
 	}
 }
 
-__global__ void __launch_bounds__(256) k_setup_raster(MeshView mesh, const float4* __restrict__ sv, m4 mvp, FrameParams fp, SetupOut o) {
+constexpr int SETUP_THREADS = 256;
+#ifndef AXR_SETUP_FPT
+#define AXR_SETUP_FPT 1
+#endif
+#ifndef AXR_SETUP_MINB
+#define AXR_SETUP_MINB 6
+#endif
+#ifndef AXR_TILE_MINB
+#define AXR_TILE_MINB 4
+#endif
+constexpr int SETUP_FPT = AXR_SETUP_FPT;  // faces per thread: the index loads and the 16 B screen-record gathers of all of them are issued back to back
+
+__global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(const __grid_constant__ MeshView mesh, const float4* __restrict__ sv,
+                                                                const __grid_constant__ m4 mvp, const __grid_constant__ FrameParams fp,
+                                                                const __grid_constant__ SetupOut o) {
 	__shared__ unsigned s_cnt[4];
 	if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
-	__syncthreads();
-	unsigned long long f = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned long long base = (unsigned long long)blockIdx.x * (SETUP_THREADS * SETUP_FPT) + threadIdx.x;
+	unsigned vi[SETUP_FPT][3];
+	float4 s[SETUP_FPT][3];
+#pragma unroll
+	for (int k = 0; k < SETUP_FPT; ++k) {
+		const unsigned long long f = base + (unsigned long long)k * SETUP_THREADS;
+		if (f < mesh.n_faces) {
+			vi[k][0] = __ldg(mesh.idx + f * 3); vi[k][1] = __ldg(mesh.idx + f * 3 + 1); vi[k][2] = __ldg(mesh.idx + f * 3 + 2);
+		}
+	}
+#pragma unroll
+	for (int k = 0; k < SETUP_FPT; ++k) {
+		const unsigned long long f = base + (unsigned long long)k * SETUP_THREADS;
+		if (f < mesh.n_faces) { s[k][0] = __ldg(sv + vi[k][0]); s[k][1] = __ldg(sv + vi[k][1]); s[k][2] = __ldg(sv + vi[k][2]); }
+	}
 	EmitCounters cnt = {0, 0, 0};
 	unsigned clipped = 0;
-	if (f < mesh.n_faces) {
-		unsigned i0 = __ldg(mesh.idx + f * 3), i1 = __ldg(mesh.idx + f * 3 + 1), i2 = __ldg(mesh.idx + f * 3 + 2);
-		float4 s0 = __ldg(sv + i0), s1 = __ldg(sv + i1), s2 = __ldg(sv + i2);
-		unsigned code = __float_as_uint(s0.w) | __float_as_uint(s1.w) | __float_as_uint(s2.w);
-		if (code == 0) {
+#pragma unroll
+	for (int k = 0; k < SETUP_FPT; ++k) {
+		const unsigned long long f = base + (unsigned long long)k * SETUP_THREADS;
+		if (f >= mesh.n_faces) continue;
+		const float4 s0 = s[k][0], s1 = s[k][1], s2 = s[k][2];
+		const unsigned k0 = __float_as_uint(s0.w), k1 = __float_as_uint(s1.w), k2 = __float_as_uint(s2.w);
+		if (((k0 | k1 | k2) & 0x3fu) == 0) {
 			// every vertex inside every plane: clipTriangle returns the triangle unchanged (reference src/pipeline.cpp:322-325)
 			if (!is_backface(s0.x, s0.y, s1.x, s1.y, s2.x, s2.y))
 				emit_triangle(fp, o, s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, (unsigned)f * 8u, cnt);
+		} else if ((k0 & k1 & k2) >> 8) {
+			// all three vertices safely outside one plane: clipTriangle returns nothing (see clip_code_safe_out)
 		} else {
-			clipped = 1;
-			setup_clipped_face(fp, o, mvp, __ldg(mesh.pos + i0), __ldg(mesh.pos + i1), __ldg(mesh.pos + i2), (unsigned)f, cnt);
+			clipped++;
+			setup_clipped_face(fp, o, mvp, __ldg(mesh.pos + vi[k][0]), __ldg(mesh.pos + vi[k][1]), __ldg(mesh.pos + vi[k][2]), (unsigned)f, cnt);
 		}
 	}
-	// block-level counter reduction: one global atomic per counter per CTA
+	// counters: warp reduce -> shared -> one striped global add per counter per CTA
+	__syncthreads();
 	unsigned w0 = __reduce_add_sync(0xffffffffu, clipped), w1 = __reduce_add_sync(0xffffffffu, cnt.tris);
 	unsigned w2 = __reduce_add_sync(0xffffffffu, cnt.small), w3 = __reduce_add_sync(0xffffffffu, cnt.binned);
 	if ((threadIdx.x & 31) == 0) {
@@ -201,12 +233,8 @@ __global__ void __launch_bounds__(256) k_setup_raster(MeshView mesh, const float
 		if (w3) atomicAdd(&s_cnt[3], w3);
 	}
 	__syncthreads();
-	if (threadIdx.x == 0) {
-		if (s_cnt[0]) atomicAdd(&o.status->clipped_faces, (unsigned long long)s_cnt[0]);
-		if (s_cnt[1]) atomicAdd(&o.status->triangles, (unsigned long long)s_cnt[1]);
-		if (s_cnt[2]) atomicAdd(&o.status->small_triangles, (unsigned long long)s_cnt[2]);
-		if (s_cnt[3]) atomicAdd(&o.status->binned_triangles, (unsigned long long)s_cnt[3]);
-	}
+	if (threadIdx.x < 4 && s_cnt[threadIdx.x])
+		atomicAdd(&o.status->stripes[threadIdx.x][blockIdx.x % STAT_STRIPES], (unsigned long long)s_cnt[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------------ bins: scan + scatter
@@ -244,6 +272,11 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(unsigned* tile_count, unsig
 		__syncthreads();
 		if (tid == 1023) s_carry = carry + s_warp[31];
 		__syncthreads();
+	}
+	if (tid < 4) {
+		unsigned long long acc = 0;
+		for (int i = 0; i < STAT_STRIPES; ++i) acc += status->stripes[tid][i];
+		(&status->clipped_faces)[tid] = acc;
 	}
 	if (tid == 0) {
 		unsigned total = s_carry;
@@ -307,81 +340,97 @@ __device__ __forceinline__ const Material& face_material(const MeshView& mesh, u
 	return mesh.materials[g];
 }
 
-struct ShadeVerts { v3 pos[3], n[3], t[3], b[3]; float uv[3][2]; float sx[3], sy[3], z[3]; };
+// Accumulate one vertex's VertexOutput into the interpolated varyings: step k of ((v0*al) + (v1*be)) + v2*ga.
+template <typename Shader>
+__device__ __forceinline__ void accumulate_vertex(const Uniforms& u, int k, float w, v3 pos, v3 n, v3 t, v3 b, float uvx, float uvy, float* var) {
+	float o[Shader::NV];
+	Shader::vertex(u, pos, n, t, b, uvx, uvy, o);
+#pragma unroll
+	for (int i = 0; i < Shader::NV; ++i) var[i] = (k == 0) ? o[i] * w : var[i] + o[i] * w;
+}
 
-// Re-derive sub-triangle `sub` of a clipped face with full attributes (reference src/pipeline.cpp:176-272)
-__device__ __noinline__ bool reclip_face(const MeshView& mesh, const m4& mvp, const unsigned vi[3], int sub, float fW, float fH,
-                                         ShadeVerts& sv) {
+template <typename Shader>
+__device__ __forceinline__ void finish_pixel(const MeshView& mesh, const Uniforms& u, const TileIn& in, unsigned face, size_t gi, float z,
+                                             const float* var) {
+	v4 col;
+	if (Shader::fragment(u, face_material(mesh, face), var, col)) return;  // true = discard (none of the shipped shaders does)
+	in.depth[gi] = z;
+	in.color[gi] = pack_bgra(col);
+}
+
+// Pixel whose visible triangle comes from a clipped face: re-derive sub-triangle (ordinal & 7) with full attributes
+// (reference src/pipeline.cpp:176-272). Rare; kept out of line so its stack frame does not burden the common path.
+template <typename Shader>
+__device__ __noinline__ void shade_pixel_clipped(const MeshView& mesh, const Uniforms& u, const FrameParams& fp, const TileIn& in,
+                                                 unsigned ordinal, unsigned i0, unsigned i1, unsigned i2, int px, int py) {
 	ClipFull a[MAX_CLIPPED_VERTS], b[MAX_CLIPPED_VERTS];
+	const unsigned vi[3] = {i0, i1, i2};
 	for (int k = 0; k < 3; ++k) {
 		float4 p = __ldg(mesh.pos + vi[k]);
 		const VAttr at = mesh.attr[vi[k]];
 		a[k].pos = V3(p.x, p.y, p.z);
-		a[k].clip = mul(mvp, V4(p.x, p.y, p.z, 1.0f));
+		a[k].clip = mul(u.mvp, V4(p.x, p.y, p.z, 1.0f));
 		a[k].uv[0] = at.uv[0]; a[k].uv[1] = at.uv[1];
 		a[k].n = V3(at.n[0], at.n[1], at.n[2]);
 		a[k].t = V3(at.t[0], at.t[1], at.t[2]);
 		a[k].b = V3(at.b[0], at.b[1], at.b[2]);
 	}
 	ClipFull* out;
-	int n = clip_triangle(a, b, &out);
-	if (sub * 3 + 2 >= n) return false;
-	for (int k = 0; k < 3; ++k) {
-		const ClipFull& c = out[sub * 3 + k];
-		sv.pos[k] = c.pos; sv.n[k] = c.n; sv.t[k] = c.t; sv.b[k] = c.b;
-		sv.uv[k][0] = c.uv[0]; sv.uv[k][1] = c.uv[1];
-		to_screen(c.clip, fW, fH, sv.sx[k], sv.sy[k], sv.z[k]);
-	}
-	return true;
-}
-
-template <typename Shader>
-__device__ __forceinline__ void shade_pixel(const MeshView& mesh, const Uniforms& u, const FrameParams& fp, const TileIn& in,
-                                            unsigned ordinal, int px, int py) {
-	const unsigned face = ordinal >> 3;
-	unsigned vi[3];
-	vi[0] = __ldg(mesh.idx + (size_t)face * 3);
-	vi[1] = __ldg(mesh.idx + (size_t)face * 3 + 1);
-	vi[2] = __ldg(mesh.idx + (size_t)face * 3 + 2);
-	float4 s0 = __ldg(in.sv + vi[0]), s1 = __ldg(in.sv + vi[1]), s2 = __ldg(in.sv + vi[2]);
-	const unsigned code = __float_as_uint(s0.w) | __float_as_uint(s1.w) | __float_as_uint(s2.w);
-	ShadeVerts q;
-	if (code == 0) {
-		q.sx[0] = s0.x; q.sy[0] = s0.y; q.z[0] = s0.z;
-		q.sx[1] = s1.x; q.sy[1] = s1.y; q.z[1] = s1.z;
-		q.sx[2] = s2.x; q.sy[2] = s2.y; q.z[2] = s2.z;
-	} else {
-		if (!reclip_face(mesh, u.mvp, vi, (int)(ordinal & 7u), (float)fp.W, (float)fp.H, q)) return;
-	}
+	const int n = clip_triangle(a, b, &out);
+	const int sub = (int)(ordinal & 7u);
+	if (sub * 3 + 2 >= n) return;
+	const ClipFull* c = out + sub * 3;
+	float sx[3], sy[3], sz[3];
+	for (int k = 0; k < 3; ++k) to_screen(c[k].clip, (float)fp.W, (float)fp.H, sx[k], sy[k], sz[k]);
 	Setup s;
-	if (!setup_triangle(q.sx[0], q.sy[0], q.sx[1], q.sy[1], q.sx[2], q.sy[2], q.z[0], q.z[1], q.z[2], fp.W, fp.y_lo, fp.y_hi, s)) return;
+	if (!setup_triangle(sx[0], sy[0], sx[1], sy[1], sx[2], sy[2], sz[0], sz[1], sz[2], fp.W, fp.y_lo, fp.y_hi, s)) return;
 	float c0, c1, c2, al, be, ga;
 	coverage(s, px, py, c0, c1, c2);
 	const float z = interp_z(s, c0, c1, c2, al, be, ga);
 	const size_t gi = (size_t)py * fp.W + px;
-	// mergeTileResults: strict tileZ < fbZ (reference src/tiled_pipeline.cpp:1148-1156)
 	if (!(z < in.depth[gi])) return;
-	typename Shader::VsOut vs[3];
-	if (code == 0) {
-#pragma unroll
-		for (int k = 0; k < 3; ++k) {
-			float4 p = __ldg(mesh.pos + vi[k]);
-			const float4* ap = reinterpret_cast<const float4*>(mesh.attr + vi[k]);
-			float4 a0 = __ldg(ap), a1 = __ldg(ap + 1), a2 = __ldg(ap + 2);
-			float uv[2] = {a0.x, a0.y};
-			Shader::vertex(u, V3(p.x, p.y, p.z), V3(a0.z, a0.w, a1.x), V3(a1.y, a1.z, a1.w), V3(a2.x, a2.y, a2.z), uv, vs[k]);
-		}
-	} else {
-		for (int k = 0; k < 3; ++k) Shader::vertex(u, q.pos[k], q.n[k], q.t[k], q.b[k], q.uv[k], vs[k]);
+	float var[Shader::NV];
+	const float w[3] = {al, be, ga};
+	for (int k = 0; k < 3; ++k) accumulate_vertex<Shader>(u, k, w[k], c[k].pos, c[k].n, c[k].t, c[k].b, c[k].uv[0], c[k].uv[1], var);
+	finish_pixel<Shader>(mesh, u, in, ordinal >> 3, gi, z, var);
+}
+
+// One visible pixel: all gathers that depend only on the vertex indices are issued together (screen records, positions,
+// attributes, framebuffer depth), then setup -> barycentrics -> depth test -> IShader::vertex x3 -> IShader::fragment.
+template <typename Shader>
+__device__ __forceinline__ void shade_pixel(const MeshView& mesh, const Uniforms& u, const FrameParams& fp, const TileIn& in,
+                                            unsigned ordinal, unsigned i0, unsigned i1, unsigned i2, int px, int py) {
+	const size_t gi = (size_t)py * fp.W + px;
+	const float4 s0 = __ldg(in.sv + i0), s1 = __ldg(in.sv + i1), s2 = __ldg(in.sv + i2);
+	const float4 p0 = __ldg(mesh.pos + i0), p1 = __ldg(mesh.pos + i1), p2 = __ldg(mesh.pos + i2);
+	const float4* ap0 = reinterpret_cast<const float4*>(mesh.attr + i0);
+	const float4* ap1 = reinterpret_cast<const float4*>(mesh.attr + i1);
+	const float4* ap2 = reinterpret_cast<const float4*>(mesh.attr + i2);
+	const float4 a00 = __ldg(ap0), a01 = __ldg(ap0 + 1), a02 = __ldg(ap0 + 2);
+	const float4 a10 = __ldg(ap1), a11 = __ldg(ap1 + 1), a12 = __ldg(ap1 + 2);
+	const float4 a20 = __ldg(ap2), a21 = __ldg(ap2 + 1), a22 = __ldg(ap2 + 2);
+	const float fbz = in.depth[gi];
+	if ((__float_as_uint(s0.w) | __float_as_uint(s1.w) | __float_as_uint(s2.w)) & 0x3fu) {
+		shade_pixel_clipped<Shader>(mesh, u, fp, in, ordinal, i0, i1, i2, px, py);
+		return;
 	}
-	v4 col;
-	if (Shader::fragment(u, face_material(mesh, face), al, be, ga, vs, col)) return;  // true = discard (none of the shipped shaders does)
-	in.depth[gi] = z;
-	in.color[gi] = pack_bgra(col);
+	Setup s;
+	if (!setup_triangle(s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, fp.W, fp.y_lo, fp.y_hi, s)) return;
+	float c0, c1, c2, al, be, ga;
+	coverage(s, px, py, c0, c1, c2);
+	const float z = interp_z(s, c0, c1, c2, al, be, ga);
+	// mergeTileResults: strict tileZ < fbZ (reference src/tiled_pipeline.cpp:1148-1156)
+	if (!(z < fbz)) return;
+	float var[Shader::NV];
+	accumulate_vertex<Shader>(u, 0, al, V3(p0.x, p0.y, p0.z), V3(a00.z, a00.w, a01.x), V3(a01.y, a01.z, a01.w), V3(a02.x, a02.y, a02.z), a00.x, a00.y, var);
+	accumulate_vertex<Shader>(u, 1, be, V3(p1.x, p1.y, p1.z), V3(a10.z, a10.w, a11.x), V3(a11.y, a11.z, a11.w), V3(a12.x, a12.y, a12.z), a10.x, a10.y, var);
+	accumulate_vertex<Shader>(u, 2, ga, V3(p2.x, p2.y, p2.z), V3(a20.z, a20.w, a21.x), V3(a21.y, a21.z, a21.w), V3(a22.x, a22.y, a22.z), a20.x, a20.y, var);
+	finish_pixel<Shader>(mesh, u, in, ordinal >> 3, gi, z, var);
 }
 
 template <typename Shader>
-__global__ void __launch_bounds__(TILE_THREADS) k_tile_shade(MeshView mesh, Uniforms u, FrameParams fp, TileIn in) {
+__global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(const __grid_constant__ MeshView mesh, const __grid_constant__ Uniforms u, const __grid_constant__ FrameParams fp,
+                                                                             const __grid_constant__ TileIn in) {
 	__shared__ unsigned long long s_keys[GT_PIX];
 	if (in.status->overflow) return;  // the host grows the bins and re-issues the draw
 	const int tx = blockIdx.x, ty = fp.ty_lo + blockIdx.y;
@@ -428,11 +477,24 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_shade(MeshView mesh, Unif
 		}
 		__syncthreads();
 	}
-	// 3. deferred shading of the visible triangle of each pixel + framebuffer resolve (one warp = one 128 B row segment)
-	for (int p = tid; p < GT_PIX; p += TILE_THREADS) {
-		unsigned long long k = s_keys[p];
-		if (k == KEY_EMPTY) continue;
-		shade_pixel<Shader>(mesh, u, fp, in, (unsigned)(k & 0xFFFFFFFFull), x0 + (p & (GT - 1)), y0 + (p / GT));
+	// 3. deferred shading of the visible triangle of each pixel + framebuffer resolve (one warp = one 128 B row segment).
+	//    The index fetches of a thread's four pixels are issued together so their latency is paid once.
+	constexpr int PPT = GT_PIX / TILE_THREADS;
+	unsigned ord[PPT], vi[PPT][3];
+#pragma unroll
+	for (int i = 0; i < PPT; ++i) {
+		const unsigned long long k = s_keys[tid + i * TILE_THREADS];
+		ord[i] = (k == KEY_EMPTY) ? 0xFFFFFFFFu : (unsigned)(k & 0xFFFFFFFFull);  // a real ordinal is < 2^32 - 1 (faces < 2^29)
+		if (ord[i] != 0xFFFFFFFFu) {
+			const unsigned* ip = mesh.idx + (size_t)(ord[i] >> 3) * 3;
+			vi[i][0] = __ldg(ip); vi[i][1] = __ldg(ip + 1); vi[i][2] = __ldg(ip + 2);
+		}
+	}
+#pragma unroll
+	for (int i = 0; i < PPT; ++i) {
+		if (ord[i] == 0xFFFFFFFFu) continue;
+		const int p = tid + i * TILE_THREADS;
+		shade_pixel<Shader>(mesh, u, fp, in, ord[i], vi[i][0], vi[i][1], vi[i][2], x0 + (p & (GT - 1)), y0 + (p / GT));
 	}
 }
 

@@ -39,6 +39,25 @@ __device__ __forceinline__ unsigned clip_code(v4 c) {
 	code |= ((c.w - c.z) >= 0.f) ? 0u : 32u;
 	return code;
 }
+// "Safely outside" code, bit k set <=> d_k < -(1e-4*(|w|+|c|) + 1e-6). If all three vertices of a face share such a bit,
+// clipTriangle (reference src/pipeline.cpp:176-228) provably returns nothing: every vertex the earlier planes create is a
+// convex combination x*(1-t) + y*t, t in [0,1], of vertices that are outside plane k by that margin; the rounding of the
+// products, sums and of 1-t moves d_k by a few 2^-24 relative to |w|+|c| per generation (at most five generations), four
+// orders of magnitude below the margin, so every sub-triangle reaches plane k with d < 0 on all vertices and is dropped
+// (:311-313). Without the margin the claim is false: d can round to exactly 0 or fall inside the |denom| < 1e-7 -> t = 0.5
+// fallback (:343-344), so faces that are outside by less than the margin take the exact slow path instead.
+__device__ __forceinline__ unsigned clip_code_safe_out(v4 c) {
+	const float aw = fabsf(c.w);
+	const float mx = 1e-4f * (aw + fabsf(c.x)) + 1e-6f, my = 1e-4f * (aw + fabsf(c.y)) + 1e-6f, mz = 1e-4f * (aw + fabsf(c.z)) + 1e-6f;
+	unsigned code = 0;
+	code |= ((c.x + c.w) < -mx) ? 1u : 0u;
+	code |= ((c.w - c.x) < -mx) ? 2u : 0u;
+	code |= ((c.y + c.w) < -my) ? 4u : 0u;
+	code |= ((c.w - c.y) < -my) ? 8u : 0u;
+	code |= ((c.z + c.w) < -mz) ? 16u : 0u;
+	code |= ((c.w - c.z) < -mz) ? 32u : 0u;
+	return code;
+}
 __device__ __forceinline__ float dist_func(v4 v, int plane) {
 	switch (plane) {
 	case 0: return v.x + v.w;

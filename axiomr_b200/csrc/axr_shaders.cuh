@@ -28,9 +28,15 @@ struct Uniforms {
 	int sampler;     // 0 nearest (reference), 1 bilinear (extension)
 };
 
-// VertexOutput (reference include/IShader.hpp:11-17); zNDC is never read by the pipeline
-struct VsFlat { v3 normal; };
-struct VsTbn { float uv[2]; v3 world; m3 tbn; };
+// VertexOutput (reference include/IShader.hpp:11-17) as a flat array of varyings (zNDC is never read by the pipeline).
+// Every shipped fragment shader starts by combining the three VertexOutputs with the barycentrics as
+// bar.x*v0 + bar.y*v1 + bar.z*v2 (component-wise for vec2/vec3/mat3), i.e. ((v0*al) + (v1*be)) + v2*ga per float.
+// The kernel performs exactly that combination (same order, same rounding) vertex by vertex, so only one VertexOutput
+// is live at a time, and hands the interpolated varyings to Shader::fragment.
+//   FlatShader : [0..2] normal
+//   Phong / PBR: [0..1] uv, [2..4] worldPos, [5..13] tbn columns T,B,N
+constexpr int VARY_FLAT = 3;
+constexpr int VARY_TBN = 14;
 
 // ------------------------------------------------------------------ Texture::sample (reference include/texture.hpp:12-34)
 __device__ __forceinline__ v4 texel(const TexRef& t, int x, int y) {
@@ -65,33 +71,30 @@ __device__ __forceinline__ v4 sample(const TexRef& t, float u, float v, int samp
 	return sampler ? sample_bilinear(t, u, v) : sample_nearest(t, u, v);
 }
 
-__device__ __forceinline__ v3 bary3(float al, float be, float ga, v3 a, v3 b, v3 c) { return (a * al + b * be) + c * ga; }
 __device__ __forceinline__ v3 xyz(v4 v) { return V3(v.x, v.y, v.z); }
 
 // PhongShader::vertex :147-168 == PBRShader::vertex :259-282
-__device__ __forceinline__ void vertex_tbn(const Uniforms& u, v3 pos, v3 n, v3 t, v3 b, const float uv[2], VsTbn& o) {
-	o.uv[0] = uv[0]; o.uv[1] = uv[1];
-	o.world = xyz(mul(u.model, V4(pos.x, pos.y, pos.z, 1.0f)));
-	o.tbn.c[0] = normalize(xyz(mul(u.model, V4(t.x, t.y, t.z, 0.0f))));
-	o.tbn.c[1] = normalize(xyz(mul(u.model, V4(b.x, b.y, b.z, 0.0f))));
-	o.tbn.c[2] = normalize(xyz(mul(u.model, V4(n.x, n.y, n.z, 0.0f))));
-}
-__device__ __forceinline__ m3 bary_m3(float al, float be, float ga, const m3& a, const m3& b, const m3& c) {
-	m3 r;
-	for (int i = 0; i < 3; ++i) r.c[i] = (a.c[i] * al + b.c[i] * be) + c.c[i] * ga;
-	return r;
+__device__ __forceinline__ void vertex_tbn(const Uniforms& u, v3 pos, v3 n, v3 t, v3 b, float uvx, float uvy, float* o) {
+	o[0] = uvx; o[1] = uvy;
+	v3 w = xyz(mul(u.model, V4(pos.x, pos.y, pos.z, 1.0f)));
+	v3 T = normalize(xyz(mul(u.model, V4(t.x, t.y, t.z, 0.0f))));
+	v3 B = normalize(xyz(mul(u.model, V4(b.x, b.y, b.z, 0.0f))));
+	v3 N = normalize(xyz(mul(u.model, V4(n.x, n.y, n.z, 0.0f))));
+	o[2] = w.x; o[3] = w.y; o[4] = w.z;
+	o[5] = T.x; o[6] = T.y; o[7] = T.z;
+	o[8] = B.x; o[9] = B.y; o[10] = B.z;
+	o[11] = N.x; o[12] = N.y; o[13] = N.z;
 }
 
 // --------------------------------------------------------------------------------------------- FlatShader :19-61
 struct FlatShader {
-	typedef VsFlat VsOut;
-	static constexpr bool kNeedsTextures = false;
-	__device__ __forceinline__ static void vertex(const Uniforms& u, v3 pos, v3 n, v3 t, v3 b, const float uv[2], VsOut& o) {
-		o.normal = mul(u.normal_mat, n);
+	static constexpr int NV = VARY_FLAT;
+	__device__ __forceinline__ static void vertex(const Uniforms& u, v3 pos, v3 n, v3 t, v3 b, float uvx, float uvy, float* o) {
+		v3 r = mul(u.normal_mat, n);
+		o[0] = r.x; o[1] = r.y; o[2] = r.z;
 	}
-	__device__ __forceinline__ static bool fragment(const Uniforms& u, const Material& m, float al, float be, float ga,
-	                                                const VsOut* vs, v4& color) {
-		v3 n = normalize(bary3(al, be, ga, vs[0].normal, vs[1].normal, vs[2].normal));
+	__device__ __forceinline__ static bool fragment(const Uniforms& u, const Material& m, const float* var, v4& color) {
+		v3 n = normalize(V3(var[0], var[1], var[2]));
 		float intensity = clampf(dot(-u.light_dir, n), 0.0f, 1.0f);
 		float c = 1.0f * intensity;
 		color = V4(c, c, c, c);
@@ -101,27 +104,23 @@ struct FlatShader {
 
 // --------------------------------------------------------------------------------------------- PhongShader :136-250
 struct PhongShader {
-	typedef VsTbn VsOut;
-	static constexpr bool kNeedsTextures = true;
-	__device__ __forceinline__ static void vertex(const Uniforms& u, v3 pos, v3 n, v3 t, v3 b, const float uv[2], VsOut& o) {
-		vertex_tbn(u, pos, n, t, b, uv, o);
+	static constexpr int NV = VARY_TBN;
+	__device__ __forceinline__ static void vertex(const Uniforms& u, v3 pos, v3 n, v3 t, v3 b, float uvx, float uvy, float* o) {
+		vertex_tbn(u, pos, n, t, b, uvx, uvy, o);
 	}
-	__device__ __forceinline__ static bool fragment(const Uniforms& u, const Material& m, float al, float be, float ga,
-	                                                const VsOut* vs, v4& color) {
-		float uvx = al * vs[0].uv[0] + be * vs[1].uv[0] + ga * vs[2].uv[0];
-		float uvy = al * vs[0].uv[1] + be * vs[1].uv[1] + ga * vs[2].uv[1];
+	__device__ __forceinline__ static bool fragment(const Uniforms& u, const Material& m, const float* var, v4& color) {
+		const float uvx = var[0], uvy = var[1];
 		v4 nm = sample(m.tex[1], uvx, uvy, u.sampler);
+		v4 albedo = sample(m.tex[0], uvx, uvy, u.sampler);
 		v3 nms = normalize(xyz(nm) * 2.0f - V3(1.0f, 1.0f, 1.0f));
-		m3 tbn = bary_m3(al, be, ga, vs[0].tbn, vs[1].tbn, vs[2].tbn);
-		v3 T = tbn.c[0];
-		v3 N = normalize(tbn.c[2]);
+		v3 T = V3(var[5], var[6], var[7]);
+		v3 N = normalize(V3(var[11], var[12], var[13]));
 		v3 Tn = normalize(T - N * dot(N, T));
 		v3 Bn = cross(N, Tn);
 		m3 ftbn;
 		ftbn.c[0] = Tn; ftbn.c[1] = Bn; ftbn.c[2] = N;
-		v4 albedo = sample(m.tex[0], uvx, uvy, u.sampler);
 		v3 normal = normalize(mul(ftbn, nms));
-		v3 fragPos = bary3(al, be, ga, vs[0].world, vs[1].world, vs[2].world);
+		v3 fragPos = V3(var[2], var[3], var[4]);
 		v3 viewDir = normalize(u.cam_pos - fragPos);
 		v3 lightDir = -u.light_dir;
 		v3 ambient = u.light_color * 0.1f;
@@ -139,29 +138,27 @@ struct PhongShader {
 
 // --------------------------------------------------------------------------------------------- PBRShader :252-423
 struct PBRShader {
-	typedef VsTbn VsOut;
-	static constexpr bool kNeedsTextures = true;
-	__device__ __forceinline__ static void vertex(const Uniforms& u, v3 pos, v3 n, v3 t, v3 b, const float uv[2], VsOut& o) {
-		vertex_tbn(u, pos, n, t, b, uv, o);
+	static constexpr int NV = VARY_TBN;
+	__device__ __forceinline__ static void vertex(const Uniforms& u, v3 pos, v3 n, v3 t, v3 b, float uvx, float uvy, float* o) {
+		vertex_tbn(u, pos, n, t, b, uvx, uvy, o);
 	}
-	__device__ __forceinline__ static bool fragment(const Uniforms& u, const Material& m, float al, float be, float ga,
-	                                                const VsOut* vs, v4& color) {
+	__device__ __forceinline__ static bool fragment(const Uniforms& u, const Material& m, const float* var, v4& color) {
 		const float PI = 3.14159265358979323846264338327950288f;
-		float uvx = al * vs[0].uv[0] + be * vs[1].uv[0] + ga * vs[2].uv[0];
-		float uvy = al * vs[0].uv[1] + be * vs[1].uv[1] + ga * vs[2].uv[1];
+		const float uvx = var[0], uvy = var[1];
 		v4 nm = sample(m.tex[1], uvx, uvy, u.sampler);
-		v3 nms = normalize(V3(nm.x * 2.0f - 1.0f, nm.y * 2.0f - 1.0f, nm.z * 2.0f - 1.0f));
-		m3 tbn = bary_m3(al, be, ga, vs[0].tbn, vs[1].tbn, vs[2].tbn);
 		v4 al4 = sample(m.tex[0], uvx, uvy, u.sampler);
-		v3 albedo = V3(powf(al4.x, 2.2f), powf(al4.y, 2.2f), powf(al4.z, 2.2f));
 		float metallic = sample(m.tex[2], uvx, uvy, u.sampler).x;
 		float roughness = sample(m.tex[3], uvx, uvy, u.sampler).x;
 		float ao = sample(m.tex[4], uvx, uvy, u.sampler).x;
+		v3 nms = normalize(V3(nm.x * 2.0f - 1.0f, nm.y * 2.0f - 1.0f, nm.z * 2.0f - 1.0f));
+		m3 tbn;
+		tbn.c[0] = V3(var[5], var[6], var[7]); tbn.c[1] = V3(var[8], var[9], var[10]); tbn.c[2] = V3(var[11], var[12], var[13]);
+		v3 albedo = V3(powf(al4.x, 2.2f), powf(al4.y, 2.2f), powf(al4.z, 2.2f));
 		float roughness2 = roughness * roughness;
 		float roughness4 = roughness2 * roughness2;
 		float oneMinusMetallic = 1.0f - metallic;
 		v3 normal = normalize(mul(tbn, nms));  // :345 uses the raw interpolated TBN; the re-orthogonalised basis (:316-323) is dead
-		v3 fragPos = bary3(al, be, ga, vs[0].world, vs[1].world, vs[2].world);
+		v3 fragPos = V3(var[2], var[3], var[4]);
 		v3 viewDir = normalize(u.cam_pos - fragPos);
 		v3 lightDir = -u.light_dir;
 		v3 halfwayDir = normalize(lightDir + viewDir);
