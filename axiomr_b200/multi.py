@@ -35,6 +35,44 @@ def views_for_rank(rank: int, world: int, n_views: int):
     return list(range(start, start + base + (1 if rank < extra else 0)))
 
 
+def gather_bands(color, depth, bands, rank: int, dist):
+    """Bands -> rank 0: every rank r>0 sends its rows [y0,y1) of colour and depth; rank 0 receives them in place
+    (row ranges are contiguous in memory, so this is a zero-copy composite). Works on any torch.distributed backend."""
+    ops = []
+    if rank == 0:
+        for r in range(1, len(bands)):
+            y0, y1 = bands[r]
+            ops.append(dist.P2POp(dist.irecv, color[y0:y1], r))
+            ops.append(dist.P2POp(dist.irecv, depth[y0:y1], r))
+    elif rank < len(bands):
+        y0, y1 = bands[rank]
+        ops.append(dist.P2POp(dist.isend, color[y0:y1], 0))
+        ops.append(dist.P2POp(dist.isend, depth[y0:y1], 0))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+def gather_views(color, depth, rank: int, world: int, dist, slots=None):
+    """Views -> rank 0: slot r-1 receives rank r's finished frame (rank 0's own frame stays in its framebuffer)."""
+    import torch
+    ops = []
+    if rank == 0:
+        if slots is None:
+            slots = (torch.empty((world - 1,) + tuple(color.shape), dtype=color.dtype, device=color.device),
+                     torch.empty((world - 1,) + tuple(depth.shape), dtype=depth.dtype, device=depth.device))
+        for r in range(1, world):
+            ops.append(dist.P2POp(dist.irecv, slots[0][r - 1], r))
+            ops.append(dist.P2POp(dist.irecv, slots[1][r - 1], r))
+    else:
+        ops.append(dist.P2POp(dist.isend, color, 0))
+        ops.append(dist.P2POp(dist.isend, depth, 0))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return slots
+
+
 class _DevArray:
     def __init__(self, ptr: int, shape, typestr: str):
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3}
@@ -88,25 +126,7 @@ class Compositor:
         if self.mode == "bands" and self.transport == "peer":
             return  # the tile kernel already stored this rank's band into GPU 0's framebuffer over NVLink
         with torch.cuda.stream(self.stream):
-            ops = []
             if self.mode == "views":
-                if self.rank == 0:
-                    for r in range(1, self.world):
-                        ops.append(dist.P2POp(dist.irecv, self.slots[0][r - 1], r))
-                        ops.append(dist.P2POp(dist.irecv, self.slots[1][r - 1], r))
-                else:
-                    ops.append(dist.P2POp(dist.isend, self.color, 0))
-                    ops.append(dist.P2POp(dist.isend, self.depth, 0))
+                self.slots = gather_views(self.color, self.depth, self.rank, self.world, dist, self.slots)
             else:
-                if self.rank == 0:
-                    for r in range(1, len(self.bands)):
-                        y0, y1 = self.bands[r]
-                        ops.append(dist.P2POp(dist.irecv, self.color[y0:y1], r))
-                        ops.append(dist.P2POp(dist.irecv, self.depth[y0:y1], r))
-                elif self.rank < len(self.bands):
-                    y0, y1 = self.bands[self.rank]
-                    ops.append(dist.P2POp(dist.isend, self.color[y0:y1], 0))
-                    ops.append(dist.P2POp(dist.isend, self.depth[y0:y1], 0))
-            if ops:
-                for w in dist.batch_isend_irecv(ops):
-                    w.wait()
+                gather_bands(self.color, self.depth, self.bands, self.rank, dist)

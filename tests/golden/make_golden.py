@@ -1,0 +1,44 @@
+"""Regenerates tests/golden/*.npz by running the UNMODIFIED reference (oracle/_ref, built from /root/reference by
+oracle/Makefile) on the deterministic cases of cases.py. Run here (the reference tree is not on the GPU box):
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, HERE)
+
+from oracle import pyoracle as po  # noqa: E402
+import cases as C  # noqa: E402
+
+po.build(ref=True)
+assert po.ref_available(), "oracle/_ref/libaxr_ref.so is needed (requires /root/reference)"
+all_cases = C.cases()
+assert list(all_cases) == C.CASE_NAMES
+for name, sc in all_cases.items():
+    c, d, _ = po.ref_render(sc, threads=3)
+    C.save_case(name, sc, c, d)
+    print(name, int(np.isfinite(d).sum()), "px covered")
+# stage-level known answers
+tris = C.clip_cases()
+clip_out = [po.ref_clip_triangle(t) for t in tris]
+setup = [po.ref_triangle_setup(t, 640, 480) for t in tris]
+rng = np.random.default_rng(3)
+uv = rng.uniform(-0.2, 1.2, (64, 2)).astype(np.float32)
+uv[:6] = [[0, 0], [1, 1], [0, 1], [1, 0], [0.5, 0.5], [0.999999, 0.000001]]
+tex = np.arange(7 * 5 * 4, dtype=np.uint8).reshape(5, 7, 4)
+np.savez_compressed(os.path.join(HERE, "stage_kat.npz"),
+                    clip_n=np.array([o.shape[0] for o in clip_out]), clip_out=np.concatenate(clip_out),
+                    setup_back=np.array([s[0] for s in setup]), setup_out=np.stack([s[1] for s in setup]),
+                    tex=tex, uv=uv, tex_out=po.ref_texture_sample(tex, uv))
+vp, vpt = po.ref_camera((0, 0, 5), (0, 0, 0), 60.0, 800, 600)
+a = np.arange(16, dtype=np.float32).reshape(4, 4) * 0.37 - 2
+out = np.zeros(16, dtype=np.float32)
+import ctypes as ct
+po.ref_lib().axr_ref_mat4_mul(vp.ctypes.data_as(ct.POINTER(ct.c_float)), a.ctypes.data_as(ct.POINTER(ct.c_float)), out.ctypes.data_as(ct.POINTER(ct.c_float)))
+np.savez_compressed(os.path.join(HERE, "camera_kat.npz"), view_proj=vp, viewport=vpt, a=a, vp_times_a=out.reshape(4, 4))
+print("stage KATs written")

@@ -111,3 +111,95 @@ def test_bands_equal_full_frame(po):
         cb, db, _ = api.render_scene(sc, band=(y0, y1))
         c[y0:y1], d[y0:y1] = cb[y0:y1], db[y0:y1]
     assert np.array_equal(c, c_full) and np.array_equal(d.view(np.uint32), d_full.view(np.uint32))
+
+
+import os as _os
+import sys as _sys
+_sys.path.insert(0, _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden"))
+import cases as _C  # noqa: E402
+
+
+@pytest.mark.parametrize("name", _C.CASE_NAMES)
+def test_cuda_matches_reference_golden(po, name):
+    """CUDA path vs outputs of the UNMODIFIED reference committed under tests/golden/ (inputs stored alongside)."""
+    sc, c_ref, d_ref = _C.load_case(name)
+    c, d, st = _gpu(sc)
+    m = po.compare(c, d, c_ref, d_ref)
+    po.assert_parity(m)
+    assert m["coverage_mismatch"] == 0 and m["depth_bit_mismatch"] == 0, m
+    assert m["color_max_diff"] <= 1, m
+
+
+def test_mirror_classes_drawmesh_host_framebuffer(po):
+    """The reference-shaped call: TiledPipeline(threads, camera, framebuffer).drawMesh(model, mesh) on HOST buffers."""
+    from axiomr_b200 import api
+    sc, c_ref, d_ref = _C.load_case("head_phong_200")
+    fb = api.Framebuffer(sc.width, sc.height, True)
+    fb.clearColor(api.Color(0, 0, 0, 255))
+    fb.clearDepth()
+    cam = api.Camera()
+    cam.setViewport(0, 0, sc.width, sc.height)
+    cam.setViewProjectionMatrix(sc.view_proj)
+    cam._pos = sc.cam_pos
+    pipe = api.TiledPipeline(8, cam, fb)
+    shader = api.PhongShader(tuple(sc.light_dir), tuple(sc.light_color))
+    pipe.setShader(shader)
+    tex = [api.Texture(t) if t is not None else None for t in sc.textures]
+    mat = api.Material("m0", tex[0], tex[2], tex[1], tex[3], tex[4], sc.specular_exponent)
+    mesh = api.Mesh(sc.vertices, sc.indices, {"m0": mat})
+    pipe.drawMesh(sc.model, mesh)
+    m = po.compare(fb.getColorData(), fb.getDepthData(), c_ref, d_ref)
+    assert m["coverage_mismatch"] == 0 and m["depth_bit_mismatch"] == 0 and m["color_max_diff"] <= 1, m
+    # drawing again onto the same framebuffer changes nothing (strict depth test)
+    before = fb.getColorData().copy()
+    pipe.drawMesh(sc.model, mesh)
+    assert np.array_equal(before, fb.getColorData())
+    # error conventions: a shader whose textures are missing is an error code, not a crash
+    bad = api.Mesh(sc.vertices, sc.indices, {"m0": api.Material("m0")})
+    with pytest.raises(api.AxrError) as e:
+        pipe.drawMesh(sc.model, bad)
+    assert e.value.code == -5
+
+
+def test_bin_overflow_regrows_and_redraws(po):
+    """More binned triangles / references than the initial bin capacity: the draw is re-issued after growing, output unchanged."""
+    from axiomr_b200 import api
+    v, f = S.random_triangles(300000, 31, extent=1.2, size=0.3, zspread=0.5)
+    sc = S.Scene("many_mid", 1024, 768, v, f, 0)
+    c1, d1, st = api.render_scene(sc)
+    assert st["binned_triangles"] > (1 << 18) or st["bin_refs"] > (1 << 20), st
+    assert st["redo"] == 1, st
+    c0, d0, _ = po.oracle_render(sc, threads=8)
+    m = po.compare(c1, d1, c0, d0)
+    assert m["coverage_mismatch"] == 0 and m["depth_bit_mismatch"] == 0, m
+
+
+def test_multi_material_groups(po):
+    """Two material groups with different textures: each face is shaded with its own group's material."""
+    from axiomr_b200 import api
+    v1, f1 = S.quad_grid(4, size=2.0, z=0.0)
+    v2, f2 = S.quad_grid(4, size=2.0, z=0.0)
+    v1[:, 0] -= 1.1
+    v2[:, 0] += 1.1
+    verts = np.concatenate([v1, v2])
+    faces = np.concatenate([f1, f2 + v1.shape[0]])
+    ta, tb = S._phong_textures(32), [S.scalar_texture(32, 0, 255, 2), S.normal_texture(32, 3), None, None, None]
+    dev = api.Device(320, 200)
+    try:
+        mesh = dev.upload_mesh(verts, faces, groups=[(0, f1.shape[0]), (f1.shape[0], f2.shape[0])])
+        h = [dev.upload_texture(t) for t in (ta[0], ta[1], tb[0], tb[1])]
+        dev.set_material(mesh, 0, h[0], h[1], specular_exponent=0.2)
+        dev.set_material(mesh, 1, h[2], h[3], specular_exponent=0.4)
+        sa = S.Scene("a", 320, 200, verts, faces[:f1.shape[0]], 1, textures=ta, specular_exponent=0.2)
+        sb = S.Scene("b", 320, 200, verts, faces[f1.shape[0]:], 1, textures=tb, specular_exponent=0.4)
+        dev.set_uniforms(sa.view_proj, sa.cam_pos)
+        dev.set_shader(1, sa.light_dir, sa.light_color)
+        dev.clear()
+        dev.draw_mesh(mesh, sa.model)
+        c1, d1 = dev.resolve()
+    finally:
+        dev.close()
+    c0, d0, _ = po.oracle_render(sa)
+    c0, d0, _ = po.oracle_render(sb, color=c0, depth=d0)
+    m = po.compare(c1, d1, c0, d0)
+    assert m["coverage_mismatch"] == 0 and m["depth_bit_mismatch"] == 0 and m["color_max_diff"] <= 1, m

@@ -1,0 +1,117 @@
+"""CPU: host-side logic, the C-ABI library's exports, multi-GPU sharding helpers (gloo, world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+from axiomr_b200 import api, multi, scenes as S  # noqa: E402
+
+
+def test_abi_library_exports_every_declared_symbol():
+    from axiomr_b200 import build
+    build.build()
+    hdr = open(os.path.join(ROOT, "include", "axr_b200.h")).read()
+    declared = set(re.findall(r"\b(axr_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(os.path.join(ROOT, "axiomr_b200", "libaxr_b200.so"))
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert declared == set(api.ABI_SYMBOLS), declared ^ set(api.ABI_SYMBOLS)
+    lib.axr_abi_version.restype = ctypes.c_int
+    assert lib.axr_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(api.AxrError) as e:
+        api.Device(64, 64)
+    assert e.value.code == -3 and "no CPU path" in str(e.value)
+
+
+def test_product_code_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "axiomr_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "pyoracle" not in src and "axr_oracle" not in src and "libaxr_ref" not in src, os.path.join(dirpath, f)
+
+
+def test_band_rows_partition():
+    assert multi.band_rows(4320, 8) == [(0, 544), (544, 1088), (1088, 1632), (1632, 2176), (2176, 2720), (2720, 3264), (3264, 3792), (3792, 4320)]
+    for h in (16, 100, 1080, 2160, 4320, 37):
+        for w in (1, 2, 3, 8):
+            b = multi.band_rows(h, w)
+            assert b[0][0] == 0 and b[-1][1] == h and all(a[1] == c[0] for a, c in zip(b, b[1:]))
+            assert all(y0 % 16 == 0 and y1 > y0 for y0, y1 in b)
+    assert sum(len(multi.views_for_rank(r, 8, 64)) for r in range(8)) == 64
+
+
+def test_scene_generators_shapes():
+    v, f = S.icosphere(3)
+    assert f.shape[0] == 20 * 4 ** 3 and v.shape == (10 * 4 ** 3 + 2, 14)
+    v, f = S.torus(12, 9)
+    assert f.shape[0] == 2 * 12 * 9 and v.shape[0] == 13 * 10
+    v, f = S.head_like()
+    assert f.shape[0] == 2450
+    assert S.diffuse_texture(16).shape == (16, 16, 4) and S.normal_texture(16).dtype == np.uint8
+    # BASELINE.md §4 triangle / vertex counts of the named configs (computed, not generated)
+    assert 20 * 4 ** 8 == 1310720 and 10 * 4 ** 8 + 2 == 655362 and 2 * 2236 ** 2 == 9999392 and 2237 ** 2 == 5004169
+
+
+def test_framebuffer_mirror_semantics():
+    fb = api.Framebuffer(8, 4, True, pinned=False)
+    assert fb.getColorData().shape == (4, 8, 4) and np.isinf(fb.getDepthData()).all()
+    fb.clearColor(api.Color(10, 20, 30, 255))
+    assert fb.getColorData()[0, 0].tolist() == [30, 20, 10, 255]  # B,G,R,A (reference src/framebuffer.cpp:29-32)
+    fb.clearDepth(0.5)
+    assert (fb.getDepthData() == 0.5).all()
+    p = api.TiledPipeline(4, None, fb)
+    p.drawMesh(np.eye(4), None)  # silent return without shader/camera (reference src/tiled_pipeline.cpp:146)
+    m = api.Mesh(np.zeros((3, 14), np.float32), np.array([[0, 1, 2]], np.uint32))
+    with pytest.raises(KeyError):
+        m.getMaterial("nope")  # unordered_map::at
+
+
+_GLOO = r'''
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+from axiomr_b200 import multi
+rank, world = int(sys.argv[1]), 2
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=sys.argv[2], RANK=str(rank), WORLD_SIZE="2")
+dist.init_process_group("gloo", rank=rank, world_size=world)
+H, W = 80, 24
+bands = multi.band_rows(H, world)
+full_c = torch.arange(H * W, dtype=torch.int32).reshape(H, W)
+full_d = torch.arange(H * W, dtype=torch.float32).reshape(H, W) * 0.5
+color = torch.zeros((H, W), dtype=torch.int32); depth = torch.full((H, W), float("inf"))
+y0, y1 = bands[rank]
+color[y0:y1] = full_c[y0:y1]; depth[y0:y1] = full_d[y0:y1]      # what this rank "rendered"
+multi.gather_bands(color, depth, bands, rank, dist)
+if rank == 0:
+    assert torch.equal(color, full_c) and torch.equal(depth, full_d)
+slots = multi.gather_views(color, depth, rank, world, dist)
+if rank == 0:
+    assert slots[0].shape == (1, H, W) and int(slots[0][0, bands[1][0], 0]) == int(full_c[bands[1][0], 0])
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_compositor_gather_logic_gloo_world2(tmp_path):
+    script = tmp_path / "gloo_rank.py"
+    script.write_text(_GLOO % ROOT)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), port], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs), outs
