@@ -203,3 +203,19 @@ def test_multi_material_groups(po):
     c0, d0, _ = po.oracle_render(sb, color=c0, depth=d0)
     m = po.compare(c1, d1, c0, d0)
     assert m["coverage_mismatch"] == 0 and m["depth_bit_mismatch"] == 0 and m["color_max_diff"] <= 1, m
+
+
+@pytest.mark.parametrize("shader", [0, 1, 2])
+def test_cpp_dropin_adapter_vs_reference_in_process(tmp_path, shader):
+    """AR::B200TiledPipeline (axiomr_b200/host, C++ adapter over the C ABI) against the reference's AR::TiledPipeline in ONE
+    process, scene loaded by the reference's own OBJ/MTL/texture loaders (oracle/_ref/dropin_demo, prebuilt where /root/reference exists)."""
+    import subprocess
+    from objutil import write_obj_scene
+    exe = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "oracle", "_ref", "dropin_demo")
+    if not _os.path.exists(exe):
+        pytest.skip("oracle/_ref/dropin_demo not built (needs /root/reference at build time)")
+    v, f = S.head_like(24, 23)
+    obj = write_obj_scene(str(tmp_path), "head", v, f, S._pbr_textures(64))
+    r = subprocess.run([exe, obj, "400", "300", str(shader)], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and "PARITY OK" in r.stdout, (r.stdout, r.stderr)
