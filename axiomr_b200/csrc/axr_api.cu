@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -254,7 +255,7 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model) {
 	k_scan_tiles<<<1, 1024, 0, s>>>(ctx->tile_count, ctx->bin_start, n_tiles(ctx), ctx->ref_cap, ctx->n_records, ctx->rec_cap, ctx->d_status);
 	++launches;
 	prof_mark(ctx);
-	CU(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(DrawStatus), cudaMemcpyDeviceToHost, s));
+	CU(cudaMemcpyAsync(ctx->h_status, ctx->d_status, offsetof(DrawStatus, stripes), cudaMemcpyDeviceToHost, s));
 	CU(cudaEventRecord(ctx->status_event, s));
 	k_bin_scatter<<<148 * 4, 256, 0, s>>>(ctx->records, ctx->n_records, ctx->fp, ctx->bin_start, ctx->tile_count, ctx->items, ctx->d_status);
 	++launches;

@@ -21,7 +21,14 @@ namespace axr {
 
 constexpr int GT = 32;            // GPU tile edge in pixels (a multiple of REF_TILE; keeps rows 128 B wide for the resolve)
 constexpr int GT_PIX = GT * GT;
-constexpr int SMALL_BOX = 4;      // triangles whose pixel box is <= SMALL_BOX x SMALL_BOX are rasterised in k_setup_raster
+// triangles whose pixel box is at most SMALL_DIM on a side and SMALL_AREA pixels are rasterised by their own thread in k_setup_raster
+#ifndef AXR_SMALL_DIM
+#define AXR_SMALL_DIM 8
+#endif
+#ifndef AXR_SMALL_AREA
+#define AXR_SMALL_AREA 32
+#endif
+constexpr int SMALL_DIM = AXR_SMALL_DIM, SMALL_AREA = AXR_SMALL_AREA;
 constexpr int TILE_THREADS = 256;
 
 // 40-byte setup record of a triangle that goes through the tile bins
@@ -37,9 +44,9 @@ struct DrawStatus {
 	unsigned overflow;                                                                // 1: records, 2: refs
 	unsigned pad;
 	// per-CTA partial counters are spread over STAT_STRIPES slots (no single hot address); k_scan_tiles folds them
-	unsigned long long stripes[4][32];
+	unsigned stripes[4][4096];
 };
-constexpr int STAT_STRIPES = 32;
+constexpr int STAT_STRIPES = 4096;
 
 struct FrameParams {
 	int W, H;
@@ -121,18 +128,16 @@ __device__ __forceinline__ void emit_triangle(const FrameParams& fp, const Setup
 	cnt.tris++;
 	Setup s;
 	if (!setup_triangle(x0, y0, x1, y1, x2, y2, z0, z1, z2, fp.W, fp.y_lo, fp.y_hi, s)) return;
-	if (s.X1 - s.X0 <= SMALL_BOX && s.Y1 - s.Y0 <= SMALL_BOX) {
+	const int bw = s.X1 - s.X0, bh = s.Y1 - s.Y0;
+	if (bw <= SMALL_DIM && bh <= SMALL_DIM && bw * bh <= SMALL_AREA) {
 		cnt.small++;
-		for (int py = s.Y0; py < s.Y1; ++py)
-			for (int px = s.X0; px < s.X1; ++px) {
-				float c0, c1, c2, al, be, ga;
-				if (!coverage(s, px, py, c0, c1, c2)) continue;
-				float z = interp_z(s, c0, c1, c2, al, be, ga);
-				if (!z_draws(z)) continue;
-				unsigned long long key = make_key(z, ordinal);
-				atomicMin(o.vis + (size_t)py * fp.W + px, key);  // result unused -> RED.MIN.64, fire and forget
-				o.tile_touched[(py / GT) * fp.ntx + (px / GT)] = 1u;
-			}
+		for_each_covered(s, s.X0, s.X1, s.Y0, s.Y1, [&](int px, int py, float c0, float c1, float c2) {
+			float al, be, ga;
+			const float z = interp_z(s, c0, c1, c2, al, be, ga);
+			if (!z_draws(z)) return;
+			atomicMin(o.vis + (size_t)py * fp.W + px, make_key(z, ordinal));  // result unused -> RED.MIN.64, fire and forget
+			o.tile_touched[(py / GT) * fp.ntx + (px / GT)] = 1u;
+		});
 		return;
 	}
 	cnt.binned++;
@@ -171,23 +176,24 @@ __device__ __noinline__ void setup_clipped_face(const FrameParams& fp, const Set
 	}
 }
 
-constexpr int SETUP_THREADS = 256;
+#ifndef AXR_SETUP_THREADS
+#define AXR_SETUP_THREADS 128
+#endif
+constexpr int SETUP_THREADS = AXR_SETUP_THREADS;
 #ifndef AXR_SETUP_FPT
 #define AXR_SETUP_FPT 1
 #endif
 #ifndef AXR_SETUP_MINB
-#define AXR_SETUP_MINB 6
+#define AXR_SETUP_MINB 12
 #endif
 #ifndef AXR_TILE_MINB
 #define AXR_TILE_MINB 4
 #endif
-constexpr int SETUP_FPT = AXR_SETUP_FPT;  // faces per thread: the index loads and the 16 B screen-record gathers of all of them are issued back to back
+constexpr int SETUP_FPT = AXR_SETUP_FPT;  // faces per thread: index loads and 16 B screen-record gathers of all of them are issued back to back
 
 __global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(const __grid_constant__ MeshView mesh, const float4* __restrict__ sv,
                                                                 const __grid_constant__ m4 mvp, const __grid_constant__ FrameParams fp,
                                                                 const __grid_constant__ SetupOut o) {
-	__shared__ unsigned s_cnt[4];
-	if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
 	const unsigned long long base = (unsigned long long)blockIdx.x * (SETUP_THREADS * SETUP_FPT) + threadIdx.x;
 	unsigned vi[SETUP_FPT][3];
 	float4 s[SETUP_FPT][3];
@@ -222,19 +228,20 @@ __global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(
 			setup_clipped_face(fp, o, mvp, __ldg(mesh.pos + vi[k][0]), __ldg(mesh.pos + vi[k][1]), __ldg(mesh.pos + vi[k][2]), (unsigned)f, cnt);
 		}
 	}
-	// counters: warp reduce -> shared -> one striped global add per counter per CTA
-	__syncthreads();
-	unsigned w0 = __reduce_add_sync(0xffffffffu, clipped), w1 = __reduce_add_sync(0xffffffffu, cnt.tris);
-	unsigned w2 = __reduce_add_sync(0xffffffffu, cnt.small), w3 = __reduce_add_sync(0xffffffffu, cnt.binned);
+#ifndef AXR_NO_STATS
+	// counters: warp reduce, then one fire-and-forget reduction per non-zero counter per warp into one of 4096 stripes
+	// (no barrier, no fence, no hot address: warps retire independently); k_scan_tiles folds the stripes
+	__syncwarp();
+	const unsigned w0 = __reduce_add_sync(0xffffffffu, clipped), w1 = __reduce_add_sync(0xffffffffu, cnt.tris);
+	const unsigned w2 = __reduce_add_sync(0xffffffffu, cnt.small), w3 = __reduce_add_sync(0xffffffffu, cnt.binned);
 	if ((threadIdx.x & 31) == 0) {
-		if (w0) atomicAdd(&s_cnt[0], w0);
-		if (w1) atomicAdd(&s_cnt[1], w1);
-		if (w2) atomicAdd(&s_cnt[2], w2);
-		if (w3) atomicAdd(&s_cnt[3], w3);
+		const unsigned stripe = (blockIdx.x * (SETUP_THREADS / 32) + (threadIdx.x >> 5)) % STAT_STRIPES;
+		if (w0) atomicAdd(&o.status->stripes[0][stripe], w0);
+		if (w1) atomicAdd(&o.status->stripes[1][stripe], w1);
+		if (w2) atomicAdd(&o.status->stripes[2][stripe], w2);
+		if (w3) atomicAdd(&o.status->stripes[3][stripe], w3);
 	}
-	__syncthreads();
-	if (threadIdx.x < 4 && s_cnt[threadIdx.x])
-		atomicAdd(&o.status->stripes[threadIdx.x][blockIdx.x % STAT_STRIPES], (unsigned long long)s_cnt[threadIdx.x]);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ bins: scan + scatter
@@ -273,10 +280,14 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(unsigned* tile_count, unsig
 		if (tid == 1023) s_carry = carry + s_warp[31];
 		__syncthreads();
 	}
-	if (tid < 4) {
-		unsigned long long acc = 0;
-		for (int i = 0; i < STAT_STRIPES; ++i) acc += status->stripes[tid][i];
-		(&status->clipped_faces)[tid] = acc;
+	{  // fold the striped counters of k_setup_raster: warp w < 4 sums counter w
+		const int c = tid >> 5;
+		if (c < 4) {
+			unsigned long long acc = 0;
+			for (int i = lane; i < STAT_STRIPES; i += 32) acc += status->stripes[c][i];
+			for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+			if (lane == 0) (&status->clipped_faces)[c] = acc;
+		}
 	}
 	if (tid == 0) {
 		unsigned total = s_carry;
@@ -454,26 +465,53 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 	}
 	__syncthreads();
 	if (tid == 0) { in.tile_touched[tile] = 0u; in.tile_cursor[tile] = 0u; }
-	// 2. binned triangles: one warp per record, 8x4 pixel blocks per step, shared-memory atomicMin
+	// 2. binned triangles. Each warp takes 32 references at a time: every lane loads and sets up ITS record (32 independent
+	//    gathers in flight), then the warp walks the set-up records one by one (setup broadcast by shuffles) and evaluates
+	//    8x4 pixel blocks per step with shared-memory atomicMin.
 	if (b1 > b0) {
 		const int warp = tid >> 5, lane = tid & 31;
 		const int lx = lane & 7, ly = lane >> 3;
 		const int yb0 = max(y0, fp.y_lo), yb1 = min(min(y0 + GT, fp.H), fp.y_hi);
-		for (unsigned r = b0 + warp; r < b1; r += TILE_THREADS / 32) {
-			const TriRecord t = in.records[in.items[r]];
+		for (unsigned rb = b0 + warp * 32; rb < b1; rb += (TILE_THREADS / 32) * 32) {
+			const unsigned r = rb + lane;
 			Setup s;
-			if (!setup_triangle(t.x0, t.y0, t.x1, t.y1, t.x2, t.y2, t.z0, t.z1, t.z2, fp.W, fp.y_lo, fp.y_hi, s)) continue;
-			const int bx0 = max(s.X0, x0), bx1 = min(s.X1, x0 + GT), by0 = max(s.Y0, yb0), by1 = min(s.Y1, yb1);
-			for (int py0 = by0; py0 < by1; py0 += 4)
-				for (int px0 = bx0; px0 < bx1; px0 += 8) {
-					int px = px0 + lx, py = py0 + ly;
-					if (px >= bx1 || py >= by1) continue;
-					float c0, c1, c2, al, be, ga;
-					if (!coverage(s, px, py, c0, c1, c2)) continue;
-					float z = interp_z(s, c0, c1, c2, al, be, ga);
-					if (!z_draws(z)) continue;
-					atomicMin(&s_keys[(py - y0) * GT + (px - x0)], make_key(z, t.ordinal));
+			unsigned ordinal = 0;
+			int bx0 = 0, bx1 = 0, by0 = 0, by1 = 0;
+			bool ok = false;
+			if (r < b1) {
+				const TriRecord t = in.records[in.items[r]];
+				ordinal = t.ordinal;
+				ok = setup_triangle(t.x0, t.y0, t.x1, t.y1, t.x2, t.y2, t.z0, t.z1, t.z2, fp.W, fp.y_lo, fp.y_hi, s);
+				if (ok) {
+					bx0 = max(s.X0, x0); bx1 = min(s.X1, x0 + GT); by0 = max(s.Y0, yb0); by1 = min(s.Y1, yb1);
+					ok = bx0 < bx1 && by0 < by1;
 				}
+			}
+			unsigned todo = __ballot_sync(0xffffffffu, ok);
+			while (todo) {
+				const int src = __ffs(todo) - 1;
+				todo &= todo - 1;
+				Setup q;
+				q.a0 = __shfl_sync(0xffffffffu, s.a0, src); q.b0 = __shfl_sync(0xffffffffu, s.b0, src); q.c0 = __shfl_sync(0xffffffffu, s.c0, src);
+				q.a1 = __shfl_sync(0xffffffffu, s.a1, src); q.b1 = __shfl_sync(0xffffffffu, s.b1, src); q.c1 = __shfl_sync(0xffffffffu, s.c1, src);
+				q.a2 = __shfl_sync(0xffffffffu, s.a2, src); q.b2 = __shfl_sync(0xffffffffu, s.b2, src); q.c2 = __shfl_sync(0xffffffffu, s.c2, src);
+				q.inv_area = __shfl_sync(0xffffffffu, s.inv_area, src);
+				q.z0 = __shfl_sync(0xffffffffu, s.z0, src); q.z1 = __shfl_sync(0xffffffffu, s.z1, src); q.z2 = __shfl_sync(0xffffffffu, s.z2, src);
+				q.fminx = __shfl_sync(0xffffffffu, s.fminx, src);
+				const int qx0 = __shfl_sync(0xffffffffu, bx0, src), qx1 = __shfl_sync(0xffffffffu, bx1, src);
+				const int qy0 = __shfl_sync(0xffffffffu, by0, src), qy1 = __shfl_sync(0xffffffffu, by1, src);
+				const unsigned qord = __shfl_sync(0xffffffffu, ordinal, src);
+				for (int py0 = qy0; py0 < qy1; py0 += 4)
+					for (int px0 = qx0; px0 < qx1; px0 += 8) {
+						const int px = px0 + lx, py = py0 + ly;
+						if (px >= qx1 || py >= qy1) continue;
+						float c0, c1, c2, al, be, ga;
+						if (!coverage(q, px, py, c0, c1, c2)) continue;
+						const float z = interp_z(q, c0, c1, c2, al, be, ga);
+						if (!z_draws(z)) continue;
+						atomicMin(&s_keys[(py - y0) * GT + (px - x0)], make_key(z, qord));
+					}
+			}
 		}
 		__syncthreads();
 	}
