@@ -123,21 +123,46 @@ struct SetupOut {
 
 struct EmitCounters { unsigned tris, small, binned; };
 
+// Mark GPU tile (tx,ty) as holding direct-path keys. Test before set: millions of plain stores to the same few thousand
+// flags serialise in L2 (measured: 86 us of a 246 us kernel on C3); the flag is monotonic within a draw, so a stale cached 0
+// only costs a redundant store.
+__device__ __forceinline__ void touch_tile(const FrameParams& fp, const SetupOut& o, int tx, int ty) {
+	unsigned* tf = o.tile_touched + ty * fp.ntx + tx;
+	if (*tf == 0u) *tf = 1u;
+}
+
+// touched: when non-null the caller flags the tiles later (warp-aggregated); it receives the tile rect of the pixel box
+// packed as tx0 | ty0<<8 | tx1<<16 | ty1<<24 in units of GPU tiles (frames up to 8192 px), or stays 0xFFFFFFFF.
 __device__ __forceinline__ void emit_triangle(const FrameParams& fp, const SetupOut& o, float x0, float y0, float x1, float y1,
-                                              float x2, float y2, float z0, float z1, float z2, unsigned ordinal, EmitCounters& cnt) {
+                                              float x2, float y2, float z0, float z1, float z2, unsigned ordinal, EmitCounters& cnt,
+                                              unsigned* touched) {
 	cnt.tris++;
+#ifdef AXR_DIAG_NO_RASTER
+	if (x0 == 123.456f) o.tile_touched[0] = 1u;
+	return;
+#endif
 	Setup s;
 	if (!setup_triangle(x0, y0, x1, y1, x2, y2, z0, z1, z2, fp.W, fp.y_lo, fp.y_hi, s)) return;
 	const int bw = s.X1 - s.X0, bh = s.Y1 - s.Y0;
 	if (bw <= SMALL_DIM && bh <= SMALL_DIM && bw * bh <= SMALL_AREA) {
 		cnt.small++;
+		bool any = false;
 		for_each_covered(s, s.X0, s.X1, s.Y0, s.Y1, [&](int px, int py, float c0, float c1, float c2) {
 			float al, be, ga;
 			const float z = interp_z(s, c0, c1, c2, al, be, ga);
 			if (!z_draws(z)) return;
 			atomicMin(o.vis + (size_t)py * fp.W + px, make_key(z, ordinal));  // result unused -> RED.MIN.64, fire and forget
-			o.tile_touched[(py / GT) * fp.ntx + (px / GT)] = 1u;
+			any = true;
 		});
+		if (any) {
+			const int tx0 = s.X0 / GT, ty0 = s.Y0 / GT, tx1 = (s.X1 - 1) / GT, ty1 = (s.Y1 - 1) / GT;  // box <= 8x8 px: at most 2x2 tiles
+			if (touched && fp.ntx <= 256 && fp.nty <= 256) {
+				*touched = (unsigned)tx0 | ((unsigned)ty0 << 8) | ((unsigned)tx1 << 16) | ((unsigned)ty1 << 24);
+			} else {
+				for (int ty = ty0; ty <= ty1; ++ty)
+					for (int tx = tx0; tx <= tx1; ++tx) touch_tile(fp, o, tx, ty);
+			}
+		}
 		return;
 	}
 	cnt.binned++;
@@ -172,7 +197,7 @@ __device__ __noinline__ void setup_clipped_face(const FrameParams& fp, const Set
 		to_screen(out[j + 1].clip, fW, fH, x1, y1, z1);
 		to_screen(out[j + 2].clip, fW, fH, x2, y2, z2);
 		if (is_backface(x0, y0, x1, y1, x2, y2)) continue;
-		emit_triangle(fp, o, x0, y0, x1, y1, x2, y2, z0, z1, z2, face * 8u + (unsigned)(j / 3), cnt);
+		emit_triangle(fp, o, x0, y0, x1, y1, x2, y2, z0, z1, z2, face * 8u + (unsigned)(j / 3), cnt, nullptr);
 	}
 }
 
@@ -211,8 +236,10 @@ __global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(
 	}
 	EmitCounters cnt = {0, 0, 0};
 	unsigned clipped = 0;
+	unsigned touched[SETUP_FPT];
 #pragma unroll
 	for (int k = 0; k < SETUP_FPT; ++k) {
+		touched[k] = 0xFFFFFFFFu;
 		const unsigned long long f = base + (unsigned long long)k * SETUP_THREADS;
 		if (f >= mesh.n_faces) continue;
 		const float4 s0 = s[k][0], s1 = s[k][1], s2 = s[k][2];
@@ -220,12 +247,25 @@ __global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(
 		if (((k0 | k1 | k2) & 0x3fu) == 0) {
 			// every vertex inside every plane: clipTriangle returns the triangle unchanged (reference src/pipeline.cpp:322-325)
 			if (!is_backface(s0.x, s0.y, s1.x, s1.y, s2.x, s2.y))
-				emit_triangle(fp, o, s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, (unsigned)f * 8u, cnt);
+				emit_triangle(fp, o, s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, (unsigned)f * 8u, cnt, &touched[k]);
 		} else if ((k0 & k1 & k2) >> 8) {
 			// all three vertices safely outside one plane: clipTriangle returns nothing (see clip_code_safe_out)
 		} else {
 			clipped++;
 			setup_clipped_face(fp, o, mvp, __ldg(mesh.pos + vi[k][0]), __ldg(mesh.pos + vi[k][1]), __ldg(mesh.pos + vi[k][2]), (unsigned)f, cnt);
+		}
+	}
+	// tile flags of the direct path, warp-aggregated: consecutive faces of a mesh land in the same one or two tiles, so one
+	// lane per distinct tile rect does the test-and-set (correct for any input; merely slower when faces are scattered)
+	__syncwarp();
+#pragma unroll
+	for (int k = 0; k < SETUP_FPT; ++k) {
+		const unsigned t = touched[k];
+		const unsigned peers = __match_any_sync(0xffffffffu, t);
+		if (t != 0xFFFFFFFFu && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) {
+			const int tx0 = t & 255, ty0 = (t >> 8) & 255, tx1 = (t >> 16) & 255, ty1 = t >> 24;
+			for (int ty = ty0; ty <= ty1; ++ty)
+				for (int tx = tx0; tx <= tx1; ++tx) touch_tile(fp, o, tx, ty);
 		}
 	}
 #ifndef AXR_NO_STATS
@@ -245,19 +285,36 @@ __global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(
 }
 
 // ------------------------------------------------------------------------------------------------ bins: scan + scatter
-// Block-wide exclusive prefix sum over the per-tile counts (one CTA of 1024 threads, chunked).
+// Block-wide exclusive prefix sum over the per-tile counts (one CTA of 1024 threads, 8 tiles per thread per round).
 // On exit: bin_start[0..n] holds offsets, tile_count[] is zeroed so k_bin_scatter can reuse it as the fill cursor.
-__global__ void __launch_bounds__(1024) k_scan_tiles(unsigned* tile_count, unsigned* bin_start, int n, unsigned ref_cap,
-                                                     const unsigned* n_records, unsigned rec_cap, DrawStatus* status) {
+// With no binned records at all (every triangle was rasterised by its own setup thread) only the counters are folded.
+constexpr int SCAN_THREADS = 1024, SCAN_PER_THREAD = 8;
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(unsigned* tile_count, unsigned* bin_start, int n, unsigned ref_cap,
+                                                             const unsigned* n_records, unsigned rec_cap, DrawStatus* status) {
 	__shared__ unsigned s_warp[32];
 	__shared__ unsigned s_carry;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	{  // fold the striped counters of k_setup_raster: warp w < 4 sums counter w
+		if (warp < 4) {
+			unsigned long long acc = 0;
+			for (int i = lane; i < STAT_STRIPES; i += 32) acc += status->stripes[warp][i];
+			for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+			if (lane == 0) (&status->clipped_faces)[warp] = acc;
+		}
+	}
+	const unsigned nrec = *n_records;
+	if (nrec == 0) {  // k_tile_shade does not read bin_start in this case
+		if (tid == 0) { status->bin_refs = 0; status->overflow = 0; }
+		return;
+	}
 	if (tid == 0) s_carry = 0;
 	__syncthreads();
-	for (int base = 0; base < n; base += 1024) {
-		int i = base + tid;
-		unsigned v = (i < n) ? tile_count[i] : 0u;
-		unsigned x = v;
+	for (int base = 0; base < n; base += SCAN_THREADS * SCAN_PER_THREAD) {
+		const int i0 = base + tid * SCAN_PER_THREAD;
+		unsigned v[SCAN_PER_THREAD], sum = 0;
+#pragma unroll
+		for (int k = 0; k < SCAN_PER_THREAD; ++k) { v[k] = (i0 + k < n) ? tile_count[i0 + k] : 0u; sum += v[k]; }
+		unsigned x = sum;
 		for (int d = 1; d < 32; d <<= 1) {
 			unsigned y = __shfl_up_sync(0xffffffffu, x, d);
 			if (lane >= d) x += y;
@@ -273,28 +330,21 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(unsigned* tile_count, unsig
 			s_warp[lane] = w;
 		}
 		__syncthreads();
-		unsigned carry = s_carry;
-		unsigned excl = carry + (warp ? s_warp[warp - 1] : 0u) + (x - v);
-		if (i < n) { bin_start[i] = excl; tile_count[i] = 0u; }
+		const unsigned carry = s_carry;
+		unsigned excl = carry + (warp ? s_warp[warp - 1] : 0u) + (x - sum);
+#pragma unroll
+		for (int k = 0; k < SCAN_PER_THREAD; ++k)
+			if (i0 + k < n) { bin_start[i0 + k] = excl; tile_count[i0 + k] = 0u; excl += v[k]; }
 		__syncthreads();
-		if (tid == 1023) s_carry = carry + s_warp[31];
+		if (tid == SCAN_THREADS - 1) s_carry = carry + s_warp[31];
 		__syncthreads();
-	}
-	{  // fold the striped counters of k_setup_raster: warp w < 4 sums counter w
-		const int c = tid >> 5;
-		if (c < 4) {
-			unsigned long long acc = 0;
-			for (int i = lane; i < STAT_STRIPES; i += 32) acc += status->stripes[c][i];
-			for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
-			if (lane == 0) (&status->clipped_faces)[c] = acc;
-		}
 	}
 	if (tid == 0) {
 		unsigned total = s_carry;
 		bin_start[n] = total;
 		status->bin_refs = total;
 		unsigned ovf = 0;
-		if (*n_records > rec_cap) ovf |= 1u;
+		if (nrec > rec_cap) ovf |= 1u;
 		if (total > ref_cap) ovf |= 2u;
 		status->overflow = ovf;
 	}
