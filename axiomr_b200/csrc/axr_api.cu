@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -81,7 +82,8 @@ struct axr_ctx {
 	unsigned rec_cap = 0;
 	unsigned* n_records = nullptr;
 	DrawStatus* d_status = nullptr;
-	DrawStatus* h_status = nullptr;  // pinned
+	DrawStatus* h_status = nullptr;      // pinned + mapped: written by k_scan_tiles
+	DrawStatus* h_status_dev = nullptr;  // device-side alias of h_status
 	cudaEvent_t status_event = nullptr;
 	PendingDraw pending;
 	axr_stats stats{};
@@ -166,7 +168,9 @@ int check_pending(axr_ctx* ctx) {
 	CU(cudaEventSynchronize(ctx->status_event));
 	PendingDraw p = ctx->pending;
 	ctx->pending.valid = false;
-	const DrawStatus st = *ctx->h_status;
+	struct { unsigned long long clipped_faces, triangles, small_triangles, binned_triangles, bin_refs; unsigned overflow, pad; } st;
+	static_assert(sizeof(st) == 48 && offsetof(DrawStatus, stripes) == 48, "status head layout");
+	memcpy(&st, ctx->h_status, sizeof st);
 	ctx->stats.clipped_faces = st.clipped_faces;
 	ctx->stats.triangles = st.triangles;
 	ctx->stats.small_triangles = st.small_triangles;
@@ -235,11 +239,12 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model) {
 
 	cudaStream_t s = ctx->stream;
 	uint64_t launches = 0;
-	CU(cudaMemsetAsync(ctx->d_status, 0, sizeof(DrawStatus), s));
-	CU(cudaMemsetAsync(ctx->n_records, 0, sizeof(unsigned), s));
 	prof_mark(ctx);
-	if (m.n_verts) {
-		k_vertex_xform<<<(unsigned)((m.n_verts + 255) / 256), 256, 0, s>>>(m.pos, m.n_verts, u.mvp, (float)ctx->fp.W, (float)ctx->fp.H, m.sv);
+	{
+		// at least sizeof(DrawStatus)/4 threads: the kernel also zeroes the draw's counters
+		const unsigned long long threads = m.n_verts > sizeof(DrawStatus) / 4 ? m.n_verts : sizeof(DrawStatus) / 4;
+		k_vertex_xform<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(m.pos, m.n_verts, u.mvp, (float)ctx->fp.W, (float)ctx->fp.H, m.sv,
+		                                                                ctx->d_status, ctx->n_records);
 		++launches;
 	}
 	prof_mark(ctx);
@@ -252,11 +257,11 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model) {
 		++launches;
 	}
 	prof_mark(ctx);
-	k_scan_tiles<<<1, 1024, 0, s>>>(ctx->tile_count, ctx->bin_start, n_tiles(ctx), ctx->ref_cap, ctx->n_records, ctx->rec_cap, ctx->d_status);
+	k_scan_tiles<<<1, SCAN_THREADS, 0, s>>>(ctx->tile_count, ctx->bin_start, n_tiles(ctx), ctx->ref_cap, ctx->n_records, ctx->rec_cap, ctx->d_status,
+	                                       ctx->h_status_dev);
 	++launches;
 	prof_mark(ctx);
-	CU(cudaMemcpyAsync(ctx->h_status, ctx->d_status, offsetof(DrawStatus, stripes), cudaMemcpyDeviceToHost, s));
-	CU(cudaEventRecord(ctx->status_event, s));
+	CU(cudaEventRecord(ctx->status_event, s));  // the scan kernel has stored the status into mapped host memory
 	k_bin_scatter<<<148 * 4, 256, 0, s>>>(ctx->records, ctx->n_records, ctx->fp, ctx->bin_start, ctx->tile_count, ctx->items, ctx->d_status);
 	++launches;
 	prof_mark(ctx);
@@ -351,7 +356,8 @@ int axr_create(const axr_config* cfg, axr_ctx** out) {
 	CUC(cudaMalloc(&c->bin_start, (nt + 1) * 4));
 	CUC(cudaMalloc(&c->n_records, 4));
 	CUC(cudaMalloc(&c->d_status, sizeof(DrawStatus)));
-	CUC(cudaMallocHost(&c->h_status, sizeof(DrawStatus)));
+	CUC(cudaHostAlloc(&c->h_status, 64, cudaHostAllocMapped));
+	CUC(cudaHostGetDevicePointer(&c->h_status_dev, c->h_status, 0));
 	CUC(cudaEventCreateWithFlags(&c->status_event, cudaEventDisableTiming));
 	c->rec_cap = 1u << 18; c->ref_cap = 1u << 20;
 	CUC(cudaMalloc(&c->records, (size_t)c->rec_cap * sizeof(TriRecord)));

@@ -99,9 +99,13 @@ __global__ void k_split_vertices(const float* __restrict__ raw, unsigned long lo
 
 // ------------------------------------------------------------------------------------------------ vertex stage
 // reference src/tiled_pipeline.cpp:210-212 (mvp * vec4(pos,1)) + :57-66 (perspective divide), once per unique vertex
+// It also zeroes the draw's device counters (k_setup_raster, the next kernel on the stream, is their first user), which
+// saves two memset nodes per draw.
 __global__ void __launch_bounds__(256) k_vertex_xform(const float4* __restrict__ pos, unsigned long long n, m4 mvp, float fW,
-                                                      float fH, float4* __restrict__ sv) {
+                                                      float fH, float4* __restrict__ sv, DrawStatus* status, unsigned* n_records) {
 	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < sizeof(DrawStatus) / 4) reinterpret_cast<unsigned*>(status)[i] = 0u;
+	if (i == 0) *n_records = 0u;
 	if (i >= n) return;
 	float4 p = __ldg(pos + i);
 	v4 c = mul(mvp, V4(p.x, p.y, p.z, 1.0f));
@@ -289,8 +293,16 @@ __global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(
 // On exit: bin_start[0..n] holds offsets, tile_count[] is zeroed so k_bin_scatter can reuse it as the fill cursor.
 // With no binned records at all (every triangle was rasterised by its own setup thread) only the counters are folded.
 constexpr int SCAN_THREADS = 1024, SCAN_PER_THREAD = 8;
+// The draw's counters go to the host through mapped pinned memory (plain stores over PCIe): a cudaMemcpyAsync between the
+// kernels would put a copy-engine operation, i.e. a bubble of ~10 us, into the middle of every draw.
+__device__ __forceinline__ void publish_status(const DrawStatus* d, DrawStatus* h) {
+	volatile unsigned long long* hv = reinterpret_cast<volatile unsigned long long*>(h);
+	const volatile unsigned long long* dv = reinterpret_cast<const volatile unsigned long long*>(d);
+	for (int i = 0; i < 6; ++i) hv[i] = dv[i];  // clipped_faces, triangles, small, binned, bin_refs, {overflow, pad}
+	__threadfence_system();
+}
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(unsigned* tile_count, unsigned* bin_start, int n, unsigned ref_cap,
-                                                             const unsigned* n_records, unsigned rec_cap, DrawStatus* status) {
+                                                             const unsigned* n_records, unsigned rec_cap, DrawStatus* status, DrawStatus* host_status) {
 	__shared__ unsigned s_warp[32];
 	__shared__ unsigned s_carry;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -304,7 +316,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(unsigned* tile_coun
 	}
 	const unsigned nrec = *n_records;
 	if (nrec == 0) {  // k_tile_shade does not read bin_start in this case
-		if (tid == 0) { status->bin_refs = 0; status->overflow = 0; }
+		__syncthreads();
+		if (tid == 0) {
+			status->bin_refs = 0; status->overflow = 0;
+			publish_status(status, host_status);
+		}
 		return;
 	}
 	if (tid == 0) s_carry = 0;
@@ -347,6 +363,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(unsigned* tile_coun
 		if (nrec > rec_cap) ovf |= 1u;
 		if (total > ref_cap) ovf |= 2u;
 		status->overflow = ovf;
+		__threadfence();
+		publish_status(status, host_status);
 	}
 }
 
@@ -566,8 +584,9 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 		__syncthreads();
 	}
 	// 3. deferred shading of the visible triangle of each pixel + framebuffer resolve (one warp = one 128 B row segment).
-	//    The index fetches of a thread's four pixels are issued together so their latency is paid once.
 	constexpr int PPT = GT_PIX / TILE_THREADS;
+#ifdef AXR_TILE_PREFETCH
+	//    The index fetches of a thread's four pixels are issued together so their latency is paid once.
 	unsigned ord[PPT], vi[PPT][3];
 #pragma unroll
 	for (int i = 0; i < PPT; ++i) {
@@ -584,6 +603,20 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 		const int p = tid + i * TILE_THREADS;
 		shade_pixel<Shader>(mesh, u, fp, in, ord[i], vi[i][0], vi[i][1], vi[i][2], x0 + (p & (GT - 1)), y0 + (p / GT));
 	}
+#else
+	//    Not unrolled: one copy of the shading code keeps the kernel inside the instruction cache (unrolled x4 with prefetched
+	//    indices: +12 % time; prefetched indices selected inside a rolled loop: +2 %).
+#pragma unroll 1
+	for (int i = 0; i < PPT; ++i) {
+		const int p = tid + i * TILE_THREADS;
+		const unsigned long long k = s_keys[p];
+		if (k == KEY_EMPTY) continue;
+		const unsigned ord = (unsigned)(k & 0xFFFFFFFFull);
+		const unsigned* ip = mesh.idx + (size_t)(ord >> 3) * 3;
+		const unsigned i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
+		shade_pixel<Shader>(mesh, u, fp, in, ord, i0, i1, i2, x0 + (p & (GT - 1)), y0 + (p / GT));
+	}
+#endif
 }
 
 }  // namespace axr
