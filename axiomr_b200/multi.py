@@ -89,28 +89,43 @@ def framebuffer_tensors(dev):
 
 
 class Compositor:
-    """Gathers every rank's finished region to GPU 0 after each frame (the path's one exchange step)."""
+    """Gathers every rank's finished region to GPU 0 after each frame (the path's one exchange step).
 
-    def __init__(self, dev, rank: int, world: int, mode: str, band, stream, transport: str = "nccl"):
+    views : rank r > 0 renders alternately into two private output buffers (axr_set_output); when a frame is finished its
+            colour + depth go to GPU 0 with NCCL send/recv on a separate stream while the next frame is being rendered into the
+            other buffer (rank 0 receives into double-buffered slots; its own view stays in its framebuffer).
+    bands : transport "peer" (default): every rank maps GPU 0's framebuffer through CUDA IPC and its clear / resolve stores go
+            straight into its own rows there over NVLink — the composite is fused into the tile kernel, rows are disjoint, no
+            per-frame synchronisation. transport "nccl": in-place grouped send/recv of the row ranges after each frame.
+    """
+
+    def __init__(self, dev, rank: int, world: int, mode: str, band, stream, transport: str | None = None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.dev, self.rank, self.world, self.mode, self.stream = dev, rank, world, mode, stream
-        self.transport = transport
+        self.transport = transport or ("peer" if mode == "bands" else "nccl")
         self.launches_per_step = 0
         self.color, self.depth = framebuffer_tensors(dev)
-        self.slots = None
+        self.step = 0
         if mode == "views":
-            if rank == 0:  # slot r receives rank r's frame; slot 0 is rank 0's own framebuffer (no copy)
-                self.slots = (torch.empty((world - 1, dev.height, dev.width), dtype=torch.int32, device=self.color.device),
-                              torch.empty((world - 1, dev.height, dev.width), dtype=torch.float32, device=self.color.device))
+            dv = self.color.device
+            self.comm = torch.cuda.Stream(device=dv)
+            self.done = [None, None]   # comm-stream events: buffer b has been sent / slot set b has been filled
+            shape = (dev.height, dev.width)
+            if rank == 0:
+                self.slots = [(torch.empty((world - 1,) + shape, dtype=torch.int32, device=dv),
+                               torch.empty((world - 1,) + shape, dtype=torch.float32, device=dv)) for _ in range(2)]
+            else:
+                self.bufs = [(torch.empty(shape, dtype=torch.int32, device=dv), torch.empty(shape, dtype=torch.float32, device=dv))
+                             for _ in range(2)]
         else:
             self.bands = band_rows(dev.height, world)
-            if transport == "peer":
+            if self.transport == "peer":
                 self._setup_peer()
 
     def _setup_peer(self):
-        """bands + peer: every rank r>0 maps GPU 0's framebuffer (CUDA IPC) and redirects its resolve stores there."""
+        """bands + peer: every rank r>0 maps GPU 0's framebuffer (CUDA IPC) and redirects its clear / resolve stores there."""
         dist = self.dist
         handles = [None]
         if self.rank == 0:
@@ -120,13 +135,40 @@ class Compositor:
             ch, dh = handles[0]
             self._peer = (self.dev.open_ipc(ch), self.dev.open_ipc(dh))
             self.dev.set_output(*self._peer)
+        dist.barrier()
+
+    def begin_step(self):
+        """Call before the frame's clear: selects the output buffer of this frame (views, rank > 0)."""
+        if self.mode == "views" and self.rank != 0:
+            b = self.step % 2
+            if self.done[b] is not None:
+                self.stream.wait_event(self.done[b])      # the send of the frame rendered two steps ago has finished
+            c, d = self.bufs[b]
+            self.dev.set_output(c.data_ptr(), d.data_ptr())
 
     def composite(self):
         torch, dist = self.torch, self.dist
-        if self.mode == "bands" and self.transport == "peer":
-            return  # the tile kernel already stored this rank's band into GPU 0's framebuffer over NVLink
-        with torch.cuda.stream(self.stream):
-            if self.mode == "views":
-                self.slots = gather_views(self.color, self.depth, self.rank, self.world, dist, self.slots)
-            else:
+        b = self.step % 2
+        self.step += 1
+        if self.mode == "bands":
+            if self.transport == "peer":
+                return  # the tile kernel already stored this rank's band into GPU 0's framebuffer over NVLink
+            with torch.cuda.stream(self.stream):
                 gather_bands(self.color, self.depth, self.bands, self.rank, dist)
+            return
+        ready = torch.cuda.Event()
+        ready.record(self.stream)                         # this frame is rendered
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(ready)
+            if self.rank == 0:
+                gather_views(None, None, 0, self.world, dist, self.slots[b])
+            else:
+                gather_views(self.bufs[b][0], self.bufs[b][1], self.rank, self.world, dist)
+            ev = torch.cuda.Event()
+            ev.record(self.comm)
+            self.done[b] = ev
+
+    def finish(self):
+        """Make the render stream wait for every outstanding transfer (call before the closing synchronisation)."""
+        if self.mode == "views":
+            self.stream.wait_stream(self.comm)

@@ -249,12 +249,16 @@ def main():
     comp = multi.Compositor(dev, rank, world, args.mode, band, stream) if world > 1 else None
 
     def step():
+        if comp:
+            comp.begin_step()
         dev.clear(0xFF000000, float("inf"))
         dev.draw_mesh(mesh, sc.model)
         if comp:
             comp.composite()
 
     def barrier():
+        if comp:
+            comp.finish()
         dev.sync()
         torch.cuda.synchronize()
         if dist:
@@ -275,6 +279,8 @@ def main():
     e0.record(stream)
     for _ in range(args.steps):
         step()
+    if comp:
+        comp.finish()
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -322,9 +328,11 @@ def main():
                        "l2": "working set (mesh %.0f MB + textures + 8 B/px keys + framebuffer) exceeds the 126 MB L2; no explicit flush"
                              % ((sc.vertices.nbytes + sc.indices.nbytes) / 1e6),
                        "parallelism": ("1 GPU" if world == 1 else f"{args.mode} x{world}: " +
-                                       ("one camera view of the replicated scene per GPU, finished frames gathered to GPU 0 over NCCL"
+                                       ("one camera view of the replicated scene per GPU; every finished frame (colour + depth, 8 B/px) is gathered to "
+                                        "GPU 0 with NCCL send/recv on a second stream while the next frame renders (double-buffered)"
                                         if args.mode == "views" else
-                                        "16-px-aligned screen bands of one frame, replicated geometry stages, bands gathered to GPU 0 over NCCL")),
+                                        "16-px-aligned screen bands of one frame, replicated geometry stages; every rank's clear + resolve "
+                                        "stores go straight into GPU 0's framebuffer through a CUDA-IPC peer mapping over NVLink")),
                        "parity_mode": "nearest sampling == reference; bilinear is an extension checked against oracle/axr_oracle.c"},
             "gpu_launches": launches_per_step * args.steps,
             "kernel_ms": kavg, "draw_ms": draw_ms, "draw_stats": stats, "covered_pixels": covered,

@@ -285,3 +285,18 @@ def test_size_independent_properties_full_c3(po):
         assert np.count_nonzero(d1.view(np.uint32) != d3.view(np.uint32)) <= d1.size // 10000   # exact z ties between chunks only
     finally:
         dev.close()
+
+
+def test_multi_gpu_composites_match_single_gpu():
+    """bands (peer stores / NCCL) and views composites on GPU 0 == single-GPU renders. Needs >= 2 GPUs (skipped otherwise)."""
+    import subprocess
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n = 2 if n < 4 else 4
+    here = _os.path.dirname(_os.path.abspath(__file__))
+    r = subprocess.run([_sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+                        "--master-port", "29577", _os.path.join(here, "multi_gpu_check.py")], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0 and "MULTI_GPU_CHECK OK" in r.stdout
