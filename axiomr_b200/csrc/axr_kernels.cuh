@@ -240,34 +240,36 @@ __global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(
 	}
 	EmitCounters cnt = {0, 0, 0};
 	unsigned clipped = 0;
-	unsigned touched[SETUP_FPT];
-#pragma unroll
+	// One copy of the cull / setup / raster code, visited SETUP_FPT times (the loads above stay batched; the loop is NOT unrolled
+	// so that the register footprint, hence occupancy, is that of a single face).
+#pragma unroll 1
 	for (int k = 0; k < SETUP_FPT; ++k) {
-		touched[k] = 0xFFFFFFFFu;
 		const unsigned long long f = base + (unsigned long long)k * SETUP_THREADS;
-		if (f >= mesh.n_faces) continue;
-		const float4 s0 = s[k][0], s1 = s[k][1], s2 = s[k][2];
-		const unsigned k0 = __float_as_uint(s0.w), k1 = __float_as_uint(s1.w), k2 = __float_as_uint(s2.w);
-		if (((k0 | k1 | k2) & 0x3fu) == 0) {
-			// every vertex inside every plane: clipTriangle returns the triangle unchanged (reference src/pipeline.cpp:322-325)
-			if (!is_backface(s0.x, s0.y, s1.x, s1.y, s2.x, s2.y))
-				emit_triangle(fp, o, s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, (unsigned)f * 8u, cnt, &touched[k]);
-		} else if ((k0 & k1 & k2) >> 8) {
-			// all three vertices safely outside one plane: clipTriangle returns nothing (see clip_code_safe_out)
-		} else {
-			clipped++;
-			setup_clipped_face(fp, o, mvp, __ldg(mesh.pos + vi[k][0]), __ldg(mesh.pos + vi[k][1]), __ldg(mesh.pos + vi[k][2]), (unsigned)f, cnt);
-		}
-	}
-	// tile flags of the direct path, warp-aggregated: consecutive faces of a mesh land in the same one or two tiles, so one
-	// lane per distinct tile rect does the test-and-set (correct for any input; merely slower when faces are scattered)
-	__syncwarp();
+		float4 s0 = s[0][0], s1 = s[0][1], s2 = s[0][2];
+		unsigned i0 = vi[0][0], i1 = vi[0][1], i2 = vi[0][2];
 #pragma unroll
-	for (int k = 0; k < SETUP_FPT; ++k) {
-		const unsigned t = touched[k];
-		const unsigned peers = __match_any_sync(0xffffffffu, t);
-		if (t != 0xFFFFFFFFu && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) {
-			const int tx0 = t & 255, ty0 = (t >> 8) & 255, tx1 = (t >> 16) & 255, ty1 = t >> 24;
+		for (int j = 1; j < SETUP_FPT; ++j)
+			if (k == j) { s0 = s[j][0]; s1 = s[j][1]; s2 = s[j][2]; i0 = vi[j][0]; i1 = vi[j][1]; i2 = vi[j][2]; }
+		unsigned touched = 0xFFFFFFFFu;
+		if (f < mesh.n_faces) {
+			const unsigned k0 = __float_as_uint(s0.w), k1 = __float_as_uint(s1.w), k2 = __float_as_uint(s2.w);
+			if (((k0 | k1 | k2) & 0x3fu) == 0) {
+				// every vertex inside every plane: clipTriangle returns the triangle unchanged (reference src/pipeline.cpp:322-325)
+				if (!is_backface(s0.x, s0.y, s1.x, s1.y, s2.x, s2.y))
+					emit_triangle(fp, o, s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, (unsigned)f * 8u, cnt, &touched);
+			} else if ((k0 & k1 & k2) >> 8) {
+				// all three vertices safely outside one plane: clipTriangle returns nothing (see clip_code_safe_out)
+			} else {
+				clipped++;
+				setup_clipped_face(fp, o, mvp, __ldg(mesh.pos + i0), __ldg(mesh.pos + i1), __ldg(mesh.pos + i2), (unsigned)f, cnt);
+			}
+		}
+		// tile flags of the direct path, warp-aggregated: consecutive faces of a mesh land in the same one or two tiles, so one
+		// lane per distinct tile rect does the test-and-set (correct for any input; merely slower when faces are scattered)
+		__syncwarp();
+		const unsigned peers = __match_any_sync(0xffffffffu, touched);
+		if (touched != 0xFFFFFFFFu && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) {
+			const int tx0 = touched & 255, ty0 = (touched >> 8) & 255, tx1 = (touched >> 16) & 255, ty1 = touched >> 24;
 			for (int ty = ty0; ty <= ty1; ++ty)
 				for (int tx = tx0; tx <= tx1; ++tx) touch_tile(fp, o, tx, ty);
 		}

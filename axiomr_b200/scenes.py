@@ -158,8 +158,9 @@ def icosphere(level: int, radius: float = 2.0):
         nf = faces.shape[0]
         m01, m12, m20 = nv + inv[:nf], nv + inv[nf:2 * nf], nv + inv[2 * nf:]
         a, b, c = faces[:, 0], faces[:, 1], faces[:, 2]
-        faces = np.concatenate([np.stack([a, m01, m20], 1), np.stack([b, m12, m01], 1),
-                                np.stack([c, m20, m12], 1), np.stack([m01, m12, m20], 1)], axis=0)
+        # the four children of a face stay adjacent in the face list (the order a recursive subdivision produces)
+        faces = np.stack([np.stack([a, m01, m20], 1), np.stack([b, m12, m01], 1),
+                          np.stack([c, m20, m12], 1), np.stack([m01, m12, m20], 1)], axis=1).reshape(-1, 3)
     nrm = verts
     pos = verts * radius
     u = 0.5 + np.arctan2(nrm[:, 2], nrm[:, 0]) / (2 * math.pi)

@@ -201,11 +201,35 @@ def reference_arm(args):
         "e2e": {"value": v, "unit": "Mtri/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "frames_per_s_extrapolated": v * 1e6 / sc.n_faces,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ----------------------------------------------------------------------------------------------- B200 arm
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL's version banner, torchrun notices) write to fd 1; the contract is ONE JSON line on stdout.
+    Everything else goes to stderr, the JSON line is written to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -398,7 +422,7 @@ def main():
         except Exception as e:  # the checker being absent must not lose the GPU numbers
             line["cpu_baseline"] = {"value": None, "unit": "Mtri/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if dist:
         dist.barrier()
         dist.destroy_process_group()

@@ -37,5 +37,6 @@ for name, path in libs.items():
     wall = (time.perf_counter() - t) / n * 1e3
     ms, draws = dev.kernel_times()
     k = {a: round(b / draws * 1e3) for a, b in ms.items()}
-    print(f"{name:10s} wall {wall:.3f} ms  kernels(us) {k} sum {sum(k.values())}", flush=True)
+    st = dev.stats()
+    print(f"{name:10s} wall {wall:.3f} ms  kernels(us) {k} sum {sum(k.values())}  tris {st['triangles']} small {st['small_triangles']} binned {st['binned_triangles']} refs {st['bin_refs']}", flush=True)
     dev.close()
