@@ -171,9 +171,9 @@ int axr_ref_render(const axr_ref_scene* sc, const float* vertices, uint64_t n_ve
 		mesh.m_Materials["m0"] = std::move(mat);
 
 		const glm::mat4 model = to_mat4(sc->model);
-		const uint64_t chunk = (uint64_t)std::max(1, sc->chunk_faces);
+		uint64_t chunk = (uint64_t)std::max(1, sc->chunk_faces);
 		double secs = 0.0;
-		for (uint64_t f0 = 0; f0 < n_faces; f0 += chunk) {
+		for (uint64_t f0 = 0; f0 < n_faces;) {
 			const uint64_t n = std::min(chunk, n_faces - f0);
 			mesh.m_Faces.resize(n);
 			for (uint64_t i = 0; i < n; ++i) {
@@ -183,8 +183,21 @@ int axr_ref_render(const axr_ref_scene* sc, const float* vertices, uint64_t n_ve
 			mesh.m_MaterialGroups.clear();
 			mesh.m_MaterialGroups.push_back({"m0", 0, (size_t)n});
 			auto t0 = std::chrono::steady_clock::now();
-			pipe->drawMesh(model, mesh);
+			try {
+				pipe->drawMesh(model, mesh);
+			} catch (const std::bad_alloc&) {
+				// The 16 MB triangle arena (include/tiled_pipeline.hpp:98-104) overflowed: how many post-cull triangles fit depends
+				// on the thread count and on how many faces of the chunk survive culling. The throw happens while m_Triangles is
+				// being assembled, before anything is rasterised or merged, so the chunk can be redrawn: fresh pipeline (the
+				// monotonic arena never gives memory back), half the chunk. Time of the failed attempt is not counted.
+				if (chunk == 1) throw;
+				chunk = std::max<uint64_t>(1, chunk / 2);
+				pipe.reset(new AR::TiledPipeline((size_t)std::max(1, sc->threads), &cam, &fb));
+				pipe->setShader(shader);
+				continue;
+			}
 			secs += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+			f0 += n;
 		}
 		std::memcpy(color_inout, fb.getColorData(), (size_t)W * H * 4);
 		std::memcpy(depth_inout, fb.getDepthData(), (size_t)W * H * sizeof(float));
