@@ -96,6 +96,8 @@ struct axr_ctx {
 	std::vector<DeviceMesh> meshes;
 	std::vector<DeviceTexture> textures;
 	std::vector<void*> ipc_opened;
+	std::vector<void*> shared_allocs;
+	int read_depth = 1;
 };
 
 namespace {
@@ -268,7 +270,7 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model) {
 	TileIn in;
 	in.vis = ctx->vis; in.tile_touched = ctx->tile_touched; in.tile_cursor = ctx->tile_count; in.bin_start = ctx->bin_start;
 	in.items = ctx->items; in.records = ctx->records; in.n_records = ctx->n_records; in.status = ctx->d_status; in.sv = m.sv;
-	in.color = ctx->out_color; in.depth = ctx->out_depth;
+	in.color = ctx->out_color; in.depth = ctx->out_depth; in.read_depth = ctx->read_depth;
 	switch (ctx->shader_kind) {
 	case AXR_SHADER_FLAT: launch_tile<FlatShader>(ctx, mv, u, in); break;
 	case AXR_SHADER_PHONG: launch_tile<PhongShader>(ctx, mv, u, in); break;
@@ -377,6 +379,7 @@ void axr_destroy(axr_ctx* ctx) {
 	for (auto& m : ctx->meshes) if (m.live) { cudaFree(m.pos); cudaFree(m.attr); cudaFree(m.idx); cudaFree(m.sv); cudaFree(m.d_materials); cudaFree(m.d_group_first); }
 	for (auto& t : ctx->textures) if (t.live) cudaFree(t.data);
 	for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
+	for (void* p : ctx->shared_allocs) cudaFree(p);
 	cudaFree(ctx->color); cudaFree(ctx->depth); cudaFree(ctx->vis); cudaFree(ctx->tile_touched); cudaFree(ctx->tile_count);
 	cudaFree(ctx->bin_start); cudaFree(ctx->items); cudaFree(ctx->records); cudaFree(ctx->n_records); cudaFree(ctx->d_status);
 	if (ctx->h_status) cudaFreeHost(ctx->h_status);
@@ -655,6 +658,39 @@ int axr_set_output(axr_ctx* ctx, void* bgra_dev, void* depth_dev) {
 	ctx->out_color = bgra_dev ? (unsigned*)bgra_dev : ctx->color;
 	ctx->out_depth = depth_dev ? (float*)depth_dev : ctx->depth;
 	return AXR_OK;
+}
+
+int axr_set_depth_read(axr_ctx* ctx, int enabled) {
+	if (!ctx) return AXR_ERR_INVALID;
+	int rc = check_pending(ctx);
+	if (rc) return rc;
+	ctx->read_depth = enabled ? 1 : 0;
+	return AXR_OK;
+}
+
+int axr_alloc_shared(axr_ctx* ctx, size_t bytes, void** dev_ptr_out, void* handle64_out) {
+	if (!ctx || !dev_ptr_out || !handle64_out || bytes == 0) return AXR_ERR_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	void* p = nullptr;
+	CU(cudaMalloc(&p, bytes));
+	cudaError_t e = cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64_out, p);
+	if (e != cudaSuccess) { cudaFree(p); return fail(ctx, AXR_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+	ctx->shared_allocs.push_back(p);
+	*dev_ptr_out = p;
+	return AXR_OK;
+}
+
+int axr_free_shared(axr_ctx* ctx, void* dev_ptr) {
+	if (!ctx || !dev_ptr) return AXR_ERR_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	for (size_t i = 0; i < ctx->shared_allocs.size(); ++i)
+		if (ctx->shared_allocs[i] == dev_ptr) {
+			CU(cudaDeviceSynchronize());
+			CU(cudaFree(dev_ptr));
+			ctx->shared_allocs.erase(ctx->shared_allocs.begin() + i);
+			return AXR_OK;
+		}
+	return fail(ctx, AXR_ERR_INVALID, "axr_free_shared: pointer was not allocated by this context");
 }
 
 int axr_framebuffer_ipc(axr_ctx* ctx, void* color_handle64, void* depth_handle64) {

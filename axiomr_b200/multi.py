@@ -91,12 +91,16 @@ def framebuffer_tensors(dev):
 class Compositor:
     """Gathers every rank's finished region to GPU 0 after each frame (the path's one exchange step).
 
-    views : rank r > 0 renders alternately into two private output buffers (axr_set_output); when a frame is finished its
-            colour + depth go to GPU 0 with NCCL send/recv on a separate stream while the next frame is being rendered into the
-            other buffer (rank 0 receives into double-buffered slots; its own view stays in its framebuffer).
-    bands : transport "peer" (default): every rank maps GPU 0's framebuffer through CUDA IPC and its clear / resolve stores go
-            straight into its own rows there over NVLink — the composite is fused into the tile kernel, rows are disjoint, no
-            per-frame synchronisation. transport "nccl": in-place grouped send/recv of the row ranges after each frame.
+    transport "peer" (default) — composite fused into the tile kernel over NVLink peer memory (CUDA IPC):
+      bands : every rank maps GPU 0's framebuffer; its clear and resolve stores go straight into its own rows there. Rows are
+              disjoint, so there is no per-frame synchronisation at all.
+      views : GPU 0 owns two sets of per-view slots (colour + depth). Rank r > 0 points its output at slot (set i%2, r): its tile
+              kernel stores the covered pixels of frame i directly into GPU 0's memory (no depth read-back: the slot is freshly
+              cleared, axr_set_depth_read(0)). GPU 0 clears the *other* set for frame i+1 on a side stream while everybody
+              renders; one tiny NCCL all-reduce per frame on the render streams orders "all stores of frame i are done"
+              before "the set is cleared again". Only covered pixels cross NVLink (≈ 25 MB instead of 66 MB per 4K view).
+    transport "nccl" — the baseline: grouped send/recv of whole regions after each frame (bands: in place; views:
+      double-buffered, on a second stream, overlapping the next frame).
     """
 
     def __init__(self, dev, rank: int, world: int, mode: str, band, stream, transport: str | None = None):
@@ -104,28 +108,31 @@ class Compositor:
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.dev, self.rank, self.world, self.mode, self.stream = dev, rank, world, mode, stream
-        self.transport = transport or ("peer" if mode == "bands" else "nccl")
+        self.transport = transport or "peer"
         self.launches_per_step = 0
         self.color, self.depth = framebuffer_tensors(dev)
         self.step = 0
-        if mode == "views":
-            dv = self.color.device
+        dv = self.color.device
+        self.H, self.W = dev.height, dev.width
+        if mode == "views" and self.transport == "nccl":
             self.comm = torch.cuda.Stream(device=dv)
             self.done = [None, None]   # comm-stream events: buffer b has been sent / slot set b has been filled
-            shape = (dev.height, dev.width)
+            shape = (self.H, self.W)
             if rank == 0:
                 self.slots = [(torch.empty((world - 1,) + shape, dtype=torch.int32, device=dv),
                                torch.empty((world - 1,) + shape, dtype=torch.float32, device=dv)) for _ in range(2)]
             else:
                 self.bufs = [(torch.empty(shape, dtype=torch.int32, device=dv), torch.empty(shape, dtype=torch.float32, device=dv))
                              for _ in range(2)]
+        elif mode == "views":
+            self._setup_peer_views()
         else:
             self.bands = band_rows(dev.height, world)
             if self.transport == "peer":
-                self._setup_peer()
+                self._setup_peer_bands()
 
-    def _setup_peer(self):
-        """bands + peer: every rank r>0 maps GPU 0's framebuffer (CUDA IPC) and redirects its clear / resolve stores there."""
+    # ------------------------------------------------------------------ bands
+    def _setup_peer_bands(self):
         dist = self.dist
         handles = [None]
         if self.rank == 0:
@@ -137,14 +144,74 @@ class Compositor:
             self.dev.set_output(*self._peer)
         dist.barrier()
 
+    # ------------------------------------------------------------------ views over peer memory
+    def _slot_offsets(self, b: int, r: int):
+        """Byte offsets of (colour, depth) of slot (set b, rank r) inside the shared allocation."""
+        npx = self.H * self.W
+        per_slot = npx * 8
+        base = ((b * (self.world - 1)) + (r - 1)) * per_slot
+        return base, base + npx * 4
+
+    def _setup_peer_views(self):
+        torch, dist = self.torch, self.dist
+        npx = self.H * self.W
+        total = 2 * (self.world - 1) * npx * 8
+        handles = [None]
+        if self.rank == 0:
+            self._shared_ptr, h = self.dev.alloc_shared(total)
+            handles = [h]
+        dist.broadcast_object_list(handles, src=0)
+        dv = self.color.device
+        self.token = torch.zeros(1, dtype=torch.int32, device=dv)
+        if self.rank == 0:
+            self.side = torch.cuda.Stream(device=dv)
+            self.slots = []
+            for b in range(2):
+                c0, _ = self._slot_offsets(b, 1)
+                # per set: (world-1) x [colour HxW int32 | depth HxW f32]; exposed as two strided views for readers
+                raw_i = torch.as_tensor(_DevArray(self._shared_ptr + c0, ((self.world - 1), 2, self.H, self.W), "<i4"), device=dv)
+                raw_f = torch.as_tensor(_DevArray(self._shared_ptr + c0, ((self.world - 1), 2, self.H, self.W), "<f4"), device=dv)
+                self.slots.append((raw_i[:, 0], raw_f[:, 1]))
+            for b in range(2):
+                self._clear_set(b)
+            torch.cuda.synchronize()
+        else:
+            self._shared_ptr = self.dev.open_ipc(handles[0])
+            self.dev.set_depth_read(False)
+        dist.barrier()
+
+    def _clear_set(self, b: int, packed_argb: int = -16777216):  # 0xFF000000 as int32
+        self.slots[b][0].fill_(packed_argb)
+        self.slots[b][1].fill_(float("inf"))
+
+    # ------------------------------------------------------------------ per frame
+    @property
+    def clears_own_target(self) -> bool:
+        """views over peer memory: the slot a rank renders into was cleared by GPU 0 already; the rank must not clear it."""
+        return not (self.mode == "views" and self.transport == "peer" and self.rank != 0)
+
     def begin_step(self):
-        """Call before the frame's clear: selects the output buffer of this frame (views, rank > 0)."""
-        if self.mode == "views" and self.rank != 0:
-            b = self.step % 2
-            if self.done[b] is not None:
-                self.stream.wait_event(self.done[b])      # the send of the frame rendered two steps ago has finished
-            c, d = self.bufs[b]
-            self.dev.set_output(c.data_ptr(), d.data_ptr())
+        """Call before the frame's clear: selects the output buffer of this frame."""
+        b = self.step % 2
+        if self.mode != "views":
+            return
+        if self.transport == "nccl":
+            if self.rank != 0:
+                if self.done[b] is not None:
+                    self.stream.wait_event(self.done[b])      # the send of the frame rendered two steps ago has finished
+                c, d = self.bufs[b]
+                self.dev.set_output(c.data_ptr(), d.data_ptr())
+            return
+        if self.rank != 0:
+            co, do = self._slot_offsets(b, self.rank)
+            self.dev.set_output(self._shared_ptr + co, self._shared_ptr + do)
+        else:
+            # clear the other set for the next frame while this one renders; ordered after the previous frame's all-reduce
+            ready = self.torch.cuda.Event()
+            ready.record(self.stream)
+            with self.torch.cuda.stream(self.side):
+                self.side.wait_event(ready)
+                self._clear_set((b + 1) % 2)
 
     def composite(self):
         torch, dist = self.torch, self.dist
@@ -155,6 +222,12 @@ class Compositor:
                 return  # the tile kernel already stored this rank's band into GPU 0's framebuffer over NVLink
             with torch.cuda.stream(self.stream):
                 gather_bands(self.color, self.depth, self.bands, self.rank, dist)
+            return
+        if self.transport == "peer":
+            with torch.cuda.stream(self.stream):
+                if self.rank == 0:
+                    self.stream.wait_stream(self.side)    # next frame's set is clear
+                dist.all_reduce(self.token)                # every rank's stores of this frame precede anything after it
             return
         ready = torch.cuda.Event()
         ready.record(self.stream)                         # this frame is rendered
@@ -170,5 +243,11 @@ class Compositor:
 
     def finish(self):
         """Make the render stream wait for every outstanding transfer (call before the closing synchronisation)."""
-        if self.mode == "views":
+        if self.mode == "views" and self.transport == "nccl":
             self.stream.wait_stream(self.comm)
+        elif self.mode == "views" and self.rank == 0:
+            self.stream.wait_stream(self.side)
+
+    def view_slot(self, b: int, r: int):
+        """(colour int32 HxW, depth f32 HxW) of rank r's frame in slot set b, on GPU 0."""
+        return self.slots[b][0][r - 1], self.slots[b][1][r - 1]

@@ -237,6 +237,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--mode", default="views", choices=["views", "bands"], help="multi-GPU sharding (N>1)")
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"], help="composite to GPU 0: fused peer stores or NCCL gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -270,12 +271,13 @@ def main():
     dev = api.Device(W, H, device=local, sampler=sc.sampler, band=band)
     mesh = dev.load_scene(sc)
     stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local))
-    comp = multi.Compositor(dev, rank, world, args.mode, band, stream) if world > 1 else None
+    comp = multi.Compositor(dev, rank, world, args.mode, band, stream, transport=args.transport) if world > 1 else None
 
     def step():
         if comp:
             comp.begin_step()
-        dev.clear(0xFF000000, float("inf"))
+        if not comp or comp.clears_own_target:
+            dev.clear(0xFF000000, float("inf"))
         dev.draw_mesh(mesh, sc.model)
         if comp:
             comp.composite()
@@ -352,8 +354,12 @@ def main():
                        "l2": "working set (mesh %.0f MB + textures + 8 B/px keys + framebuffer) exceeds the 126 MB L2; no explicit flush"
                              % ((sc.vertices.nbytes + sc.indices.nbytes) / 1e6),
                        "parallelism": ("1 GPU" if world == 1 else f"{args.mode} x{world}: " +
-                                       ("one camera view of the replicated scene per GPU; every finished frame (colour + depth, 8 B/px) is gathered to "
-                                        "GPU 0 with NCCL send/recv on a second stream while the next frame renders (double-buffered)"
+                                       (("one camera view of the replicated scene per GPU; the tile kernel of every rank stores its covered pixels "
+                                         "(colour + depth) straight into a per-view slot in GPU 0's memory through a CUDA-IPC peer mapping over "
+                                         "NVLink; GPU 0 clears the slots; one 4-byte NCCL all-reduce per frame orders frames"
+                                         if args.transport == "peer" else
+                                         "one camera view of the replicated scene per GPU; every finished frame (colour + depth, 8 B/px) is gathered to "
+                                         "GPU 0 with NCCL send/recv on a second stream while the next frame renders (double-buffered)")
                                         if args.mode == "views" else
                                         "16-px-aligned screen bands of one frame, replicated geometry stages; every rank's clear + resolve "
                                         "stores go straight into GPU 0's framebuffer through a CUDA-IPC peer mapping over NVLink")),

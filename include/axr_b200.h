@@ -152,6 +152,14 @@ int axr_framebuffer_device(axr_ctx* ctx, void** bgra_dev, void** depth_dev);  /*
 /* Redirect this context's band output into another allocation laid out as a full frame (e.g. GPU 0's framebuffer
  * mapped through CUDA IPC / peer access): the resolve stores then go straight over NVLink. NULL restores the own buffers. */
 int axr_set_output(axr_ctx* ctx, void* bgra_dev, void* depth_dev);
+/* The tile kernel reads the output depth for the reference's merge test `z < fbZ` (src/tiled_pipeline.cpp:1148-1156). When the
+ * caller guarantees that the output was just cleared to depth = +inf and receives exactly one draw (e.g. a per-view slot on
+ * another GPU, where that read would cross NVLink), the read can be turned off: every drawable z passes `z < +inf`.
+ * Default: enabled. */
+int axr_set_depth_read(axr_ctx* ctx, int enabled);
+/* Device memory that other processes can map (cudaMalloc + cudaIpcGetMemHandle): composite targets on GPU 0. */
+int axr_alloc_shared(axr_ctx* ctx, size_t bytes, void** dev_ptr_out, void* handle64_out);
+int axr_free_shared(axr_ctx* ctx, void* dev_ptr);
 /* CUDA IPC handles (64 bytes each) of the own framebuffer allocations, for one-process-per-GPU compositing. */
 int axr_framebuffer_ipc(axr_ctx* ctx, void* color_handle64, void* depth_handle64);
 int axr_open_ipc(axr_ctx* ctx, const void* handle64, void** dev_ptr_out);

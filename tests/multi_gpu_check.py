@@ -54,34 +54,38 @@ for transport in ("peer", "nccl"):
         dev.set_output(None, None)
     dev.close()
 # ---- views
-sc = S.Scene("t", W, H, v, f, S.SHADER_PHONG, model=base.model, textures=base.textures)
-sc.view_proj, sc.cam_pos = S.view_matrix_for(rank, 8, W, H)
-dev = api.Device(W, H, device=local)
-mesh = dev.load_scene(sc)
-stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local))
-comp = multi.Compositor(dev, rank, world, "views", None, stream)
-for _ in range(4):
-    comp.begin_step()
-    dev.clear()
-    dev.draw_mesh(mesh, sc.model)
-    comp.composite()
-comp.finish()
-dev.sync()
-torch.cuda.synchronize()
-dist.barrier()
-if rank == 0:
-    for r in range(1, world):
-        other = S.Scene("t", W, H, v, f, S.SHADER_PHONG, model=base.model, textures=base.textures)
-        other.view_proj, other.cam_pos = S.view_matrix_for(r, 8, W, H)
-        c0, d0 = full_frame(other)
-        for b in range(2):
-            c = comp.slots[b][0][r - 1].cpu().numpy().view(np.uint8).reshape(H, W, 4)
-            d = comp.slots[b][1][r - 1].cpu().numpy()
-            same = np.array_equal(c, c0) and np.array_equal(d.view(np.uint32), d0.view(np.uint32))
-            print(f"views: slot set {b} view {r} == single-GPU render: {same}", flush=True)
-            ok &= same
-dist.barrier()
-dev.close()
+for transport in ("peer", "nccl"):
+    sc = S.Scene("t", W, H, v, f, S.SHADER_PHONG, model=base.model, textures=base.textures)
+    sc.view_proj, sc.cam_pos = S.view_matrix_for(rank, 8, W, H)
+    dev = api.Device(W, H, device=local)
+    mesh = dev.load_scene(sc)
+    stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local))
+    comp = multi.Compositor(dev, rank, world, "views", None, stream, transport=transport)
+    for _ in range(5):
+        comp.begin_step()
+        if comp.clears_own_target:
+            dev.clear()
+        dev.draw_mesh(mesh, sc.model)
+        comp.composite()
+    comp.finish()
+    dev.sync()
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        for r in range(1, world):
+            other = S.Scene("t", W, H, v, f, S.SHADER_PHONG, model=base.model, textures=base.textures)
+            other.view_proj, other.cam_pos = S.view_matrix_for(r, 8, W, H)
+            c0, d0 = full_frame(other)
+            # peer: the last frame (step 4) went to set 0 and set 1 has been cleared for the next one; nccl: both sets hold frames
+            for b in ((0,) if transport == "peer" else (0, 1)):
+                cs, ds = (comp.view_slot(b, r) if transport == "peer" else (comp.slots[b][0][r - 1], comp.slots[b][1][r - 1]))
+                c = cs.contiguous().cpu().numpy().view(np.uint8).reshape(H, W, 4)
+                d = ds.contiguous().cpu().numpy()
+                same = np.array_equal(c, c0) and np.array_equal(d.view(np.uint32), d0.view(np.uint32))
+                print(f"views/{transport}: slot set {b} view {r} == single-GPU render: {same}", flush=True)
+                ok &= same
+    dist.barrier()
+    dev.close()
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.broadcast(flag, 0)
 dist.destroy_process_group()
