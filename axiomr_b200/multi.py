@@ -96,8 +96,7 @@ class Compositor:
               disjoint, so there is no per-frame synchronisation at all.
       views : GPU 0 owns two sets of per-view slots (colour + depth). Rank r > 0 points its output at slot (set i%2, r): its tile
               kernel stores the covered pixels of frame i directly into GPU 0's memory (no depth read-back: the slot is freshly
-              cleared, axr_set_depth_read(0)). GPU 0 clears the *other* set for frame i+1 on a side stream while everybody
-              renders; one tiny NCCL all-reduce per frame on the render streams orders "all stores of frame i are done"
+              cleared, axr_set_depth_read(0)). GPU 0 clears the *other* set for frame i+1 before its own draw; one tiny NCCL all-reduce per frame on the render streams orders "all stores of frame i are done"
               before "the set is cleared again". Only covered pixels cross NVLink (≈ 25 MB instead of 66 MB per 4K view).
     transport "nccl" — the baseline: grouped send/recv of whole regions after each frame (bands: in place; views:
       double-buffered, on a second stream, overlapping the next frame).
@@ -146,11 +145,11 @@ class Compositor:
 
     # ------------------------------------------------------------------ views over peer memory
     def _slot_offsets(self, b: int, r: int):
-        """Byte offsets of (colour, depth) of slot (set b, rank r) inside the shared allocation."""
+        """Byte offsets of (colour, depth) of slot (set b, rank r) inside the shared allocation.
+        Per set: [colour of ranks 1..N-1, contiguous][depth of ranks 1..N-1, contiguous] so a set is cleared by two flat fills."""
         npx = self.H * self.W
-        per_slot = npx * 8
-        base = ((b * (self.world - 1)) + (r - 1)) * per_slot
-        return base, base + npx * 4
+        base = b * (self.world - 1) * npx * 8
+        return base + (r - 1) * npx * 4, base + (self.world - 1) * npx * 4 + (r - 1) * npx * 4
 
     def _setup_peer_views(self):
         torch, dist = self.torch, self.dist
@@ -164,14 +163,12 @@ class Compositor:
         dv = self.color.device
         self.token = torch.zeros(1, dtype=torch.int32, device=dv)
         if self.rank == 0:
-            self.side = torch.cuda.Stream(device=dv)
             self.slots = []
             for b in range(2):
-                c0, _ = self._slot_offsets(b, 1)
-                # per set: (world-1) x [colour HxW int32 | depth HxW f32]; exposed as two strided views for readers
-                raw_i = torch.as_tensor(_DevArray(self._shared_ptr + c0, ((self.world - 1), 2, self.H, self.W), "<i4"), device=dv)
-                raw_f = torch.as_tensor(_DevArray(self._shared_ptr + c0, ((self.world - 1), 2, self.H, self.W), "<f4"), device=dv)
-                self.slots.append((raw_i[:, 0], raw_f[:, 1]))
+                co, do = self._slot_offsets(b, 1)
+                shape = ((self.world - 1), self.H, self.W)
+                self.slots.append((torch.as_tensor(_DevArray(self._shared_ptr + co, shape, "<i4"), device=dv),
+                                   torch.as_tensor(_DevArray(self._shared_ptr + do, shape, "<f4"), device=dv)))
             for b in range(2):
                 self._clear_set(b)
             torch.cuda.synchronize()
@@ -206,11 +203,10 @@ class Compositor:
             co, do = self._slot_offsets(b, self.rank)
             self.dev.set_output(self._shared_ptr + co, self._shared_ptr + do)
         else:
-            # clear the other set for the next frame while this one renders; ordered after the previous frame's all-reduce
-            ready = self.torch.cuda.Event()
-            ready.record(self.stream)
-            with self.torch.cuda.stream(self.side):
-                self.side.wait_event(ready)
+            # Clear the other set for the next frame, on the render stream, before this frame's draw (ordered after the previous
+            # frame's all-reduce by stream order). Doing it concurrently on a side stream was measured slower: the 66 MB-per-view
+            # fills fight the vertex / setup kernels for L2 and HBM (N = 8: +220 us on GPU 0) — serialised they cost ~80 us.
+            with self.torch.cuda.stream(self.stream):
                 self._clear_set((b + 1) % 2)
 
     def composite(self):
@@ -225,8 +221,6 @@ class Compositor:
             return
         if self.transport == "peer":
             with torch.cuda.stream(self.stream):
-                if self.rank == 0:
-                    self.stream.wait_stream(self.side)    # next frame's set is clear
                 dist.all_reduce(self.token)                # every rank's stores of this frame precede anything after it
             return
         ready = torch.cuda.Event()
@@ -245,8 +239,6 @@ class Compositor:
         """Make the render stream wait for every outstanding transfer (call before the closing synchronisation)."""
         if self.mode == "views" and self.transport == "nccl":
             self.stream.wait_stream(self.comm)
-        elif self.mode == "views" and self.rank == 0:
-            self.stream.wait_stream(self.side)
 
     def view_slot(self, b: int, r: int):
         """(colour int32 HxW, depth f32 HxW) of rank r's frame in slot set b, on GPU 0."""
