@@ -74,7 +74,7 @@ ABI_SYMBOLS = [
     "axr_upload_texture", "axr_free_texture", "axr_set_material", "axr_set_uniforms", "axr_set_shader", "axr_set_sampler",
     "axr_clear", "axr_upload_framebuffer", "axr_resolve", "axr_draw_mesh", "axr_sync", "axr_get_stats", "axr_host_alloc",
     "axr_host_free", "axr_stream", "axr_framebuffer_device", "axr_set_output", "axr_framebuffer_ipc", "axr_open_ipc",
-    "axr_close_ipc", "axr_set_profiling", "axr_get_kernel_times", "axr_set_depth_read", "axr_alloc_shared", "axr_free_shared",
+    "axr_close_ipc", "axr_set_profiling", "axr_get_kernel_times", "axr_set_depth_read", "axr_alloc_shared", "axr_free_shared", "axr_set_overlap",
 ]
 STAGES = ["vertex_xform", "setup_raster", "scan_tiles", "bin_scatter", "tile_shade"]
 
@@ -122,6 +122,7 @@ def load_library():
     lib.axr_open_ipc.argtypes = [vp, C.c_void_p, C.POINTER(vp)]
     lib.axr_close_ipc.argtypes = [vp, vp]
     lib.axr_set_depth_read.argtypes = [vp, C.c_int]
+    lib.axr_set_overlap.argtypes = [vp, C.c_int]
     lib.axr_alloc_shared.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.c_void_p]
     lib.axr_free_shared.argtypes = [vp, vp]
     lib.axr_set_profiling.argtypes = [vp, C.c_int]
@@ -279,6 +280,9 @@ class Device:
         p = C.c_void_p()
         self._check(self.lib.axr_open_ipc(self.h, C.create_string_buffer(handle, 64), C.byref(p)))
         return int(p.value)
+
+    def set_overlap(self, enabled: bool):
+        self._check(self.lib.axr_set_overlap(self.h, 1 if enabled else 0))
 
     def set_depth_read(self, enabled: bool):
         self._check(self.lib.axr_set_depth_read(self.h, 1 if enabled else 0))

@@ -26,7 +26,7 @@ struct DeviceMesh {
 	float4* pos = nullptr;
 	VAttr* attr = nullptr;
 	unsigned* idx = nullptr;
-	float4* sv = nullptr;  // per-draw screen-space vertex records (16 B each)
+	float4* sv[2] = {nullptr, nullptr};  // per-draw screen-space vertex records (16 B each), one per draw slot
 	unsigned long long n_verts = 0, n_faces = 0;
 	std::vector<unsigned long long> group_first;  // n_groups + 1
 	std::vector<Material> materials;              // host copy
@@ -43,6 +43,7 @@ struct DeviceTexture {
 
 struct PendingDraw {
 	bool valid = false;
+	int slot = 0;
 	axr_mesh mesh = -1;
 	float model[16];
 	int redo_depth = 0;
@@ -71,26 +72,36 @@ struct axr_ctx {
 	int shader_kind = AXR_SHADER_FLAT;
 	axr_shader_params shader_params{};
 
-	// raster state
-	unsigned long long* vis = nullptr;
-	unsigned* tile_touched = nullptr;
-	unsigned* tile_count = nullptr;
-	unsigned* bin_start = nullptr;
-	unsigned* items = nullptr;
-	unsigned ref_cap = 0;
-	TriRecord* records = nullptr;
-	unsigned rec_cap = 0;
-	unsigned* n_records = nullptr;
-	DrawStatus* d_status = nullptr;
-	DrawStatus* h_status = nullptr;      // pinned + mapped: written by k_scan_tiles
-	DrawStatus* h_status_dev = nullptr;  // device-side alias of h_status
-	cudaEvent_t status_event = nullptr;
+	// Raster state of one draw in flight. Two slots alternate so that the geometry stages of draw i+1 (vertex, setup, bins — on
+	// geom_stream) overlap the tile / shading kernel of draw i (on the main stream): the two halves stress different parts of
+	// the SM (latency-bound gathers vs FP32 issue), so running them side by side raises throughput.
+	struct DrawSlot {
+		unsigned long long* vis = nullptr;
+		unsigned* tile_touched = nullptr;
+		unsigned* tile_count = nullptr;
+		unsigned* bin_start = nullptr;
+		unsigned* items = nullptr;
+		unsigned ref_cap = 0;
+		TriRecord* records = nullptr;
+		unsigned rec_cap = 0;
+		unsigned* n_records = nullptr;
+		DrawStatus* d_status = nullptr;
+		DrawStatus* h_status = nullptr;      // pinned + mapped: written by k_scan_tiles
+		DrawStatus* h_status_dev = nullptr;  // device-side alias of h_status
+		cudaEvent_t status_event = nullptr;  // geom_stream: counters published
+		cudaEvent_t geom_done = nullptr;     // geom_stream: bins complete, the tile kernel may start
+		cudaEvent_t shade_done = nullptr;    // main stream: the tile kernel has consumed (and reset) this slot
+		bool used = false;
+	} slot[2];
+	unsigned draw_counter = 0;
+	cudaStream_t geom_stream = nullptr;
+	bool overlap = false;  // axr_set_overlap: geometry stages on geom_stream (else everything on the main stream)
 	PendingDraw pending;
 	axr_stats stats{};
 
 	// optional per-kernel timing
 	bool profiling = false;
-	std::vector<cudaEvent_t> prof_events;  // (AXR_NUM_STAGES + 1) per profiled draw
+	std::vector<cudaEvent_t> prof_events;  // 2 * AXR_NUM_STAGES per profiled draw: (begin, end) of every stage on its own stream
 	std::vector<cudaEvent_t> prof_pool;
 
 	std::vector<DeviceMesh> meshes;
@@ -127,52 +138,59 @@ inline int grid_for(size_t n, int block, int cap = 148 * 16) {
 
 int n_tiles(const axr_ctx* c) { return c->fp.ntx * c->fp.nty; }
 
-int reset_raster_state(axr_ctx* ctx) {
+int reset_raster_state(axr_ctx* ctx, int si) {
+	axr_ctx::DrawSlot& sl = ctx->slot[si];
 	size_t npx = (size_t)ctx->fp.W * ctx->fp.H;
-	k_fill_u64<<<grid_for(npx, 256), 256, 0, ctx->stream>>>(ctx->vis, KEY_EMPTY, npx);
-	k_fill_u32<<<grid_for(n_tiles(ctx), 256), 256, 0, ctx->stream>>>(ctx->tile_touched, 0u, (size_t)n_tiles(ctx));
-	k_fill_u32<<<grid_for(n_tiles(ctx), 256), 256, 0, ctx->stream>>>(ctx->tile_count, 0u, (size_t)n_tiles(ctx));
+	k_fill_u64<<<grid_for(npx, 256), 256, 0, ctx->stream>>>(sl.vis, KEY_EMPTY, npx);
+	k_fill_u32<<<grid_for(n_tiles(ctx), 256), 256, 0, ctx->stream>>>(sl.tile_touched, 0u, (size_t)n_tiles(ctx));
+	k_fill_u32<<<grid_for(n_tiles(ctx), 256), 256, 0, ctx->stream>>>(sl.tile_count, 0u, (size_t)n_tiles(ctx));
 	CU(cudaGetLastError());
 	return AXR_OK;
 }
 
-int ensure_bins(axr_ctx* ctx, unsigned want_rec, unsigned want_ref) {
-	if (want_rec > ctx->rec_cap) {
-		if (ctx->records) CU(cudaFree(ctx->records));
-		ctx->records = nullptr;
+int ensure_bins(axr_ctx* ctx, int si, unsigned want_rec, unsigned want_ref) {
+	axr_ctx::DrawSlot& sl = ctx->slot[si];
+	if (want_rec > sl.rec_cap) {
+		if (sl.records) CU(cudaFree(sl.records));
+		sl.records = nullptr;
 		unsigned cap = want_rec + want_rec / 8 + 1024;
-		CU(cudaMalloc(&ctx->records, (size_t)cap * sizeof(TriRecord)));
-		ctx->rec_cap = cap;
+		CU(cudaMalloc(&sl.records, (size_t)cap * sizeof(TriRecord)));
+		sl.rec_cap = cap;
 	}
-	if (want_ref > ctx->ref_cap) {
-		if (ctx->items) CU(cudaFree(ctx->items));
-		ctx->items = nullptr;
+	if (want_ref > sl.ref_cap) {
+		if (sl.items) CU(cudaFree(sl.items));
+		sl.items = nullptr;
 		unsigned cap = want_ref + want_ref / 8 + 4096;
-		CU(cudaMalloc(&ctx->items, (size_t)cap * sizeof(unsigned)));
-		ctx->ref_cap = cap;
+		CU(cudaMalloc(&sl.items, (size_t)cap * sizeof(unsigned)));
+		sl.ref_cap = cap;
 	}
 	return AXR_OK;
 }
 
 int sync_materials(axr_ctx* ctx, DeviceMesh& m) {
 	if (!m.materials_dirty) return AXR_OK;
+	CU(cudaStreamSynchronize(ctx->geom_stream));  // no draw in flight may still read the old table
+	CU(cudaStreamSynchronize(ctx->stream));
 	CU(cudaMemcpyAsync(m.d_materials, m.materials.data(), m.materials.size() * sizeof(Material), cudaMemcpyHostToDevice, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));  // the host vector may change right after
 	m.materials_dirty = false;
 	return AXR_OK;
 }
 
-int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model);
+int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si);
 
 // Inspect the status of the draw issued last; if its bins overflowed (its tile kernel then did nothing), grow and re-issue.
+// Every API call that touches the context starts here, so at most one draw is ever unchecked and a later draw is never
+// composited ahead of an earlier one that has to be redone.
 int check_pending(axr_ctx* ctx) {
 	if (!ctx->pending.valid) return AXR_OK;
-	CU(cudaEventSynchronize(ctx->status_event));
 	PendingDraw p = ctx->pending;
+	axr_ctx::DrawSlot& sl = ctx->slot[p.slot];
+	CU(cudaEventSynchronize(sl.status_event));
 	ctx->pending.valid = false;
 	struct { unsigned long long clipped_faces, triangles, small_triangles, binned_triangles, bin_refs; unsigned overflow, pad; } st;
 	static_assert(sizeof(st) == 48 && offsetof(DrawStatus, stripes) == 48, "status head layout");
-	memcpy(&st, ctx->h_status, sizeof st);
+	memcpy(&st, sl.h_status, sizeof st);
 	ctx->stats.clipped_faces = st.clipped_faces;
 	ctx->stats.triangles = st.triangles;
 	ctx->stats.small_triangles = st.small_triangles;
@@ -181,24 +199,26 @@ int check_pending(axr_ctx* ctx) {
 	if (!st.overflow) return AXR_OK;
 	if (p.redo_depth >= 2) return fail(ctx, AXR_ERR_CAPACITY, "bin capacity still exceeded after regrowing (records %llu refs %llu)",
 	                                   (unsigned long long)st.binned_triangles, (unsigned long long)st.bin_refs);
+	CU(cudaStreamSynchronize(ctx->geom_stream));
 	CU(cudaStreamSynchronize(ctx->stream));
-	int rc = ensure_bins(ctx, (unsigned)st.binned_triangles, (unsigned)st.bin_refs);
+	int rc = ensure_bins(ctx, p.slot, (unsigned)st.binned_triangles, (unsigned)st.bin_refs);
 	if (rc) return rc;
-	rc = reset_raster_state(ctx);
+	rc = reset_raster_state(ctx, p.slot);
 	if (rc) return rc;
-	rc = issue_draw(ctx, p.mesh, p.model);
+	CU(cudaStreamSynchronize(ctx->stream));
+	rc = issue_draw(ctx, p.mesh, p.model, p.slot);
 	if (rc) return rc;
 	ctx->pending.redo_depth = p.redo_depth + 1;
 	ctx->stats.redo = 1;
 	return check_pending(ctx);
 }
 
-cudaEvent_t prof_mark(axr_ctx* ctx) {
+cudaEvent_t prof_mark(axr_ctx* ctx, cudaStream_t s) {
 	if (!ctx->profiling) return nullptr;
 	cudaEvent_t e = nullptr;
 	if (!ctx->prof_pool.empty()) { e = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
 	else if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
-	cudaEventRecord(e, ctx->stream);
+	cudaEventRecord(e, s);
 	ctx->prof_events.push_back(e);
 	return e;
 }
@@ -209,8 +229,9 @@ void launch_tile(axr_ctx* ctx, const MeshView& mv, const Uniforms& u, const Tile
 	k_tile_shade<Shader><<<grid, TILE_THREADS, 0, ctx->stream>>>(mv, u, ctx->fp, in);
 }
 
-int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model) {
+int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si) {
 	DeviceMesh& m = ctx->meshes[mh];
+	axr_ctx::DrawSlot& sl = ctx->slot[si];
 	int rc = sync_materials(ctx, m);
 	if (rc) return rc;
 	// shader / material validation (the reference dereferences null textures, include/shaders/shaders.hpp:178,210)
@@ -239,37 +260,47 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model) {
 	mv.group_first = m.d_group_first;
 	mv.n_groups = (int)m.materials.size();
 
-	cudaStream_t s = ctx->stream;
+	// ---- geometry stages on geom_stream. The slot was last used two draws ago: wait until that draw's tile kernel has
+	//      consumed it (it resets the keys, flags and cursors it read).
+	cudaStream_t g = ctx->overlap ? ctx->geom_stream : ctx->stream;
+	if (sl.used) CU(cudaStreamWaitEvent(g, sl.shade_done, 0));
 	uint64_t launches = 0;
-	prof_mark(ctx);
+	prof_mark(ctx, g);
 	{
 		// at least sizeof(DrawStatus)/4 threads: the kernel also zeroes the draw's counters
 		const unsigned long long threads = m.n_verts > sizeof(DrawStatus) / 4 ? m.n_verts : sizeof(DrawStatus) / 4;
-		k_vertex_xform<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(m.pos, m.n_verts, u.mvp, (float)ctx->fp.W, (float)ctx->fp.H, m.sv,
-		                                                                ctx->d_status, ctx->n_records);
+		k_vertex_xform<<<(unsigned)((threads + 255) / 256), 256, 0, g>>>(m.pos, m.n_verts, u.mvp, (float)ctx->fp.W, (float)ctx->fp.H, m.sv[si],
+		                                                                sl.d_status, sl.n_records);
 		++launches;
 	}
-	prof_mark(ctx);
+	prof_mark(ctx, g);
+	prof_mark(ctx, g);
 	SetupOut so;
-	so.vis = ctx->vis; so.tile_touched = ctx->tile_touched; so.tile_count = ctx->tile_count;
-	so.records = ctx->records; so.rec_cap = ctx->rec_cap; so.n_records = ctx->n_records; so.status = ctx->d_status;
+	so.vis = sl.vis; so.tile_touched = sl.tile_touched; so.tile_count = sl.tile_count;
+	so.records = sl.records; so.rec_cap = sl.rec_cap; so.n_records = sl.n_records; so.status = sl.d_status;
 	if (m.n_faces) {
 		const unsigned long long per_cta = (unsigned long long)SETUP_THREADS * SETUP_FPT;
-		k_setup_raster<<<(unsigned)((m.n_faces + per_cta - 1) / per_cta), SETUP_THREADS, 0, s>>>(mv, m.sv, u.mvp, ctx->fp, so);
+		k_setup_raster<<<(unsigned)((m.n_faces + per_cta - 1) / per_cta), SETUP_THREADS, 0, g>>>(mv, m.sv[si], u.mvp, ctx->fp, so);
 		++launches;
 	}
-	prof_mark(ctx);
-	k_scan_tiles<<<1, SCAN_THREADS, 0, s>>>(ctx->tile_count, ctx->bin_start, n_tiles(ctx), ctx->ref_cap, ctx->n_records, ctx->rec_cap, ctx->d_status,
-	                                       ctx->h_status_dev);
+	prof_mark(ctx, g);
+	prof_mark(ctx, g);
+	k_scan_tiles<<<1, SCAN_THREADS, 0, g>>>(sl.tile_count, sl.bin_start, n_tiles(ctx), sl.ref_cap, sl.n_records, sl.rec_cap, sl.d_status,
+	                                       sl.h_status_dev);
 	++launches;
-	prof_mark(ctx);
-	CU(cudaEventRecord(ctx->status_event, s));  // the scan kernel has stored the status into mapped host memory
-	k_bin_scatter<<<148 * 4, 256, 0, s>>>(ctx->records, ctx->n_records, ctx->fp, ctx->bin_start, ctx->tile_count, ctx->items, ctx->d_status);
+	prof_mark(ctx, g);
+	CU(cudaEventRecord(sl.status_event, g));  // the scan kernel has stored the status into mapped host memory
+	prof_mark(ctx, g);
+	k_bin_scatter<<<148 * 4, 256, 0, g>>>(sl.records, sl.n_records, ctx->fp, sl.bin_start, sl.tile_count, sl.items, sl.d_status);
 	++launches;
-	prof_mark(ctx);
+	prof_mark(ctx, g);
+	CU(cudaEventRecord(sl.geom_done, g));
+	// ---- tile raster + shading + resolve on the main stream (the one clears, uploads and resolves are ordered on)
+	CU(cudaStreamWaitEvent(ctx->stream, sl.geom_done, 0));
+	prof_mark(ctx, ctx->stream);
 	TileIn in;
-	in.vis = ctx->vis; in.tile_touched = ctx->tile_touched; in.tile_cursor = ctx->tile_count; in.bin_start = ctx->bin_start;
-	in.items = ctx->items; in.records = ctx->records; in.n_records = ctx->n_records; in.status = ctx->d_status; in.sv = m.sv;
+	in.vis = sl.vis; in.tile_touched = sl.tile_touched; in.tile_cursor = sl.tile_count; in.bin_start = sl.bin_start;
+	in.items = sl.items; in.records = sl.records; in.n_records = sl.n_records; in.status = sl.d_status; in.sv = m.sv[si];
 	in.color = ctx->out_color; in.depth = ctx->out_depth; in.read_depth = ctx->read_depth;
 	switch (ctx->shader_kind) {
 	case AXR_SHADER_FLAT: launch_tile<FlatShader>(ctx, mv, u, in); break;
@@ -278,15 +309,25 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model) {
 	default: return fail(ctx, AXR_ERR_UNSUPPORTED, "unknown shader kind %d", ctx->shader_kind);
 	}
 	++launches;
-	prof_mark(ctx);
+	prof_mark(ctx, ctx->stream);
+	CU(cudaEventRecord(sl.shade_done, ctx->stream));
+	sl.used = true;
 	CU(cudaGetLastError());
 	ctx->stats.faces = m.n_faces;
 	ctx->stats.kernel_launches = launches;
 	ctx->stats.redo = 0;
 	ctx->pending.valid = true;
+	ctx->pending.slot = si;
 	ctx->pending.mesh = mh;
 	memcpy(ctx->pending.model, model, sizeof(float) * 16);
 	ctx->pending.redo_depth = 0;
+	return AXR_OK;
+}
+
+// Every host-visible synchronisation waits for both streams.
+int sync_all(axr_ctx* ctx) {
+	CU(cudaStreamSynchronize(ctx->geom_stream));
+	CU(cudaStreamSynchronize(ctx->stream));
 	return AXR_OK;
 }
 
@@ -352,19 +393,32 @@ int axr_create(const axr_config* cfg, axr_ctx** out) {
 	CUC(cudaMalloc(&c->color, npx * 4));
 	CUC(cudaMalloc(&c->depth, npx * 4));
 	c->out_color = c->color; c->out_depth = c->depth;
-	CUC(cudaMalloc(&c->vis, npx * 8));
-	CUC(cudaMalloc(&c->tile_touched, nt * 4));
-	CUC(cudaMalloc(&c->tile_count, nt * 4));
-	CUC(cudaMalloc(&c->bin_start, (nt + 1) * 4));
-	CUC(cudaMalloc(&c->n_records, 4));
-	CUC(cudaMalloc(&c->d_status, sizeof(DrawStatus)));
-	CUC(cudaHostAlloc(&c->h_status, 64, cudaHostAllocMapped));
-	CUC(cudaHostGetDevicePointer(&c->h_status_dev, c->h_status, 0));
-	CUC(cudaEventCreateWithFlags(&c->status_event, cudaEventDisableTiming));
-	c->rec_cap = 1u << 18; c->ref_cap = 1u << 20;
-	CUC(cudaMalloc(&c->records, (size_t)c->rec_cap * sizeof(TriRecord)));
-	CUC(cudaMalloc(&c->items, (size_t)c->ref_cap * 4));
-	if (reset_raster_state(c) != AXR_OK) { g_create_error = c->error; axr_destroy(c); return AXR_ERR_CUDA; }
+	{
+		// geometry CTAs are scheduled ahead of the (much longer) tile kernel's remaining CTAs, so the two really interleave on the SMs
+		int lo = 0, hi = 0;
+		cudaDeviceGetStreamPriorityRange(&lo, &hi);
+		(void)lo;
+		CUC(cudaStreamCreateWithPriority(&c->geom_stream, cudaStreamNonBlocking, hi));
+	}
+	for (int si = 0; si < 2; ++si) {
+		axr_ctx::DrawSlot& sl = c->slot[si];
+		CUC(cudaMalloc(&sl.vis, npx * 8));
+		CUC(cudaMalloc(&sl.tile_touched, nt * 4));
+		CUC(cudaMalloc(&sl.tile_count, nt * 4));
+		CUC(cudaMalloc(&sl.bin_start, (nt + 1) * 4));
+		CUC(cudaMalloc(&sl.n_records, 4));
+		CUC(cudaMalloc(&sl.d_status, sizeof(DrawStatus)));
+		CUC(cudaHostAlloc(&sl.h_status, 64, cudaHostAllocMapped));
+		CUC(cudaHostGetDevicePointer(&sl.h_status_dev, sl.h_status, 0));
+		CUC(cudaEventCreateWithFlags(&sl.status_event, cudaEventDisableTiming));
+		CUC(cudaEventCreateWithFlags(&sl.geom_done, cudaEventDisableTiming));
+		CUC(cudaEventCreateWithFlags(&sl.shade_done, cudaEventDisableTiming));
+		sl.rec_cap = 1u << 18; sl.ref_cap = 1u << 20;
+		CUC(cudaMalloc(&sl.records, (size_t)sl.rec_cap * sizeof(TriRecord)));
+		CUC(cudaMalloc(&sl.items, (size_t)sl.ref_cap * 4));
+	}
+	for (int si = 0; si < 2; ++si)
+		if (reset_raster_state(c, si) != AXR_OK) { g_create_error = c->error; axr_destroy(c); return AXR_ERR_CUDA; }
 	k_clear<<<grid_for(npx, 256), 256, 0, c->stream>>>(c->color, c->depth, 0u, INFINITY, 0, npx);  // Framebuffer ctor: colour 0, depth +inf
 	CUC(cudaStreamSynchronize(c->stream));
 #undef CUC
@@ -375,15 +429,22 @@ int axr_create(const axr_config* cfg, axr_ctx** out) {
 void axr_destroy(axr_ctx* ctx) {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
+	if (ctx->geom_stream) cudaStreamSynchronize(ctx->geom_stream);
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-	for (auto& m : ctx->meshes) if (m.live) { cudaFree(m.pos); cudaFree(m.attr); cudaFree(m.idx); cudaFree(m.sv); cudaFree(m.d_materials); cudaFree(m.d_group_first); }
+	for (auto& m : ctx->meshes) if (m.live) { cudaFree(m.pos); cudaFree(m.attr); cudaFree(m.idx); cudaFree(m.sv[0]); cudaFree(m.sv[1]); cudaFree(m.d_materials); cudaFree(m.d_group_first); }
 	for (auto& t : ctx->textures) if (t.live) cudaFree(t.data);
 	for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
 	for (void* p : ctx->shared_allocs) cudaFree(p);
-	cudaFree(ctx->color); cudaFree(ctx->depth); cudaFree(ctx->vis); cudaFree(ctx->tile_touched); cudaFree(ctx->tile_count);
-	cudaFree(ctx->bin_start); cudaFree(ctx->items); cudaFree(ctx->records); cudaFree(ctx->n_records); cudaFree(ctx->d_status);
-	if (ctx->h_status) cudaFreeHost(ctx->h_status);
-	if (ctx->status_event) cudaEventDestroy(ctx->status_event);
+	cudaFree(ctx->color); cudaFree(ctx->depth);
+	for (auto& sl : ctx->slot) {
+		cudaFree(sl.vis); cudaFree(sl.tile_touched); cudaFree(sl.tile_count); cudaFree(sl.bin_start); cudaFree(sl.items);
+		cudaFree(sl.records); cudaFree(sl.n_records); cudaFree(sl.d_status);
+		if (sl.h_status) cudaFreeHost(sl.h_status);
+		if (sl.status_event) cudaEventDestroy(sl.status_event);
+		if (sl.geom_done) cudaEventDestroy(sl.geom_done);
+		if (sl.shade_done) cudaEventDestroy(sl.shade_done);
+	}
+	if (ctx->geom_stream) cudaStreamDestroy(ctx->geom_stream);
 	for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
 	for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
 	if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -422,7 +483,8 @@ int axr_upload_mesh(axr_ctx* ctx, const float* vertices, uint64_t n_verts, const
 	float* raw = nullptr;
 	CU(cudaMalloc(&m.pos, nv * sizeof(float4)));
 	CU(cudaMalloc(&m.attr, nv * sizeof(VAttr)));
-	CU(cudaMalloc(&m.sv, nv * sizeof(float4)));
+	CU(cudaMalloc(&m.sv[0], nv * sizeof(float4)));
+	CU(cudaMalloc(&m.sv[1], nv * sizeof(float4)));
 	CU(cudaMalloc(&m.idx, nf * 3 * sizeof(unsigned)));
 	CU(cudaMalloc(&m.d_materials, ng * sizeof(Material)));
 	CU(cudaMalloc(&m.d_group_first, (ng + 1) * sizeof(unsigned long long)));
@@ -450,9 +512,10 @@ int axr_free_mesh(axr_ctx* ctx, axr_mesh mh) {
 	CU(cudaSetDevice(ctx->device));
 	int rc = check_pending(ctx);
 	if (rc) return rc;
-	CU(cudaStreamSynchronize(ctx->stream));
+	rc = sync_all(ctx);
+	if (rc) return rc;
 	DeviceMesh& m = ctx->meshes[mh];
-	cudaFree(m.pos); cudaFree(m.attr); cudaFree(m.idx); cudaFree(m.sv); cudaFree(m.d_materials); cudaFree(m.d_group_first);
+	cudaFree(m.pos); cudaFree(m.attr); cudaFree(m.idx); cudaFree(m.sv[0]); cudaFree(m.sv[1]); cudaFree(m.d_materials); cudaFree(m.d_group_first);
 	m = DeviceMesh();
 	return AXR_OK;
 }
@@ -581,7 +644,7 @@ int axr_draw_mesh(axr_ctx* ctx, axr_mesh mh, const float model[16]) {
 	CU(cudaSetDevice(ctx->device));
 	int rc = check_pending(ctx);
 	if (rc) return rc;
-	return issue_draw(ctx, mh, model);
+	return issue_draw(ctx, mh, model, (int)(ctx->draw_counter++ & 1u));
 }
 
 int axr_sync(axr_ctx* ctx) {
@@ -604,6 +667,7 @@ int axr_get_stats(axr_ctx* ctx, axr_stats* out) {
 int axr_set_profiling(axr_ctx* ctx, int enabled) {
 	if (!ctx) return AXR_ERR_INVALID;
 	CU(cudaSetDevice(ctx->device));
+	CU(cudaStreamSynchronize(ctx->geom_stream));
 	CU(cudaStreamSynchronize(ctx->stream));
 	for (cudaEvent_t e : ctx->prof_events) ctx->prof_pool.push_back(e);
 	ctx->prof_events.clear();
@@ -617,13 +681,13 @@ int axr_get_kernel_times(axr_ctx* ctx, float ms_out[AXR_NUM_STAGES], uint64_t* d
 	int rc = check_pending(ctx);
 	if (rc) return rc;
 	CU(cudaStreamSynchronize(ctx->stream));
-	const size_t per = AXR_NUM_STAGES + 1;
+	const size_t per = 2 * AXR_NUM_STAGES;  // (begin, end) per stage, each pair recorded on the stream its kernel runs on
 	const size_t draws = ctx->prof_events.size() / per;
 	for (int k = 0; k < AXR_NUM_STAGES; ++k) ms_out[k] = 0.f;
 	for (size_t d = 0; d < draws; ++d)
 		for (int k = 0; k < AXR_NUM_STAGES; ++k) {
 			float ms = 0.f;
-			CU(cudaEventElapsedTime(&ms, ctx->prof_events[d * per + k], ctx->prof_events[d * per + k + 1]));
+			CU(cudaEventElapsedTime(&ms, ctx->prof_events[d * per + 2 * k], ctx->prof_events[d * per + 2 * k + 1]));
 			ms_out[k] += ms;
 		}
 	for (cudaEvent_t e : ctx->prof_events) ctx->prof_pool.push_back(e);
@@ -657,6 +721,17 @@ int axr_set_output(axr_ctx* ctx, void* bgra_dev, void* depth_dev) {
 	if ((bgra_dev == nullptr) != (depth_dev == nullptr)) return fail(ctx, AXR_ERR_INVALID, "axr_set_output: pass both pointers or neither");
 	ctx->out_color = bgra_dev ? (unsigned*)bgra_dev : ctx->color;
 	ctx->out_depth = depth_dev ? (float*)depth_dev : ctx->depth;
+	return AXR_OK;
+}
+
+int axr_set_overlap(axr_ctx* ctx, int enabled) {
+	if (!ctx) return AXR_ERR_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	int rc = check_pending(ctx);
+	if (rc) return rc;
+	rc = sync_all(ctx);
+	if (rc) return rc;
+	ctx->overlap = enabled != 0;
 	return AXR_OK;
 }
 

@@ -611,7 +611,14 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 	//    indices: +12 % time; prefetched indices selected inside a rolled loop: +2 %).
 #pragma unroll 1
 	for (int i = 0; i < PPT; ++i) {
-		const int p = tid + i * TILE_THREADS;
+#ifdef AXR_TILE_ROWS
+		const int p = tid + i * TILE_THREADS;  // a warp = one 32-pixel row segment
+#else
+		// a warp = one compact 8x4 pixel block: neighbouring pixels share triangle vertices, so the 32 lanes of a gather touch
+		// fewer distinct cache lines than along a 32x1 row; the stores still fill whole 32 B sectors (8 px x 4 B per row)
+		const int blk = i * (TILE_THREADS / 32) + (tid >> 5);
+		const int p = ((blk >> 2) * 4 + ((tid & 31) >> 3)) * GT + (blk & 3) * 8 + (tid & 7);
+#endif
 		const unsigned long long k = s_keys[p];
 		if (k == KEY_EMPTY) continue;
 		const unsigned ord = (unsigned)(k & 0xFFFFFFFFull);
