@@ -74,7 +74,7 @@ ABI_SYMBOLS = [
     "axr_upload_texture", "axr_free_texture", "axr_set_material", "axr_set_uniforms", "axr_set_shader", "axr_set_sampler",
     "axr_clear", "axr_upload_framebuffer", "axr_resolve", "axr_draw_mesh", "axr_sync", "axr_get_stats", "axr_host_alloc",
     "axr_host_free", "axr_stream", "axr_framebuffer_device", "axr_set_output", "axr_framebuffer_ipc", "axr_open_ipc",
-    "axr_close_ipc", "axr_set_profiling", "axr_get_kernel_times", "axr_set_depth_read", "axr_alloc_shared", "axr_free_shared", "axr_set_overlap",
+    "axr_close_ipc", "axr_set_profiling", "axr_get_kernel_times", "axr_set_depth_read", "axr_alloc_shared", "axr_free_shared", "axr_set_overlap", "axr_upload_framebuffer_async",
 ]
 STAGES = ["vertex_xform", "setup_raster", "scan_tiles", "bin_scatter", "tile_shade"]
 
@@ -106,6 +106,7 @@ def load_library():
     lib.axr_set_sampler.argtypes = [vp, C.c_int]
     lib.axr_clear.argtypes = [vp, C.c_uint32, C.c_float]
     lib.axr_upload_framebuffer.argtypes = [vp, C.c_void_p, C.c_void_p]
+    lib.axr_upload_framebuffer_async.argtypes = [vp, C.c_void_p, C.c_void_p]
     lib.axr_resolve.argtypes = [vp, C.c_void_p, C.c_void_p]
     lib.axr_draw_mesh.argtypes = [vp, C.c_int32, _f32p]
     lib.axr_sync.argtypes = [vp]
@@ -221,10 +222,12 @@ class Device:
     def clear(self, packed_argb: int = 0xFF000000, depth: float = float("inf")):
         self._check(self.lib.axr_clear(self.h, packed_argb, depth))
 
-    def upload_framebuffer(self, color: np.ndarray | None, depth: np.ndarray | None):
+    def upload_framebuffer(self, color: np.ndarray | None, depth: np.ndarray | None, wait: bool = True):
+        """wait=False: only enqueued — the arrays must stay untouched until the next resolve()/sync()."""
         cp = color.ctypes.data if color is not None else None
         dp = depth.ctypes.data if depth is not None else None
-        self._check(self.lib.axr_upload_framebuffer(self.h, cp, dp))
+        fn = self.lib.axr_upload_framebuffer if wait else self.lib.axr_upload_framebuffer_async
+        self._check(fn(self.h, cp, dp))
 
     def resolve(self, color: np.ndarray | None = None, depth: np.ndarray | None = None):
         """Device -> host, synchronous. Allocates the outputs when not given. Returns (BGRA8 HxWx4, depth HxW)."""
@@ -529,6 +532,7 @@ class TiledPipeline(Pipeline):
             if self.device is not None:
                 self.device.close()
             self.device = Device(fb.getWidth(), fb.getHeight(), self._device_index, self._sampler)
+            self.device.set_overlap(True)  # the geometry stages run while the host framebuffer is still being uploaded
             self._mesh_cache.clear()
             self._tex_cache.clear()
 
@@ -568,7 +572,7 @@ class TiledPipeline(Pipeline):
         dev.set_uniforms(cam.getViewProjectionMatrix(), cam.getPosition(), cam.getViewportMatrix())
         sh = self.m_Shader
         dev.set_shader(sh.kind, sh.lightDirection, getattr(sh, "lightColor", (1.0, 1.0, 1.0)))
-        dev.upload_framebuffer(fb.getColorData(), fb.getDepthData())
+        dev.upload_framebuffer(fb.getColorData(), fb.getDepthData(), wait=False)  # consumed before resolve() returns
         dev.draw_mesh(h, modelMatrix)
         dev.resolve(fb.getColorData(), fb.getDepthData())
         self.last_h2d_bytes += fb.getColorData().nbytes + fb.getDepthData().nbytes + 16 * 4 * 3 + 12

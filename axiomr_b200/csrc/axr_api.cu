@@ -614,7 +614,7 @@ int axr_clear(axr_ctx* ctx, uint32_t packed_argb, float depth) {
 	return AXR_OK;
 }
 
-int axr_upload_framebuffer(axr_ctx* ctx, const uint8_t* bgra, const float* depth) {
+static int upload_framebuffer(axr_ctx* ctx, const uint8_t* bgra, const float* depth, bool wait) {
 	if (!ctx) return AXR_ERR_INVALID;
 	CU(cudaSetDevice(ctx->device));
 	int rc = check_pending(ctx);
@@ -622,9 +622,12 @@ int axr_upload_framebuffer(axr_ctx* ctx, const uint8_t* bgra, const float* depth
 	const size_t first = (size_t)ctx->fp.y_lo * ctx->fp.W, n = (size_t)(ctx->fp.y_hi - ctx->fp.y_lo) * ctx->fp.W;
 	if (bgra) CU(cudaMemcpyAsync(ctx->out_color + first, bgra + first * 4, n * 4, cudaMemcpyHostToDevice, ctx->stream));
 	if (depth) CU(cudaMemcpyAsync(ctx->out_depth + first, depth + first, n * 4, cudaMemcpyHostToDevice, ctx->stream));
-	CU(cudaStreamSynchronize(ctx->stream));
+	if (wait) CU(cudaStreamSynchronize(ctx->stream));
 	return AXR_OK;
 }
+
+int axr_upload_framebuffer(axr_ctx* ctx, const uint8_t* bgra, const float* depth) { return upload_framebuffer(ctx, bgra, depth, true); }
+int axr_upload_framebuffer_async(axr_ctx* ctx, const uint8_t* bgra, const float* depth) { return upload_framebuffer(ctx, bgra, depth, false); }
 
 int axr_resolve(axr_ctx* ctx, uint8_t* bgra_out, float* depth_out) {
 	if (!ctx) return AXR_ERR_INVALID;

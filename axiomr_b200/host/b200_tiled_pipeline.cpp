@@ -35,6 +35,7 @@ void B200TiledPipeline::ensureContext() {
 	cfg.sampler = AXR_SAMPLER_NEAREST;  // Texture::sample as shipped (reference include/texture.hpp:12-34)
 	int rc = axr_create(&cfg, &m_Ctx);
 	if (rc != AXR_OK) fail("axr_create", rc);
+	axr_set_overlap(m_Ctx, 1);
 	m_CtxW = w;
 	m_CtxH = h;
 }
@@ -129,8 +130,10 @@ void B200TiledPipeline::drawMesh(const glm::mat4& modelMatrix, const Mesh& mesh)
 
 	const int h = meshHandle(mesh);
 	const size_t npx = (size_t)m_Framebuffer->getWidth() * m_Framebuffer->getHeight();
-	rc = axr_upload_framebuffer(m_Ctx, m_Framebuffer->getColorData(), m_Framebuffer->getDepthData());
-	if (rc != AXR_OK) fail("axr_upload_framebuffer", rc);
+	// only enqueued: the geometry stages of the draw below run while the copy is in flight; axr_resolve at the end of this
+	// function is the synchronisation point, the framebuffer vectors are not touched in between
+	rc = axr_upload_framebuffer_async(m_Ctx, m_Framebuffer->getColorData(), m_Framebuffer->getDepthData());
+	if (rc != AXR_OK) fail("axr_upload_framebuffer_async", rc);
 	rc = axr_draw_mesh(m_Ctx, h, &modelMatrix[0][0]);
 	if (rc != AXR_OK) fail("axr_draw_mesh", rc);
 	rc = axr_resolve(m_Ctx, m_Framebuffer->getColorData(), m_Framebuffer->getDepthData());  // synchronous: complete on return

@@ -123,6 +123,10 @@ int axr_set_sampler(axr_ctx* ctx, int sampler);
  *      row 0 is the bottom of the image (y up), depth is f32 NDC z with +inf = empty. */
 int axr_clear(axr_ctx* ctx, uint32_t packed_argb, float depth);
 int axr_upload_framebuffer(axr_ctx* ctx, const uint8_t* bgra, const float* depth);
+/* Same, but only enqueued: the host buffers must stay untouched until the next axr_resolve / axr_sync (pinned memory, see
+ * axr_host_alloc, is needed for the copy to be truly asynchronous). With axr_set_overlap(1) the geometry stages of the
+ * following axr_draw_mesh run while the copy is still in flight (they do not read the framebuffer). */
+int axr_upload_framebuffer_async(axr_ctx* ctx, const uint8_t* bgra, const float* depth);
 /* Device -> host copy of the whole frame (or this context's band rows only, at their place in the full image),
  * synchronous: on return the draw(s) are complete, like the reference's drawMesh. NULL pointers are skipped. */
 int axr_resolve(axr_ctx* ctx, uint8_t* bgra_out, float* depth_out);
