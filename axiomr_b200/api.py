@@ -74,7 +74,7 @@ ABI_SYMBOLS = [
     "axr_upload_texture", "axr_free_texture", "axr_set_material", "axr_set_uniforms", "axr_set_shader", "axr_set_sampler",
     "axr_clear", "axr_upload_framebuffer", "axr_resolve", "axr_draw_mesh", "axr_sync", "axr_get_stats", "axr_host_alloc",
     "axr_host_free", "axr_stream", "axr_framebuffer_device", "axr_set_output", "axr_framebuffer_ipc", "axr_open_ipc",
-    "axr_close_ipc", "axr_set_profiling", "axr_get_kernel_times", "axr_set_depth_read", "axr_alloc_shared", "axr_free_shared", "axr_set_overlap", "axr_upload_framebuffer_async",
+    "axr_close_ipc", "axr_set_profiling", "axr_get_kernel_times", "axr_set_depth_read", "axr_alloc_shared", "axr_free_shared", "axr_set_overlap", "axr_upload_framebuffer_async", "axr_draw_mesh_host",
 ]
 STAGES = ["vertex_xform", "setup_raster", "scan_tiles", "bin_scatter", "tile_shade"]
 
@@ -109,6 +109,7 @@ def load_library():
     lib.axr_upload_framebuffer_async.argtypes = [vp, C.c_void_p, C.c_void_p]
     lib.axr_resolve.argtypes = [vp, C.c_void_p, C.c_void_p]
     lib.axr_draw_mesh.argtypes = [vp, C.c_int32, _f32p]
+    lib.axr_draw_mesh_host.argtypes = [vp, C.c_int32, _f32p, C.c_void_p, C.c_void_p]
     lib.axr_sync.argtypes = [vp]
     lib.axr_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.axr_host_alloc.argtypes = [C.c_size_t]
@@ -242,6 +243,12 @@ class Device:
     def draw_mesh(self, mesh: int, model):
         m = _mat(model)
         self._check(self.lib.axr_draw_mesh(self.h, mesh, m.ctypes.data_as(_f32p)))
+
+    def draw_mesh_host(self, mesh: int, model, color: np.ndarray, depth: np.ndarray):
+        """drawMesh onto a HOST framebuffer (BGRA8 HxWx4 + f32 HxW, C-contiguous), complete on return."""
+        m = _mat(model)
+        assert color.flags.c_contiguous and depth.flags.c_contiguous and color.dtype == np.uint8 and depth.dtype == np.float32
+        self._check(self.lib.axr_draw_mesh_host(self.h, mesh, m.ctypes.data_as(_f32p), color.ctypes.data, depth.ctypes.data))
 
     def sync(self):
         self._check(self.lib.axr_sync(self.h))
@@ -572,11 +579,10 @@ class TiledPipeline(Pipeline):
         dev.set_uniforms(cam.getViewProjectionMatrix(), cam.getPosition(), cam.getViewportMatrix())
         sh = self.m_Shader
         dev.set_shader(sh.kind, sh.lightDirection, getattr(sh, "lightColor", (1.0, 1.0, 1.0)))
-        dev.upload_framebuffer(fb.getColorData(), fb.getDepthData(), wait=False)  # consumed before resolve() returns
-        dev.draw_mesh(h, modelMatrix)
-        dev.resolve(fb.getColorData(), fb.getDepthData())
-        self.last_h2d_bytes += fb.getColorData().nbytes + fb.getDepthData().nbytes + 16 * 4 * 3 + 12
-        self.last_d2h_bytes = fb.getColorData().nbytes + fb.getDepthData().nbytes
+        # host depth goes up (4 B/px), the pixels that pass the depth test come back through zero-copy stores (8 B each)
+        dev.draw_mesh_host(h, modelMatrix, fb.getColorData(), fb.getDepthData())
+        self.last_h2d_bytes += fb.getDepthData().nbytes + 16 * 4 * 3 + 12
+        self.last_d2h_bytes = None  # 8 bytes per updated pixel; the caller knows how many pixels changed
 
 
 def render_scene(scene, device: int = 0, color=None, depth=None, band=None, dev: Device | None = None):

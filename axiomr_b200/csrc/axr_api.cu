@@ -108,6 +108,8 @@ struct axr_ctx {
 	std::vector<DeviceTexture> textures;
 	std::vector<void*> ipc_opened;
 	std::vector<void*> shared_allocs;
+	std::vector<std::pair<void*, size_t>> registered;  // host ranges page-locked by axr_draw_mesh_host
+	const float* depth_read_override = nullptr;        // set for the duration of one axr_draw_mesh_host
 	int read_depth = 1;
 };
 
@@ -302,6 +304,7 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si) {
 	in.vis = sl.vis; in.tile_touched = sl.tile_touched; in.tile_cursor = sl.tile_count; in.bin_start = sl.bin_start;
 	in.items = sl.items; in.records = sl.records; in.n_records = sl.n_records; in.status = sl.d_status; in.sv = m.sv[si];
 	in.color = ctx->out_color; in.depth = ctx->out_depth; in.read_depth = ctx->read_depth;
+	in.depth_read = ctx->depth_read_override ? ctx->depth_read_override : ctx->out_depth;
 	switch (ctx->shader_kind) {
 	case AXR_SHADER_FLAT: launch_tile<FlatShader>(ctx, mv, u, in); break;
 	case AXR_SHADER_PHONG: launch_tile<PhongShader>(ctx, mv, u, in); break;
@@ -435,6 +438,7 @@ void axr_destroy(axr_ctx* ctx) {
 	for (auto& t : ctx->textures) if (t.live) cudaFree(t.data);
 	for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
 	for (void* p : ctx->shared_allocs) cudaFree(p);
+	for (auto& r : ctx->registered) cudaHostUnregister(r.first);
 	cudaFree(ctx->color); cudaFree(ctx->depth);
 	for (auto& sl : ctx->slot) {
 		cudaFree(sl.vis); cudaFree(sl.tile_touched); cudaFree(sl.tile_count); cudaFree(sl.bin_start); cudaFree(sl.items);
@@ -648,6 +652,46 @@ int axr_draw_mesh(axr_ctx* ctx, axr_mesh mh, const float model[16]) {
 	int rc = check_pending(ctx);
 	if (rc) return rc;
 	return issue_draw(ctx, mh, model, (int)(ctx->draw_counter++ & 1u));
+}
+
+// Device-side alias of a host range, page-locking it on first use. Returns nullptr when the range cannot be mapped.
+static void* map_host_range(axr_ctx* ctx, void* p, size_t bytes) {
+	void* d = nullptr;
+	if (cudaHostGetDevicePointer(&d, p, 0) == cudaSuccess && d) return d;
+	cudaGetLastError();
+	for (auto& r : ctx->registered)
+		if (r.first == p && r.second >= bytes) return cudaHostGetDevicePointer(&d, p, 0) == cudaSuccess ? d : nullptr;
+	if (cudaHostRegister(p, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	ctx->registered.emplace_back(p, bytes);
+	if (cudaHostGetDevicePointer(&d, p, 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	return d;
+}
+
+int axr_draw_mesh_host(axr_ctx* ctx, axr_mesh mh, const float model[16], uint8_t* bgra, float* depth) {
+	if (!ctx) return AXR_ERR_INVALID;
+	if (!valid_mesh(ctx, mh) || !model || !bgra || !depth) return fail(ctx, AXR_ERR_INVALID, "axr_draw_mesh_host: bad mesh handle %d or null pointer", mh);
+	CU(cudaSetDevice(ctx->device));
+	int rc = check_pending(ctx);
+	if (rc) return rc;
+	const size_t npx = (size_t)ctx->fp.W * ctx->fp.H;
+	const size_t first = (size_t)ctx->fp.y_lo * ctx->fp.W, n = (size_t)(ctx->fp.y_hi - ctx->fp.y_lo) * ctx->fp.W;
+	void* dc = map_host_range(ctx, bgra, npx * 4);
+	void* dd = dc ? map_host_range(ctx, depth, npx * 4) : nullptr;
+	if (!dc || !dd) {  // not mappable: the plain round trip
+		rc = upload_framebuffer(ctx, bgra, depth, false);
+		if (!rc) rc = issue_draw(ctx, mh, model, (int)(ctx->draw_counter++ & 1u));
+		if (!rc) rc = axr_resolve(ctx, bgra, depth);
+		return rc;
+	}
+	// host depth -> device copy for the merge test; the geometry stages do not wait for it when overlap is on
+	CU(cudaMemcpyAsync(ctx->depth + first, depth + first, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+	unsigned* save_c = ctx->out_color; float* save_d = ctx->out_depth;
+	ctx->out_color = (unsigned*)dc; ctx->out_depth = (float*)dd; ctx->depth_read_override = ctx->depth;
+	rc = issue_draw(ctx, mh, model, (int)(ctx->draw_counter++ & 1u));
+	if (!rc) rc = check_pending(ctx);  // a bin overflow re-issues the draw while the host pointers are still installed
+	ctx->out_color = save_c; ctx->out_depth = save_d; ctx->depth_read_override = nullptr;
+	if (rc) return rc;
+	return sync_all(ctx);  // complete on return: the kernel's stores have landed in the host arrays
 }
 
 int axr_sync(axr_ctx* ctx) {

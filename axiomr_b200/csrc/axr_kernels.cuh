@@ -402,6 +402,7 @@ struct TileIn {
 	const float4* sv;
 	unsigned* color;                // BGRA8 as packed words (B | G<<8 | R<<16 | A<<24), full-frame pitch W
 	float* depth;
+	const float* depth_read;        // where the merge test reads fbZ from (== depth unless the output is write-only host memory)
 	int read_depth;                 // 0: the caller guarantees depth == +inf everywhere (freshly cleared single-draw target)
 };
 
@@ -470,7 +471,7 @@ __device__ __noinline__ void shade_pixel_clipped(const MeshView& mesh, const Uni
 	coverage(s, px, py, c0, c1, c2);
 	const float z = interp_z(s, c0, c1, c2, al, be, ga);
 	const size_t gi = (size_t)py * fp.W + px;
-	if (!(z < (in.read_depth ? in.depth[gi] : INFINITY))) return;
+	if (!(z < (in.read_depth ? in.depth_read[gi] : INFINITY))) return;
 	float var[Shader::NV];
 	const float w[3] = {al, be, ga};
 	for (int k = 0; k < 3; ++k) accumulate_vertex<Shader>(u, k, w[k], c[k].pos, c[k].n, c[k].t, c[k].b, c[k].uv[0], c[k].uv[1], var);
@@ -491,7 +492,7 @@ __device__ __forceinline__ void shade_pixel(const MeshView& mesh, const Uniforms
 	const float4 a00 = __ldg(ap0), a01 = __ldg(ap0 + 1), a02 = __ldg(ap0 + 2);
 	const float4 a10 = __ldg(ap1), a11 = __ldg(ap1 + 1), a12 = __ldg(ap1 + 2);
 	const float4 a20 = __ldg(ap2), a21 = __ldg(ap2 + 1), a22 = __ldg(ap2 + 2);
-	const float fbz = in.read_depth ? in.depth[gi] : INFINITY;
+	const float fbz = in.read_depth ? in.depth_read[gi] : INFINITY;
 	if ((__float_as_uint(s0.w) | __float_as_uint(s1.w) | __float_as_uint(s2.w)) & 0x3fu) {
 		shade_pixel_clipped<Shader>(mesh, u, fp, in, ordinal, i0, i1, i2, px, py);
 		return;

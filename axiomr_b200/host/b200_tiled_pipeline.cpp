@@ -130,16 +130,11 @@ void B200TiledPipeline::drawMesh(const glm::mat4& modelMatrix, const Mesh& mesh)
 
 	const int h = meshHandle(mesh);
 	const size_t npx = (size_t)m_Framebuffer->getWidth() * m_Framebuffer->getHeight();
-	// only enqueued: the geometry stages of the draw below run while the copy is in flight; axr_resolve at the end of this
-	// function is the synchronisation point, the framebuffer vectors are not touched in between
-	rc = axr_upload_framebuffer_async(m_Ctx, m_Framebuffer->getColorData(), m_Framebuffer->getDepthData());
-	if (rc != AXR_OK) fail("axr_upload_framebuffer_async", rc);
-	rc = axr_draw_mesh(m_Ctx, h, &modelMatrix[0][0]);
-	if (rc != AXR_OK) fail("axr_draw_mesh", rc);
-	rc = axr_resolve(m_Ctx, m_Framebuffer->getColorData(), m_Framebuffer->getDepthData());  // synchronous: complete on return
-	if (rc != AXR_OK) fail("axr_resolve", rc);
-	m_LastH2D += npx * 8 + 16 * 4 * 3 + 12;
-	m_LastD2H += npx * 8;
+	// host depth up (4 B/px), passing pixels back through zero-copy stores (8 B each); complete on return
+	rc = axr_draw_mesh_host(m_Ctx, h, &modelMatrix[0][0], m_Framebuffer->getColorData(), m_Framebuffer->getDepthData());
+	if (rc != AXR_OK) fail("axr_draw_mesh_host", rc);
+	m_LastH2D += npx * 4 + 16 * 4 * 3 + 12;
+	m_LastD2H += 0;  // 8 bytes per updated pixel, written by the kernel
 }
 
 }  // namespace AR

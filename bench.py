@@ -431,9 +431,12 @@ def main():
             e2e_ms = float(t.item())
         if rank == 0:
             line["e2e"] = {"value": units / (e2e_ms * 1e-3) / 1e6, "unit": "Mtri/s", "ms_per_step": e2e_ms, "steps": n_e2e,
-                           "h2d_bytes_per_step": int(pipe.last_h2d_bytes), "d2h_bytes_per_step": int(pipe.last_d2h_bytes),
-                           "call": "TiledPipeline.drawMesh(model, mesh) on a pinned host Framebuffer: host clear, H2D of colour+depth, "
-                                   "draw, D2H of colour+depth, complete on return; mesh/textures cached on the device after the first call",
+                           "h2d_bytes_per_step": int(pipe.last_h2d_bytes), "d2h_bytes_per_step": int(covered) * 8,
+                           "call": "TiledPipeline.drawMesh(model, mesh) on a pinned host Framebuffer (axr_draw_mesh_host): H2D of the host "
+                                   "depth (4 B/px, the kernel never reads colour), draw, the pixels that pass the depth test stored by the tile "
+                                   "kernel straight into the host arrays (zero-copy, 8 B per updated pixel), complete on return; host-side "
+                                   "clearColor/clearDepth before the call are the caller's and untimed, as in the CPU arm; mesh/textures cached "
+                                   "on the device after the first call",
                            "mesh_upload_bytes_first_call": int(sc.vertices.nbytes + sc.indices.nbytes)}
         pipe.device.close()
     elif rank == 0:

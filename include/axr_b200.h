@@ -135,6 +135,13 @@ int axr_resolve(axr_ctx* ctx, uint8_t* bgra_out, float* depth_out);
  *      (reference src/tiled_pipeline.cpp:143-322). Composites onto the current framebuffer contents with the
  *      reference's strict depth test; never clears. Asynchronous on the context stream. */
 int axr_draw_mesh(axr_ctx* ctx, axr_mesh mesh, const float model[16]);
+/* drawMesh with the reference's exact calling convention: composite onto a HOST framebuffer (Framebuffer::getColorData() /
+ * getDepthData()), complete on return. Only the host depth is uploaded (the tile kernel never reads colour); the pixels that
+ * pass the depth test are stored by the kernel straight into the host arrays through a zero-copy mapping (pinned memory from
+ * axr_host_alloc is mapped already, other memory is page-locked with cudaHostRegister on first use and remembered), so the
+ * device -> host traffic is 8 bytes per updated pixel instead of the whole frame. Falls back to upload / draw / resolve when the
+ * host memory cannot be mapped. The device-resident framebuffer of the context is left unspecified by this call. */
+int axr_draw_mesh_host(axr_ctx* ctx, axr_mesh mesh, const float model[16], uint8_t* bgra, float* depth);
 int axr_sync(axr_ctx* ctx);
 int axr_get_stats(axr_ctx* ctx, axr_stats* out);
 
