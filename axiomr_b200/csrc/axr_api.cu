@@ -228,7 +228,8 @@ cudaEvent_t prof_mark(axr_ctx* ctx, cudaStream_t s) {
 template <typename Shader>
 void launch_tile(axr_ctx* ctx, const MeshView& mv, const Uniforms& u, const TileIn& in) {
 	dim3 grid(ctx->fp.ntx, ctx->fp.ty_hi - ctx->fp.ty_lo);
-	k_tile_shade<Shader><<<grid, TILE_THREADS, 0, ctx->stream>>>(mv, u, ctx->fp, in);
+	if (u.sampler) k_tile_shade<Shader, 1><<<grid, TILE_THREADS, 0, ctx->stream>>>(mv, u, ctx->fp, in);
+	else k_tile_shade<Shader, 0><<<grid, TILE_THREADS, 0, ctx->stream>>>(mv, u, ctx->fp, in);
 }
 
 int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si) {

@@ -432,18 +432,18 @@ __device__ __forceinline__ void accumulate_vertex(const Uniforms& u, int k, floa
 	for (int i = 0; i < Shader::NV; ++i) var[i] = (k == 0) ? o[i] * w : var[i] + o[i] * w;
 }
 
-template <typename Shader>
+template <typename Shader, int SMP>
 __device__ __forceinline__ void finish_pixel(const MeshView& mesh, const Uniforms& u, const TileIn& in, unsigned face, size_t gi, float z,
                                              const float* var) {
 	v4 col;
-	if (Shader::fragment(u, face_material(mesh, face), var, col)) return;  // true = discard (none of the shipped shaders does)
+	if (Shader::template fragment<SMP>(u, face_material(mesh, face), var, col)) return;  // true = discard (none of the shipped shaders does)
 	in.depth[gi] = z;
 	in.color[gi] = pack_bgra(col);
 }
 
 // Pixel whose visible triangle comes from a clipped face: re-derive sub-triangle (ordinal & 7) with full attributes
 // (reference src/pipeline.cpp:176-272). Rare; kept out of line so its stack frame does not burden the common path.
-template <typename Shader>
+template <typename Shader, int SMP>
 __device__ __noinline__ void shade_pixel_clipped(const MeshView& mesh, const Uniforms& u, const FrameParams& fp, const TileIn& in,
                                                  unsigned ordinal, unsigned i0, unsigned i1, unsigned i2, int px, int py) {
 	ClipFull a[MAX_CLIPPED_VERTS], b[MAX_CLIPPED_VERTS];
@@ -475,12 +475,12 @@ __device__ __noinline__ void shade_pixel_clipped(const MeshView& mesh, const Uni
 	float var[Shader::NV];
 	const float w[3] = {al, be, ga};
 	for (int k = 0; k < 3; ++k) accumulate_vertex<Shader>(u, k, w[k], c[k].pos, c[k].n, c[k].t, c[k].b, c[k].uv[0], c[k].uv[1], var);
-	finish_pixel<Shader>(mesh, u, in, ordinal >> 3, gi, z, var);
+	finish_pixel<Shader, SMP>(mesh, u, in, ordinal >> 3, gi, z, var);
 }
 
 // One visible pixel: all gathers that depend only on the vertex indices are issued together (screen records, positions,
 // attributes, framebuffer depth), then setup -> barycentrics -> depth test -> IShader::vertex x3 -> IShader::fragment.
-template <typename Shader>
+template <typename Shader, int SMP>
 __device__ __forceinline__ void shade_pixel(const MeshView& mesh, const Uniforms& u, const FrameParams& fp, const TileIn& in,
                                             unsigned ordinal, unsigned i0, unsigned i1, unsigned i2, int px, int py) {
 	const size_t gi = (size_t)py * fp.W + px;
@@ -494,7 +494,7 @@ __device__ __forceinline__ void shade_pixel(const MeshView& mesh, const Uniforms
 	const float4 a20 = __ldg(ap2), a21 = __ldg(ap2 + 1), a22 = __ldg(ap2 + 2);
 	const float fbz = in.read_depth ? in.depth_read[gi] : INFINITY;
 	if ((__float_as_uint(s0.w) | __float_as_uint(s1.w) | __float_as_uint(s2.w)) & 0x3fu) {
-		shade_pixel_clipped<Shader>(mesh, u, fp, in, ordinal, i0, i1, i2, px, py);
+		shade_pixel_clipped<Shader, SMP>(mesh, u, fp, in, ordinal, i0, i1, i2, px, py);
 		return;
 	}
 	Setup s;
@@ -508,10 +508,10 @@ __device__ __forceinline__ void shade_pixel(const MeshView& mesh, const Uniforms
 	accumulate_vertex<Shader>(u, 0, al, V3(p0.x, p0.y, p0.z), V3(a00.z, a00.w, a01.x), V3(a01.y, a01.z, a01.w), V3(a02.x, a02.y, a02.z), a00.x, a00.y, var);
 	accumulate_vertex<Shader>(u, 1, be, V3(p1.x, p1.y, p1.z), V3(a10.z, a10.w, a11.x), V3(a11.y, a11.z, a11.w), V3(a12.x, a12.y, a12.z), a10.x, a10.y, var);
 	accumulate_vertex<Shader>(u, 2, ga, V3(p2.x, p2.y, p2.z), V3(a20.z, a20.w, a21.x), V3(a21.y, a21.z, a21.w), V3(a22.x, a22.y, a22.z), a20.x, a20.y, var);
-	finish_pixel<Shader>(mesh, u, in, ordinal >> 3, gi, z, var);
+	finish_pixel<Shader, SMP>(mesh, u, in, ordinal >> 3, gi, z, var);
 }
 
-template <typename Shader>
+template <typename Shader, int SMP>
 __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(const __grid_constant__ MeshView mesh, const __grid_constant__ Uniforms u, const __grid_constant__ FrameParams fp,
                                                                              const __grid_constant__ TileIn in) {
 	__shared__ unsigned long long s_keys[GT_PIX];
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 	for (int i = 0; i < PPT; ++i) {
 		if (ord[i] == 0xFFFFFFFFu) continue;
 		const int p = tid + i * TILE_THREADS;
-		shade_pixel<Shader>(mesh, u, fp, in, ord[i], vi[i][0], vi[i][1], vi[i][2], x0 + (p & (GT - 1)), y0 + (p / GT));
+		shade_pixel<Shader, SMP>(mesh, u, fp, in, ord[i], vi[i][0], vi[i][1], vi[i][2], x0 + (p & (GT - 1)), y0 + (p / GT));
 	}
 #else
 	//    Not unrolled: one copy of the shading code keeps the kernel inside the instruction cache (unrolled x4 with prefetched
@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 		const unsigned ord = (unsigned)(k & 0xFFFFFFFFull);
 		const unsigned* ip = mesh.idx + (size_t)(ord >> 3) * 3;
 		const unsigned i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
-		shade_pixel<Shader>(mesh, u, fp, in, ord, i0, i1, i2, x0 + (p & (GT - 1)), y0 + (p / GT));
+		shade_pixel<Shader, SMP>(mesh, u, fp, in, ord, i0, i1, i2, x0 + (p & (GT - 1)), y0 + (p / GT));
 	}
 #endif
 }

@@ -67,8 +67,11 @@ __device__ __forceinline__ v4 sample_bilinear(const TexRef& t, float u, float v)
 	v4 c01 = texel(t, x0, t.h - 1 - y1), c11 = texel(t, x1, t.h - 1 - y1);
 	return mix(mix(c00, c10, tx), mix(c01, c11, tx), ty);
 }
-__device__ __forceinline__ v4 sample(const TexRef& t, float u, float v, int sampler) {
-	return sampler ? sample_bilinear(t, u, v) : sample_nearest(t, u, v);
+// The sampler mode is a compile-time parameter of the shading kernel: no per-sample branch, and the four texel fetches of
+// every bilinear tap of every map of a fragment are independent loads the scheduler can issue together.
+template <int SMP>
+__device__ __forceinline__ v4 sample(const TexRef& t, float u, float v) {
+	return SMP ? sample_bilinear(t, u, v) : sample_nearest(t, u, v);
 }
 
 __device__ __forceinline__ v3 xyz(v4 v) { return V3(v.x, v.y, v.z); }
@@ -93,6 +96,7 @@ struct FlatShader {
 		v3 r = mul(u.normal_mat, n);
 		o[0] = r.x; o[1] = r.y; o[2] = r.z;
 	}
+	template <int SMP>
 	__device__ __forceinline__ static bool fragment(const Uniforms& u, const Material& m, const float* var, v4& color) {
 		v3 n = normalize(V3(var[0], var[1], var[2]));
 		float intensity = clampf(dot(-u.light_dir, n), 0.0f, 1.0f);
@@ -108,10 +112,11 @@ struct PhongShader {
 	__device__ __forceinline__ static void vertex(const Uniforms& u, v3 pos, v3 n, v3 t, v3 b, float uvx, float uvy, float* o) {
 		vertex_tbn(u, pos, n, t, b, uvx, uvy, o);
 	}
+	template <int SMP>
 	__device__ __forceinline__ static bool fragment(const Uniforms& u, const Material& m, const float* var, v4& color) {
 		const float uvx = var[0], uvy = var[1];
-		v4 nm = sample(m.tex[1], uvx, uvy, u.sampler);
-		v4 albedo = sample(m.tex[0], uvx, uvy, u.sampler);
+		v4 nm = sample<SMP>(m.tex[1], uvx, uvy);
+		v4 albedo = sample<SMP>(m.tex[0], uvx, uvy);
 		v3 nms = normalize(xyz(nm) * 2.0f - V3(1.0f, 1.0f, 1.0f));
 		v3 T = V3(var[5], var[6], var[7]);
 		v3 N = normalize(V3(var[11], var[12], var[13]));
@@ -142,14 +147,15 @@ struct PBRShader {
 	__device__ __forceinline__ static void vertex(const Uniforms& u, v3 pos, v3 n, v3 t, v3 b, float uvx, float uvy, float* o) {
 		vertex_tbn(u, pos, n, t, b, uvx, uvy, o);
 	}
+	template <int SMP>
 	__device__ __forceinline__ static bool fragment(const Uniforms& u, const Material& m, const float* var, v4& color) {
 		const float PI = 3.14159265358979323846264338327950288f;
 		const float uvx = var[0], uvy = var[1];
-		v4 nm = sample(m.tex[1], uvx, uvy, u.sampler);
-		v4 al4 = sample(m.tex[0], uvx, uvy, u.sampler);
-		float metallic = sample(m.tex[2], uvx, uvy, u.sampler).x;
-		float roughness = sample(m.tex[3], uvx, uvy, u.sampler).x;
-		float ao = sample(m.tex[4], uvx, uvy, u.sampler).x;
+		v4 nm = sample<SMP>(m.tex[1], uvx, uvy);
+		v4 al4 = sample<SMP>(m.tex[0], uvx, uvy);
+		float metallic = sample<SMP>(m.tex[2], uvx, uvy).x;
+		float roughness = sample<SMP>(m.tex[3], uvx, uvy).x;
+		float ao = sample<SMP>(m.tex[4], uvx, uvy).x;
 		v3 nms = normalize(V3(nm.x * 2.0f - 1.0f, nm.y * 2.0f - 1.0f, nm.z * 2.0f - 1.0f));
 		m3 tbn;
 		tbn.c[0] = V3(var[5], var[6], var[7]); tbn.c[1] = V3(var[8], var[9], var[10]); tbn.c[2] = V3(var[11], var[12], var[13]);
