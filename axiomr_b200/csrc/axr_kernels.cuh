@@ -301,19 +301,26 @@ __device__ __forceinline__ void publish_status(const DrawStatus* d, DrawStatus* 
 	volatile unsigned long long* hv = reinterpret_cast<volatile unsigned long long*>(h);
 	const volatile unsigned long long* dv = reinterpret_cast<const volatile unsigned long long*>(d);
 	for (int i = 0; i < 6; ++i) hv[i] = dv[i];  // clipped_faces, triangles, small, binned, bin_refs, {overflow, pad}
-	__threadfence_system();
+	// no system fence: the host reads after synchronising on an event recorded behind this kernel
 }
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(unsigned* tile_count, unsigned* bin_start, int n, unsigned ref_cap,
                                                              const unsigned* n_records, unsigned rec_cap, DrawStatus* status, DrawStatus* host_status) {
 	__shared__ unsigned s_warp[32];
 	__shared__ unsigned s_carry;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	{  // fold the striped counters of k_setup_raster: warp w < 4 sums counter w
-		if (warp < 4) {
-			unsigned long long acc = 0;
-			for (int i = lane; i < STAT_STRIPES; i += 32) acc += status->stripes[warp][i];
-			for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
-			if (lane == 0) (&status->clipped_faces)[warp] = acc;
+	{  // fold the striped counters of k_setup_raster: 256 threads per counter, 16 stripes each, then shuffle + shared reduction
+		__shared__ unsigned long long s_fold[32];
+		const int c = tid >> 8, t = tid & 255;
+		unsigned long long acc = 0;
+#pragma unroll
+		for (int i = 0; i < STAT_STRIPES / 256; ++i) acc += status->stripes[c][t + i * 256];
+		for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+		if (lane == 0) s_fold[warp] = acc;
+		__syncthreads();
+		if (tid < 4) {
+			unsigned long long sum = 0;
+			for (int w = 0; w < 8; ++w) sum += s_fold[tid * 8 + w];
+			(&status->clipped_faces)[tid] = sum;
 		}
 	}
 	const unsigned nrec = *n_records;
