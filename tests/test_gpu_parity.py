@@ -334,3 +334,19 @@ def test_overlapped_draws_identical(po):
     c, d, _ = po.oracle_render(b2, color=c, depth=d)
     m = po.compare(frames[True][0][0], frames[True][0][1], c, d)
     assert m["coverage_mismatch"] == 0 and m["depth_bit_mismatch"] == 0, m
+
+
+def test_edge_cases_torture(po):
+    """CUDA vs the CPU checker on adversarial inputs: shared-edge ties through pixel centres, duplicate triangles, vertices on tile
+    borders / pixel centres / the frame border with partial tiles, zero-area and sub-1e-12-area triangles, frame-wide slivers,
+    vertices at w = 0 and behind the camera, near / far crossings, huge triangles, +0 / -0 depth ties."""
+    from torture import torture_scenes
+    for sc in torture_scenes():
+        c1, d1, st = _gpu(sc)
+        if po.ref_available():
+            c0, d0, _ = po.ref_render(sc, threads=2, chunk=5)
+        else:
+            c0, d0, _ = po.oracle_render(sc, threads=2)
+        m = po.compare(c1, d1, c0, d0)
+        print(sc.name, st, m)
+        assert m["coverage_mismatch"] == 0 and m["depth_bit_mismatch"] == 0 and m["color_max_diff"] <= 1, (sc.name, m)

@@ -92,3 +92,15 @@ def test_oracle_vs_live_reference_random(po, seed):
     c1, d1, _ = po.oracle_render(sc, threads=2)
     m = po.compare(c1, d1, c0, d0)
     assert m["coverage_mismatch"] == 0 and m["depth_bit_mismatch"] == 0 and m["color_max_diff"] == 0, m
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/tiled_pipeline.cpp"), reason="reference tree not present")
+def test_oracle_vs_live_reference_edge_cases(po):
+    """Shared-edge ties, duplicates, tile/centre-aligned vertices, degenerate triangles, w = 0 / w < 0, near/far crossings, signed-zero depth."""
+    from torture import torture_scenes
+    for sc in torture_scenes():
+        c0, d0, _ = po.ref_render(sc, threads=3, chunk=7)
+        c1, d1, _ = po.oracle_render(sc, threads=2)
+        m = po.compare(c1, d1, c0, d0)
+        assert m["coverage_mismatch"] == 0 and m["depth_bit_mismatch"] == 0 and m["color_max_diff"] == 0, (sc.name, m)
+        assert m["covered"] > 0, sc.name
