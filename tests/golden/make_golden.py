@@ -42,3 +42,29 @@ import ctypes as ct
 po.ref_lib().axr_ref_mat4_mul(vp.ctypes.data_as(ct.POINTER(ct.c_float)), a.ctypes.data_as(ct.POINTER(ct.c_float)), out.ctypes.data_as(ct.POINTER(ct.c_float)))
 np.savez_compressed(os.path.join(HERE, "camera_kat.npz"), view_proj=vp, viewport=vpt, a=a, vp_times_a=out.reshape(4, 4))
 print("stage KATs written")
+# OBJ / MTL ingestion through the reference's own loader (src/mesh.cpp): the file texts + the arrays it produced
+import tempfile
+sys.path.insert(0, os.path.dirname(HERE))
+from objutil import write_obj_scene  # noqa: E402
+from axiomr_b200 import scenes as S  # noqa: E402
+d = tempfile.mkdtemp()
+v, f = S.head_like(10, 9)
+quad_v, quad_f = S.quad_grid(3)
+fix = {}
+for name, (vv, ff) in {"head": (v, f), "quad": (quad_v, quad_f)}.items():
+    pth = write_obj_scene(d, name, vv, ff, None)
+    rv, rf = po.ref_load_obj(pth)
+    fix[name + "_obj"] = np.frombuffer(open(pth, "rb").read(), dtype=np.uint8)
+    fix[name + "_mtl"] = np.frombuffer(open(pth[:-4] + ".mtl", "rb").read(), dtype=np.uint8)
+    fix[name + "_vertices"], fix[name + "_faces"] = rv, rf
+# a polygon face (fan triangulation), shared / repeated corners (de-duplication), a face without vt/vn, degenerate uv (fallback tangent)
+poly = b"v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 0.5 1.5 0.25\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nvn 0 0 1\nvn 0.9 0 0.43589\nusemtl m0\n" \
+       b"f 1/1/1 2/2/1 3/3/1 4/4/1 5/3/2\nf 1/1/1 3/3/1 2/2/1\nf 1 2 5\nf 1/1/1 2/1/1 3/1/1\n"
+open(os.path.join(d, "poly.obj"), "wb").write(poly)
+open(os.path.join(d, "poly.mtl"), "wb").write(b"newmtl m0\nNs 0.25\n")
+rv, rf = po.ref_load_obj(os.path.join(d, "poly.obj"))
+fix["poly_obj"] = np.frombuffer(poly, dtype=np.uint8)
+fix["poly_mtl"] = np.frombuffer(b"newmtl m0\nNs 0.25\n", dtype=np.uint8)
+fix["poly_vertices"], fix["poly_faces"] = rv, rf
+np.savez_compressed(os.path.join(HERE, "obj_loader.npz"), **fix)
+print("OBJ loader fixtures written", {k: fix[k].shape for k in fix if k.endswith("vertices")})

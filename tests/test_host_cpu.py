@@ -115,3 +115,23 @@ def test_compositor_gather_logic_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs), outs
+
+
+def test_obj_loader_matches_reference_loader_golden(tmp_path):
+    """axiomr_b200/obj.py (mirror of AR::Mesh(path), reference src/mesh.cpp) against arrays produced by the reference's own
+    loader (tests/golden/obj_loader.npz): de-duplication order, fan triangulation, tangent / bitangent generation, bit for bit."""
+    from axiomr_b200 import obj
+    z = np.load(os.path.join(ROOT, "tests", "golden", "obj_loader.npz"))
+    for name in ("head", "quad", "poly"):
+        p = tmp_path / f"{name}.obj"
+        p.write_bytes(z[name + "_obj"].tobytes())
+        (tmp_path / f"{name}.mtl").write_bytes(z[name + "_mtl"].tobytes())
+        m = obj.load_obj(str(p))
+        assert np.array_equal(m.getFaces(), z[name + "_faces"]), name
+        got, want = m.getVertices(), z[name + "_vertices"]
+        assert got.shape == want.shape, name
+        assert np.array_equal(np.isnan(got), np.isnan(want)), name
+        ok = (got.view(np.uint32) == want.view(np.uint32)) | np.isnan(want)
+        assert ok.all(), (name, np.argwhere(~ok)[:5])
+        assert m.getMaterialGroups()[0].materialName == "m0" and m.getMaterialGroups()[0].faceCount == want.shape[0] * 0 + m.getFaces().shape[0]
+    assert abs(m.getMaterial("m0").specularExponent - 0.25) < 1e-7
