@@ -141,10 +141,6 @@ __device__ __forceinline__ void emit_triangle(const FrameParams& fp, const Setup
                                               float x2, float y2, float z0, float z1, float z2, unsigned ordinal, EmitCounters& cnt,
                                               unsigned* touched) {
 	cnt.tris++;
-#ifdef AXR_DIAG_NO_RASTER
-	if (x0 == 123.456f) o.tile_touched[0] = 1u;
-	return;
-#endif
 	Setup s;
 	if (!setup_triangle(x0, y0, x1, y1, x2, y2, z0, z1, z2, fp.W, fp.y_lo, fp.y_hi, s)) return;
 	const int bw = s.X1 - s.X0, bh = s.Y1 - s.Y0;
