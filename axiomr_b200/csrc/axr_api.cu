@@ -281,6 +281,9 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si) {
 	SetupOut so;
 	so.vis = sl.vis; so.tile_touched = sl.tile_touched; so.tile_count = sl.tile_count;
 	so.records = sl.records; so.rec_cap = sl.rec_cap; so.n_records = sl.n_records; so.status = sl.d_status;
+	const bool tput = m.n_faces >= SMALL_TPUT_MIN_FACES;
+	so.small_dim = tput ? SMALL_DIM_TPUT : SMALL_DIM_LAT;
+	so.small_area = tput ? SMALL_AREA_TPUT : SMALL_AREA_LAT;
 	if (m.n_faces) {
 		const unsigned long long per_cta = (unsigned long long)SETUP_THREADS * SETUP_FPT;
 		k_setup_raster<<<(unsigned)((m.n_faces + per_cta - 1) / per_cta), SETUP_THREADS, 0, g>>>(mv, m.sv[si], u.mvp, ctx->fp, so);

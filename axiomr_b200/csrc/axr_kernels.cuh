@@ -21,14 +21,13 @@ namespace axr {
 
 constexpr int GT = 32;            // GPU tile edge in pixels (a multiple of REF_TILE; keeps rows 128 B wide for the resolve)
 constexpr int GT_PIX = GT * GT;
-// triangles whose pixel box is at most SMALL_DIM on a side and SMALL_AREA pixels are rasterised by their own thread in k_setup_raster
-#ifndef AXR_SMALL_DIM
-#define AXR_SMALL_DIM 8
-#endif
-#ifndef AXR_SMALL_AREA
-#define AXR_SMALL_AREA 32
-#endif
-constexpr int SMALL_DIM = AXR_SMALL_DIM, SMALL_AREA = AXR_SMALL_AREA;
+// Triangles whose pixel box is at most small_dim on a side and small_area pixels are rasterised by their own thread in
+// k_setup_raster; the rest go through the tile bins. The limits are per draw (SetupOut): a throughput-bound draw of millions of
+// faces prefers the larger pair (the binned path costs more per triangle up to ~64 px: C3 at 8K 1.31 -> 1.07 ms), a draw of a
+// few thousand faces is latency-bound and prefers the smaller one (a lone thread walking 64 pixels is the critical path:
+// C1 0.111 -> 0.122 ms). Results are identical either way.
+constexpr int SMALL_DIM_LAT = 8, SMALL_AREA_LAT = 32, SMALL_DIM_TPUT = 12, SMALL_AREA_TPUT = 64;
+constexpr unsigned long long SMALL_TPUT_MIN_FACES = 500000ull;
 constexpr int TILE_THREADS = 256;
 
 // 40-byte setup record of a triangle that goes through the tile bins
@@ -123,6 +122,7 @@ struct SetupOut {
 	unsigned rec_cap;
 	unsigned* n_records;         // device counter (also the number wanted when it overflows)
 	DrawStatus* status;
+	int small_dim, small_area;   // direct-raster limits of this draw
 };
 
 struct EmitCounters { unsigned tris, small, binned; };
@@ -144,7 +144,7 @@ __device__ __forceinline__ void emit_triangle(const FrameParams& fp, const Setup
 	Setup s;
 	if (!setup_triangle(x0, y0, x1, y1, x2, y2, z0, z1, z2, fp.W, fp.y_lo, fp.y_hi, s)) return;
 	const int bw = s.X1 - s.X0, bh = s.Y1 - s.Y0;
-	if (bw <= SMALL_DIM && bh <= SMALL_DIM && bw * bh <= SMALL_AREA) {
+	if (bw <= o.small_dim && bh <= o.small_dim && bw * bh <= o.small_area) {
 		cnt.small++;
 		bool any = false;
 		for_each_covered(s, s.X0, s.X1, s.Y0, s.Y1, [&](int px, int py, float c0, float c1, float c2) {
@@ -155,7 +155,7 @@ __device__ __forceinline__ void emit_triangle(const FrameParams& fp, const Setup
 			any = true;
 		});
 		if (any) {
-			const int tx0 = s.X0 / GT, ty0 = s.Y0 / GT, tx1 = (s.X1 - 1) / GT, ty1 = (s.Y1 - 1) / GT;  // box <= 8x8 px: at most 2x2 tiles
+			const int tx0 = s.X0 / GT, ty0 = s.Y0 / GT, tx1 = (s.X1 - 1) / GT, ty1 = (s.Y1 - 1) / GT;  // box <= 12x12 px: at most 2x2 tiles
 			if (touched && fp.ntx <= 256 && fp.nty <= 256) {
 				*touched = (unsigned)tx0 | ((unsigned)ty0 << 8) | ((unsigned)tx1 << 16) | ((unsigned)ty1 << 24);
 			} else {

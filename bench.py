@@ -42,6 +42,10 @@ def build_workload(name: str) -> S.Scene:
         return S.config1()
     if name == "c5":      # C3 scene at 8K (bands mode)
         return S.config3(w=7680, h=4320, sampler=S.SAMPLER_BILINEAR)
+    if name == "mid":     # mid-size triangles (box area ~100-400 px): icosphere level 6 at 4K, Phong
+        v, f = S.icosphere(6)
+        return S.Scene("mid_icosphere6_phong_4k", 3840, 2160, v, f, S.SHADER_PHONG, S.SAMPLER_BILINEAR, model=S._f32(S.rotate_y(0.5)),
+                       textures=S._phong_textures(2048))
     if name == "tiny":    # CI-sized stand-in
         return S.config3(n=300, w=1280, h=720, tex=512, sampler=S.SAMPLER_BILINEAR)
     raise SystemExit(f"unknown workload {name}")
