@@ -329,13 +329,30 @@ class Color:
     a: int = 255
 
 
+class _PinnedBlock:
+    """cudaHostAlloc'ed bytes exposed through __array_interface__; freed when the last numpy view is gone."""
+
+    def __init__(self, lib, nbytes: int):
+        self.lib, self.nbytes = lib, nbytes
+        self.ptr = lib.axr_host_alloc(nbytes)
+        if self.ptr:
+            self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(self.ptr), False), "version": 3}
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            try:
+                self.lib.axr_host_free(self.ptr)
+            except Exception:
+                pass
+            self.ptr = None
+
+
 class Framebuffer:
     """AR::Framebuffer (reference include/framebuffer.hpp, src/framebuffer.cpp): BGRA8 colour + f32 depth on the host,
     row 0 = bottom. Backed by pinned memory when the CUDA library is available."""
 
     def __init__(self, width: int, height: int, useDepth: bool = True, pinned: bool = True):
         self._w, self._h, self._use_depth = int(width), int(height), bool(useDepth)
-        self._pinned = []
         self._color = self._alloc((height, width, 4), np.uint8, pinned)
         self._color[:] = 0
         self._depth = self._alloc((height, width), np.float32, pinned)
@@ -345,22 +362,13 @@ class Framebuffer:
         n = int(np.prod(shape)) * np.dtype(dtype).itemsize
         if pinned and os.path.exists(LIB_PATH):
             try:
-                lib = load_library()
-                p = lib.axr_host_alloc(n)
-                if p:
-                    self._pinned.append((lib, p))
-                    buf = (C.c_uint8 * n).from_address(p)
-                    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+                block = _PinnedBlock(load_library(), n)
+                if block.ptr:
+                    # the block is the array's base object: the pinned memory lives as long as any view of it does
+                    return np.asarray(block).view(dtype).reshape(shape)
             except OSError:
                 pass
         return np.zeros(shape, dtype=dtype)
-
-    def __del__(self):
-        for lib, p in getattr(self, "_pinned", []):
-            try:
-                lib.axr_host_free(p)
-            except Exception:
-                pass
 
     def clearColor(self, color: Color):
         packed = (color.a << 24) | (color.r << 16) | (color.g << 8) | color.b  # src/framebuffer.cpp:29-32

@@ -1,15 +1,21 @@
 // CUDA kernels of the B200 tiled-raster path (sm_100a). One draw =
-//   k_vertex_xform   per unique vertex : mvp transform, clip code, perspective divide -> 16 B screen record
-//   k_setup_raster   per input face    : clip (slow path) / cull / setup; tiny triangles are rasterised right here
-//                                        with 64-bit atomicMin visibility keys, larger ones become 40 B setup records
-//                                        and are counted per 32x32 screen tile (warp-aggregated append)
-//   k_scan_tiles     one CTA           : block-wide exclusive prefix sum of the per-tile counts
-//   k_bin_scatter    per record        : scatter record ids into the per-tile lists
-//   k_tile_shade<S>  one CTA per tile  : tile keys staged in shared memory, binned triangles rasterised with shared
-//                                        atomics, then deferred IShader::vertex x3 + IShader::fragment for the single
-//                                        visible triangle of each pixel, depth test against the framebuffer and one
-//                                        coalesced BGRA8 + f32 store
-// Nothing here is a dense contraction, so there is no tensor-core work; the path is HBM/L2-gather and FP32-issue bound.
+//   k_vertex_xform   per unique vertex : mvp transform, exact + "safely outside" clip codes, perspective divide -> 16 B screen
+//                                        record (also zeroes the draw's counters)
+//   k_setup_raster   per input face    : 3 index loads + 3 record gathers; all-inside -> back-face test; provably outside ->
+//                                        nothing; else McGuire clip (slow path). Triangles whose pixel box is small (<= 32 or
+//                                        64 px, per draw) are rasterised right here by their own thread: exact coverage per
+//                                        pixel, 64-bit RED.MIN of (orderable(z) << 32 | face*8+sub) into the visibility buffer,
+//                                        warp-aggregated tile flags. Larger ones: warp-aggregated append of a 40 B record +
+//                                        per-tile count
+//   k_scan_tiles     one CTA           : block-wide exclusive prefix sum of the per-tile counts, folds the striped counters,
+//                                        publishes the draw status to mapped host memory
+//   k_bin_scatter    per record        : scatter record ids into the per-tile lists (order-free: the key carries the ordinal)
+//   k_tile_shade<S,M> one CTA per 32x32 tile : stage the tile's keys in shared memory (and hand the global ones back empty), raster
+//                                        the binned records (lane-per-record setup, shared atomicMin), then per visible pixel:
+//                                        gather indices -> screen records / positions / attributes / framebuffer depth in one
+//                                        batch -> setup -> barycentrics -> depth test -> IShader::vertex x3 accumulated into
+//                                        varyings -> IShader::fragment (textures from HBM) -> BGRA8 + f32 store
+// Nothing here is a dense contraction, so there is no tensor-core work; the path is gather-, latency- and FP32-issue bound.
 #pragma once
 #include <cooperative_groups.h>
 
