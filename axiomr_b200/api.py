@@ -74,7 +74,7 @@ ABI_SYMBOLS = [
     "axr_upload_texture", "axr_free_texture", "axr_set_material", "axr_set_uniforms", "axr_set_shader", "axr_set_sampler",
     "axr_clear", "axr_upload_framebuffer", "axr_resolve", "axr_draw_mesh", "axr_sync", "axr_get_stats", "axr_host_alloc",
     "axr_host_free", "axr_stream", "axr_framebuffer_device", "axr_set_output", "axr_framebuffer_ipc", "axr_open_ipc",
-    "axr_close_ipc", "axr_set_profiling", "axr_get_kernel_times", "axr_set_depth_read", "axr_alloc_shared", "axr_free_shared", "axr_set_overlap", "axr_upload_framebuffer_async", "axr_draw_mesh_host",
+    "axr_close_ipc", "axr_set_profiling", "axr_get_kernel_times", "axr_set_depth_read", "axr_alloc_shared", "axr_free_shared", "axr_set_overlap", "axr_upload_framebuffer_async", "axr_draw_mesh_host", "axr_generate_tangents",
 ]
 STAGES = ["vertex_xform", "setup_raster", "scan_tiles", "bin_scatter", "tile_shade"]
 
@@ -98,6 +98,7 @@ def load_library():
     lib.axr_last_error.restype = C.c_char_p
     lib.axr_upload_mesh.argtypes = [vp, _f32p, C.c_uint64, _u32p, C.c_uint64, C.POINTER(_Group), C.c_uint32, C.POINTER(C.c_int32)]
     lib.axr_free_mesh.argtypes = [vp, C.c_int32]
+    lib.axr_generate_tangents.argtypes = [vp, _f32p, C.c_uint64, _u32p, C.c_uint64, _f32p]
     lib.axr_upload_texture.argtypes = [vp, _u8p, C.c_int, C.c_int, C.POINTER(C.c_int32)]
     lib.axr_free_texture.argtypes = [vp, C.c_int32]
     lib.axr_set_material.argtypes = [vp, C.c_int32, C.c_uint32] + [C.c_int32] * 5 + [C.c_float]
@@ -195,6 +196,15 @@ class Device:
         self._check(self.lib.axr_upload_mesh(self.h, v.ctypes.data_as(_f32p), v.shape[0], f.ctypes.data_as(_u32p), f.shape[0],
                                              garr, ng, C.byref(out)))
         return out.value
+
+    def generate_tangents(self, pos_uv_normal: np.ndarray, indices: np.ndarray) -> np.ndarray:
+        """Mesh::calculateTangentBitangent on the device: (V,8) f32 + (T,3) u32 -> (V,14) f32 in AR::Vertex layout."""
+        v = np.ascontiguousarray(pos_uv_normal, dtype=np.float32).reshape(-1, 8)
+        f = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1, 3)
+        out = np.zeros((v.shape[0], 14), dtype=np.float32)
+        self._check(self.lib.axr_generate_tangents(self.h, v.ctypes.data_as(_f32p), v.shape[0], f.ctypes.data_as(_u32p), f.shape[0],
+                                                   out.ctypes.data_as(_f32p)))
+        return out
 
     def free_mesh(self, mesh: int):
         self._check(self.lib.axr_free_mesh(self.h, mesh))

@@ -14,6 +14,7 @@
 
 #include "../../include/axr_b200.h"
 #include "axr_kernels.cuh"
+#include "axr_tangents.cuh"
 
 using namespace axr;
 
@@ -511,6 +512,51 @@ int axr_upload_mesh(axr_ctx* ctx, const float* vertices, uint64_t n_verts, const
 	for (size_t i = 0; i < ctx->meshes.size(); ++i) if (!ctx->meshes[i].live) { slot = i; break; }
 	if (slot == ctx->meshes.size()) ctx->meshes.push_back(std::move(m)); else ctx->meshes[slot] = std::move(m);
 	*out = (axr_mesh)slot;
+	return AXR_OK;
+}
+
+int axr_generate_tangents(axr_ctx* ctx, const float* v8, uint64_t n_verts, const uint32_t* indices, uint64_t n_faces, float* out14) {
+	if (!ctx) return AXR_ERR_INVALID;
+	if ((n_verts && (!v8 || !out14)) || (n_faces && !indices)) return fail(ctx, AXR_ERR_INVALID, "axr_generate_tangents: null argument");
+	if (n_verts >= (1ull << 32) || n_faces * 3 >= (1ull << 32)) return fail(ctx, AXR_ERR_CAPACITY, "axr_generate_tangents: mesh too large for 32-bit corner ids");
+	for (uint64_t i = 0; i < n_faces * 3; ++i)
+		if (indices[i] >= n_verts) return fail(ctx, AXR_ERR_INVALID, "axr_generate_tangents: index %u out of range", indices[i]);
+	if (n_verts == 0) return AXR_OK;
+	CU(cudaSetDevice(ctx->device));
+	int rc = check_pending(ctx);
+	if (rc) return rc;
+	cudaStream_t s = ctx->stream;
+	float *d_v8 = nullptr, *d_out = nullptr;
+	unsigned *d_idx = nullptr, *d_deg = nullptr, *d_start = nullptr, *d_cur = nullptr, *d_corners = nullptr;
+	FaceTB* d_ftb = nullptr;
+	void* d_tmp = nullptr;
+	size_t tmp_bytes = 0;
+	const size_t nf = n_faces ? n_faces : 1;
+	auto cleanup = [&]() { cudaFree(d_v8); cudaFree(d_out); cudaFree(d_idx); cudaFree(d_deg); cudaFree(d_start); cudaFree(d_cur); cudaFree(d_corners); cudaFree(d_ftb); cudaFree(d_tmp); };
+#define CUT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ctx, AXR_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
+	CUT(cudaMalloc(&d_v8, n_verts * 8 * sizeof(float)));
+	CUT(cudaMalloc(&d_out, n_verts * 14 * sizeof(float)));
+	CUT(cudaMalloc(&d_idx, nf * 3 * sizeof(unsigned)));
+	CUT(cudaMalloc(&d_deg, (n_verts + 1) * sizeof(unsigned)));
+	CUT(cudaMalloc(&d_start, (n_verts + 1) * sizeof(unsigned)));
+	CUT(cudaMalloc(&d_cur, n_verts * sizeof(unsigned)));
+	CUT(cudaMalloc(&d_corners, nf * 3 * sizeof(unsigned)));
+	CUT(cudaMalloc(&d_ftb, nf * sizeof(FaceTB)));
+	CUT(cudaMemcpyAsync(d_v8, v8, n_verts * 8 * sizeof(float), cudaMemcpyHostToDevice, s));
+	if (n_faces) CUT(cudaMemcpyAsync(d_idx, indices, n_faces * 3 * sizeof(unsigned), cudaMemcpyHostToDevice, s));
+	CUT(cudaMemsetAsync(d_deg, 0, (n_verts + 1) * sizeof(unsigned), s));
+	CUT(cudaMemsetAsync(d_cur, 0, n_verts * sizeof(unsigned), s));
+	if (n_faces) k_tan_faces<<<(unsigned)((n_faces + 255) / 256), 256, 0, s>>>(d_v8, d_idx, n_faces, d_ftb, d_deg);
+	CUT(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_deg, d_start, (int)(n_verts + 1), s));
+	CUT(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1));
+	CUT(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_deg, d_start, (int)(n_verts + 1), s));
+	if (n_faces) k_tan_fill<<<(unsigned)((n_faces + 255) / 256), 256, 0, s>>>(d_idx, n_faces, d_start, d_cur, d_corners);
+	k_tan_vertices<<<(unsigned)((n_verts + 255) / 256), 256, 0, s>>>(d_v8, n_verts, d_start, d_corners, d_ftb, d_out);
+	CUT(cudaGetLastError());
+	CUT(cudaMemcpyAsync(out14, d_out, n_verts * 14 * sizeof(float), cudaMemcpyDeviceToHost, s));
+	CUT(cudaStreamSynchronize(s));
+#undef CUT
+	cleanup();
 	return AXR_OK;
 }
 

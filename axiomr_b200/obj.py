@@ -164,12 +164,14 @@ def _load_image(path: str):
         return None
 
 
-def load_obj(path: str, texture_loader=_load_image) -> Mesh:
-    """AR::Mesh(path): OBJ + '<basename>.mtl' next to it (reference src/mesh.cpp:8-27,197-220)."""
+def load_obj(path: str, texture_loader=_load_image, device=None) -> Mesh:
+    """AR::Mesh(path): OBJ + '<basename>.mtl' next to it (reference src/mesh.cpp:8-27,197-220).
+    With `device` (an api.Device) the tangents / bitangents are generated on the GPU (axr_generate_tangents, bit-identical);
+    the per-corner Python loop of `tangents` is only practical for small meshes."""
     with open(path, "rb") as fh:
         text = fh.read().decode("utf-8", "replace")
     v8, faces, groups = parse_obj(text)
-    verts = tangents(v8, faces)
+    verts = device.generate_tangents(v8, faces) if device is not None else tangents(v8, faces)
     directory = os.path.dirname(path)
     mtl = os.path.join(directory, os.path.splitext(os.path.basename(path))[0] + ".mtl")
     mats = {}

@@ -110,6 +110,13 @@ int axr_free_texture(axr_ctx* ctx, axr_tex tex);
 int axr_set_material(axr_ctx* ctx, axr_mesh mesh, uint32_t group, axr_tex diffuse, axr_tex bump, axr_tex metallic,
                      axr_tex roughness, axr_tex ao, float specular_exponent);
 
+/* ---- mesh ingestion helper: Mesh::calculateTangentBitangent (reference src/mesh.cpp:222-298) on the device.
+ *      in: n_verts x 8 f32 (position3, uv2, normal3) as the OBJ parser leaves them + 3 u32 per face;
+ *      out: n_verts x 14 f32 in AR::Vertex layout with the reference's tangents / bitangents, bit for bit (per-vertex sums are
+ *      taken in face order like the reference's). Host in, host out, synchronous. */
+int axr_generate_tangents(axr_ctx* ctx, const float* pos_uv_normal, uint64_t n_verts, const uint32_t* indices, uint64_t n_faces,
+                          float* vertices_out);
+
 /* ---- per-frame state: replaces Pipeline::setCamera / the uniform writes at src/tiled_pipeline.cpp:148-155.
  *      view_proj = Camera::getViewProjectionMatrix(), viewport = Camera::getViewportMatrix() (carried, unused by
  *      the shipped shaders), cam_pos = Camera::getPosition(). mvp = view_proj * model is formed per draw in glm order. */

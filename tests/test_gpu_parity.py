@@ -350,3 +350,37 @@ def test_edge_cases_torture(po):
         m = po.compare(c1, d1, c0, d0)
         print(sc.name, st, m)
         assert m["coverage_mismatch"] == 0 and m["depth_bit_mismatch"] == 0 and m["color_max_diff"] <= 1, (sc.name, m)
+
+
+def test_gpu_tangent_generation_matches_reference_loader_arithmetic():
+    """axr_generate_tangents (Mesh::calculateTangentBitangent on the device) against the numpy mirror of the reference loader
+    (axiomr_b200/obj.py::tangents, itself pinned bit-for-bit to the reference loader by tests/golden/obj_loader.npz)."""
+    from axiomr_b200 import api, obj
+    dev = api.Device(64, 64)
+    try:
+        z = np.load(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden", "obj_loader.npz"))
+        meshes = {name: (z[name + "_vertices"][:, :8].copy(), z[name + "_faces"].copy()) for name in ("head", "quad", "poly")}
+        v, f = S.icosphere(4)
+        meshes["icosphere4"] = (v[:, :8].copy(), f)
+        v, f = S.head_like(20, 40)            # poles with valence 40
+        meshes["poles"] = (v[:, :8].copy(), f)
+        v, f = S.random_triangles(500, 77)
+        v8 = v[:, :8].copy()
+        v8[::7, 3:5] = 0.25                   # degenerate uv on some corners -> |den| < 1e-8 fallbacks
+        v8 = np.concatenate([v8, v8[:3]])     # three vertices no face references
+        meshes["random_degenerate_uv"] = (v8, f)
+        for name, (v8, f) in meshes.items():
+            want = obj.tangents(v8.astype(np.float32), f)
+            got = dev.generate_tangents(v8, f)
+            assert got.shape == want.shape
+            assert np.array_equal(np.isnan(got), np.isnan(want)), name
+            ok = (got.view(np.uint32) == want.view(np.uint32)) | np.isnan(want)
+            assert ok.all(), (name, np.argwhere(~ok)[:5].tolist())
+        # the arrays the reference's own loader produced (golden) are reproduced from its de-duplicated vertices + faces
+        for name in ("head", "quad", "poly"):
+            want = z[name + "_vertices"]
+            got = dev.generate_tangents(want[:, :8], z[name + "_faces"])
+            ok = (got.view(np.uint32) == want.view(np.uint32)) | np.isnan(want)
+            assert ok.all(), name
+    finally:
+        dev.close()
