@@ -74,7 +74,7 @@ ABI_SYMBOLS = [
     "axr_upload_texture", "axr_free_texture", "axr_set_material", "axr_set_uniforms", "axr_set_shader", "axr_set_sampler",
     "axr_clear", "axr_upload_framebuffer", "axr_resolve", "axr_draw_mesh", "axr_sync", "axr_get_stats", "axr_host_alloc",
     "axr_host_free", "axr_stream", "axr_framebuffer_device", "axr_set_output", "axr_framebuffer_ipc", "axr_open_ipc",
-    "axr_close_ipc", "axr_set_profiling", "axr_get_kernel_times", "axr_set_depth_read", "axr_alloc_shared", "axr_free_shared", "axr_set_overlap", "axr_upload_framebuffer_async", "axr_draw_mesh_host", "axr_generate_tangents",
+    "axr_close_ipc", "axr_set_profiling", "axr_get_kernel_times", "axr_set_depth_read", "axr_alloc_shared", "axr_free_shared", "axr_set_overlap", "axr_upload_framebuffer_async", "axr_draw_mesh_host", "axr_generate_tangents", "axr_measure_fp32_issue",
 ]
 STAGES = ["vertex_xform", "setup_raster", "scan_tiles", "bin_scatter", "tile_shade"]
 
@@ -128,6 +128,7 @@ def load_library():
     lib.axr_set_overlap.argtypes = [vp, C.c_int]
     lib.axr_alloc_shared.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.c_void_p]
     lib.axr_free_shared.argtypes = [vp, vp]
+    lib.axr_measure_fp32_issue.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.axr_set_profiling.argtypes = [vp, C.c_int]
     lib.axr_get_kernel_times.argtypes = [vp, _f32p, C.POINTER(C.c_uint64)]
     _lib = lib
@@ -267,6 +268,12 @@ class Device:
         s = Stats()
         self._check(self.lib.axr_get_stats(self.h, C.byref(s)))
         return s.as_dict()
+
+    def measure_fp32_issue(self):
+        """(FMUL+FADD warp-instructions/s, FFMA warp-instructions/s) measured on this GPU."""
+        a, b = C.c_double(0), C.c_double(0)
+        self._check(self.lib.axr_measure_fp32_issue(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def set_profiling(self, enabled: bool):
         self._check(self.lib.axr_set_profiling(self.h, 1 if enabled else 0))

@@ -793,6 +793,44 @@ int axr_get_kernel_times(axr_ctx* ctx, float ms_out[AXR_NUM_STAGES], uint64_t* d
 	return AXR_OK;
 }
 
+int axr_measure_fp32_issue(axr_ctx* ctx, double* fmul_fadd_winst_per_s, double* ffma_winst_per_s) {
+	if (!ctx) return AXR_ERR_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	int rc = check_pending(ctx);
+	if (rc) return rc;
+	rc = sync_all(ctx);
+	if (rc) return rc;
+	const int ctas = 148 * 8, threads = 256, iters = 2048;
+	float* buf = nullptr;
+	CU(cudaMalloc(&buf, (size_t)ctas * threads * sizeof(float)));
+	cudaEvent_t e0, e1;
+	CU(cudaEventCreate(&e0));
+	CU(cudaEventCreate(&e1));
+	double res[2] = {0, 0};
+	for (int mode = 0; mode < 2; ++mode) {
+		float best = 1e30f;
+		for (int rep = 0; rep < 4; ++rep) {  // first repetition warms up
+			cudaEventRecord(e0, ctx->stream);
+			if (mode == 0) k_fp32_peak<0><<<ctas, threads, 0, ctx->stream>>>(buf, 1.0000001f, 1e-7f, iters);
+			else k_fp32_peak<1><<<ctas, threads, 0, ctx->stream>>>(buf, 1.0000001f, 1e-7f, iters);
+			cudaEventRecord(e1, ctx->stream);
+			cudaEventSynchronize(e1);
+			float ms = 0.f;
+			cudaEventElapsedTime(&ms, e0, e1);
+			if (rep && ms < best) best = ms;
+		}
+		const double warp_inst = (double)ctas * (threads / 32) * (double)iters * 16.0 * 8.0 * (mode == 0 ? 2.0 : 1.0);
+		res[mode] = warp_inst / (best * 1e-3);
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(buf);
+	CU(cudaGetLastError());
+	if (fmul_fadd_winst_per_s) *fmul_fadd_winst_per_s = res[0];
+	if (ffma_winst_per_s) *ffma_winst_per_s = res[1];
+	return AXR_OK;
+}
+
 void* axr_host_alloc(size_t bytes) {
 	void* p = nullptr;
 	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) return nullptr;

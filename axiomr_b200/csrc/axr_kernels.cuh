@@ -102,6 +102,28 @@ __global__ void k_split_vertices(const float* __restrict__ raw, unsigned long lo
 	attr[i] = a;
 }
 
+// ------------------------------------------------------------------------------------------------ FP32 issue micro-benchmark
+// the shading / setup kernels are ALU-heavy, so every report carries an FP32-issue bound next to the HBM one.
+// Eight independent chains per thread; MODE 0: x = x*a + b as separate FMUL + FADD (what the path executes: the library is built
+// with -fmad=false for parity), MODE 1: fused (__fmaf_rn). The result is stored so nothing is optimised away.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_fp32_peak(float* out, float a, float b, int iters) {
+	float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+	for (int i = 0; i < iters; ++i) {
+#pragma unroll
+		for (int k = 0; k < 16; ++k) {
+			if (MODE == 0) {
+				x0 = x0 * a + b; x1 = x1 * a + b; x2 = x2 * a + b; x3 = x3 * a + b;
+				x4 = x4 * a + b; x5 = x5 * a + b; x6 = x6 * a + b; x7 = x7 * a + b;
+			} else {
+				x0 = __fmaf_rn(x0, a, b); x1 = __fmaf_rn(x1, a, b); x2 = __fmaf_rn(x2, a, b); x3 = __fmaf_rn(x3, a, b);
+				x4 = __fmaf_rn(x4, a, b); x5 = __fmaf_rn(x5, a, b); x6 = __fmaf_rn(x6, a, b); x7 = __fmaf_rn(x7, a, b);
+			}
+		}
+	}
+	out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
 // ------------------------------------------------------------------------------------------------ vertex stage
 // reference src/tiled_pipeline.cpp:210-212 (mvp * vec4(pos,1)) + :57-66 (perspective divide), once per unique vertex
 // It also zeroes the draw's device counters (k_setup_raster, the next kernel on the stream, is their first user), which

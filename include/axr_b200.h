@@ -161,6 +161,10 @@ int axr_get_stats(axr_ctx* ctx, axr_stats* out);
 int axr_set_profiling(axr_ctx* ctx, int enabled);
 int axr_get_kernel_times(axr_ctx* ctx, float ms_out[AXR_NUM_STAGES], uint64_t* draws_out);
 
+/* ---- FP32 issue micro-benchmark: measured warp-instructions per second of this GPU for (0) separate
+ *      FMUL + FADD, which is what the path executes (no contraction, for parity), and (1) FFMA. One warp-instruction = 32 lanes. */
+int axr_measure_fp32_issue(axr_ctx* ctx, double* fmul_fadd_winst_per_s, double* ffma_winst_per_s);
+
 /* ---- pinned host memory for framebuffers / staging (cudaHostAlloc): makes axr_upload_framebuffer / axr_resolve
  *      run at full PCIe rate. Plain malloc'ed memory works too, just slower. */
 void* axr_host_alloc(size_t bytes);
