@@ -490,22 +490,28 @@ int axr_upload_mesh(axr_ctx* ctx, const float* vertices, uint64_t n_verts, const
 	m.materials.assign(ng, Material{});
 	const size_t nv = n_verts ? n_verts : 1, nf = n_faces ? n_faces : 1;
 	float* raw = nullptr;
-	CU(cudaMalloc(&m.pos, nv * sizeof(float4)));
-	CU(cudaMalloc(&m.attr, nv * sizeof(VAttr)));
-	CU(cudaMalloc(&m.sv[0], nv * sizeof(float4)));
-	CU(cudaMalloc(&m.sv[1], nv * sizeof(float4)));
-	CU(cudaMalloc(&m.idx, nf * 3 * sizeof(unsigned)));
-	CU(cudaMalloc(&m.d_materials, ng * sizeof(Material)));
-	CU(cudaMalloc(&m.d_group_first, (ng + 1) * sizeof(unsigned long long)));
+	auto release = [&]() {  // a failed upload leaves nothing behind
+		cudaFree(m.pos); cudaFree(m.attr); cudaFree(m.sv[0]); cudaFree(m.sv[1]); cudaFree(m.idx); cudaFree(m.d_materials);
+		cudaFree(m.d_group_first); cudaFree(raw);
+	};
+#define CUM(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { release(); return fail(ctx, AXR_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
+	CUM(cudaMalloc(&m.pos, nv * sizeof(float4)));
+	CUM(cudaMalloc(&m.attr, nv * sizeof(VAttr)));
+	CUM(cudaMalloc(&m.sv[0], nv * sizeof(float4)));
+	CUM(cudaMalloc(&m.sv[1], nv * sizeof(float4)));
+	CUM(cudaMalloc(&m.idx, nf * 3 * sizeof(unsigned)));
+	CUM(cudaMalloc(&m.d_materials, ng * sizeof(Material)));
+	CUM(cudaMalloc(&m.d_group_first, (ng + 1) * sizeof(unsigned long long)));
 	if (n_verts) {
-		CU(cudaMalloc(&raw, n_verts * 14 * sizeof(float)));
-		CU(cudaMemcpyAsync(raw, vertices, n_verts * 14 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+		CUM(cudaMalloc(&raw, n_verts * 14 * sizeof(float)));
+		CUM(cudaMemcpyAsync(raw, vertices, n_verts * 14 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
 		k_split_vertices<<<(unsigned)((n_verts + 255) / 256), 256, 0, ctx->stream>>>(raw, n_verts, m.pos, m.attr);
 	}
-	if (n_faces) CU(cudaMemcpyAsync(m.idx, indices, n_faces * 3 * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
-	CU(cudaMemcpyAsync(m.d_group_first, m.group_first.data(), (ng + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
-	CU(cudaStreamSynchronize(ctx->stream));
-	if (raw) CU(cudaFree(raw));
+	if (n_faces) CUM(cudaMemcpyAsync(m.idx, indices, n_faces * 3 * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+	CUM(cudaMemcpyAsync(m.d_group_first, m.group_first.data(), (ng + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+	CUM(cudaStreamSynchronize(ctx->stream));
+#undef CUM
+	if (raw) { cudaFree(raw); raw = nullptr; }
 	m.live = true;
 	m.materials_dirty = true;
 	size_t slot = ctx->meshes.size();
