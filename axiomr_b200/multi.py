@@ -169,6 +169,11 @@ class Compositor:
                 shape = ((self.world - 1), self.H, self.W)
                 self.slots.append((torch.as_tensor(_DevArray(self._shared_ptr + co, shape, "<i4"), device=dv),
                                    torch.as_tensor(_DevArray(self._shared_ptr + do, shape, "<f4"), device=dv)))
+            # cleared templates: a set is re-cleared with device-to-device copies (copy engines, no SM time) on a side stream
+            # while GPU 0 renders its own view
+            self.side = torch.cuda.Stream(device=dv)
+            self.tmpl_c = torch.full((self.H, self.W), -16777216, dtype=torch.int32, device=dv)   # 0xFF000000
+            self.tmpl_d = torch.full((self.H, self.W), float("inf"), dtype=torch.float32, device=dv)
             for b in range(2):
                 self._clear_set(b)
             torch.cuda.synchronize()
@@ -177,9 +182,10 @@ class Compositor:
             self.dev.set_depth_read(False)
         dist.barrier()
 
-    def _clear_set(self, b: int, packed_argb: int = -16777216):  # 0xFF000000 as int32
-        self.slots[b][0].fill_(packed_argb)
-        self.slots[b][1].fill_(float("inf"))
+    def _clear_set(self, b: int):
+        for r in range(self.world - 1):
+            self.slots[b][0][r].copy_(self.tmpl_c, non_blocking=True)
+            self.slots[b][1][r].copy_(self.tmpl_d, non_blocking=True)
 
     # ------------------------------------------------------------------ per frame
     @property
@@ -203,10 +209,13 @@ class Compositor:
             co, do = self._slot_offsets(b, self.rank)
             self.dev.set_output(self._shared_ptr + co, self._shared_ptr + do)
         else:
-            # Clear the other set for the next frame, on the render stream, before this frame's draw (ordered after the previous
-            # frame's all-reduce by stream order). Doing it concurrently on a side stream was measured slower: the 66 MB-per-view
-            # fills fight the vertex / setup kernels for L2 and HBM (N = 8: +220 us on GPU 0) — serialised they cost ~80 us.
-            with self.torch.cuda.stream(self.stream):
+            # Clear the other set for the next frame while this one renders: device-to-device copies of a cleared template on a
+            # side stream, ordered after the previous frame's all-reduce. (Fill KERNELS on a side stream were measured slower than
+            # no overlap at all — they fight the vertex / setup kernels for SM slots: N = 8, +220 us on GPU 0.)
+            ready = self.torch.cuda.Event()
+            ready.record(self.stream)
+            with self.torch.cuda.stream(self.side):
+                self.side.wait_event(ready)
                 self._clear_set((b + 1) % 2)
 
     def composite(self):
@@ -221,6 +230,8 @@ class Compositor:
             return
         if self.transport == "peer":
             with torch.cuda.stream(self.stream):
+                if self.rank == 0:
+                    self.stream.wait_stream(self.side)    # the next frame's set is clear
                 dist.all_reduce(self.token)                # every rank's stores of this frame precede anything after it
             return
         ready = torch.cuda.Event()
@@ -239,6 +250,8 @@ class Compositor:
         """Make the render stream wait for every outstanding transfer (call before the closing synchronisation)."""
         if self.mode == "views" and self.transport == "nccl":
             self.stream.wait_stream(self.comm)
+        elif self.mode == "views" and self.rank == 0:
+            self.stream.wait_stream(self.side)
 
     def view_slot(self, b: int, r: int):
         """(colour int32 HxW, depth f32 HxW) of rank r's frame in slot set b, on GPU 0."""
