@@ -135,3 +135,25 @@ def test_obj_loader_matches_reference_loader_golden(tmp_path):
         assert ok.all(), (name, np.argwhere(~ok)[:5])
         assert m.getMaterialGroups()[0].materialName == "m0" and m.getMaterialGroups()[0].faceCount == want.shape[0] * 0 + m.getFaces().shape[0]
     assert abs(m.getMaterial("m0").specularExponent - 0.25) < 1e-7
+
+
+def test_bench_reference_arm_line_and_no_cpu_fallback():
+    """bench.py --impl reference prints ONE JSON line with the contract's keys (tiny workload, runs on the CPU);
+    the B200 arm refuses to run without a GPU instead of falling back."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["vs_baseline"] is None and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "tiny", "--steps", "1"], capture_output=True, text=True, timeout=300)
+        assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
