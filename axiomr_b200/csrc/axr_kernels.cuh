@@ -298,7 +298,6 @@ __global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(
 				for (int tx = tx0; tx <= tx1; ++tx) touch_tile(fp, o, tx, ty);
 		}
 	}
-#ifndef AXR_NO_STATS
 	// counters: warp reduce, then one fire-and-forget reduction per non-zero counter per warp into one of 4096 stripes
 	// (no barrier, no fence, no hot address: warps retire independently); k_scan_tiles folds the stripes
 	__syncwarp();
@@ -311,7 +310,6 @@ __global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(
 		if (w2) atomicAdd(&o.status->stripes[2][stripe], w2);
 		if (w3) atomicAdd(&o.status->stripes[3][stripe], w3);
 	}
-#endif
 }
 
 // ------------------------------------------------------------------------------------------------ bins: scan + scatter
@@ -618,39 +616,16 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 		}
 		__syncthreads();
 	}
-	// 3. deferred shading of the visible triangle of each pixel + framebuffer resolve (one warp = one 128 B row segment).
+	// 3. deferred shading of the visible triangle of each pixel + framebuffer resolve.
 	constexpr int PPT = GT_PIX / TILE_THREADS;
-#ifdef AXR_TILE_PREFETCH
-	//    The index fetches of a thread's four pixels are issued together so their latency is paid once.
-	unsigned ord[PPT], vi[PPT][3];
-#pragma unroll
-	for (int i = 0; i < PPT; ++i) {
-		const unsigned long long k = s_keys[tid + i * TILE_THREADS];
-		ord[i] = (k == KEY_EMPTY) ? 0xFFFFFFFFu : (unsigned)(k & 0xFFFFFFFFull);  // a real ordinal is < 2^32 - 1 (faces < 2^29)
-		if (ord[i] != 0xFFFFFFFFu) {
-			const unsigned* ip = mesh.idx + (size_t)(ord[i] >> 3) * 3;
-			vi[i][0] = __ldg(ip); vi[i][1] = __ldg(ip + 1); vi[i][2] = __ldg(ip + 2);
-		}
-	}
-#pragma unroll
-	for (int i = 0; i < PPT; ++i) {
-		if (ord[i] == 0xFFFFFFFFu) continue;
-		const int p = tid + i * TILE_THREADS;
-		shade_pixel<Shader, SMP>(mesh, u, fp, in, ord[i], vi[i][0], vi[i][1], vi[i][2], x0 + (p & (GT - 1)), y0 + (p / GT));
-	}
-#else
 	//    Not unrolled: one copy of the shading code keeps the kernel inside the instruction cache (unrolled x4 with prefetched
 	//    indices: +12 % time; prefetched indices selected inside a rolled loop: +2 %).
 #pragma unroll 1
 	for (int i = 0; i < PPT; ++i) {
-#ifdef AXR_TILE_ROWS
-		const int p = tid + i * TILE_THREADS;  // a warp = one 32-pixel row segment
-#else
-		// a warp = one compact 8x4 pixel block: neighbouring pixels share triangle vertices, so the 32 lanes of a gather touch
-		// fewer distinct cache lines than along a 32x1 row; the stores still fill whole 32 B sectors (8 px x 4 B per row)
+		// a warp = one compact 8x4 pixel block (neighbouring pixels share triangle vertices); the stores still fill whole 32 B
+		// sectors (8 px x 4 B per row). Measured equal to 32x1 rows on C3.
 		const int blk = i * (TILE_THREADS / 32) + (tid >> 5);
 		const int p = ((blk >> 2) * 4 + ((tid & 31) >> 3)) * GT + (blk & 3) * 8 + (tid & 7);
-#endif
 		const unsigned long long k = s_keys[p];
 		if (k == KEY_EMPTY) continue;
 		const unsigned ord = (unsigned)(k & 0xFFFFFFFFull);
@@ -658,7 +633,6 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 		const unsigned i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
 		shade_pixel<Shader, SMP>(mesh, u, fp, in, ord, i0, i1, i2, x0 + (p & (GT - 1)), y0 + (p / GT));
 	}
-#endif
 }
 
 }  // namespace axr
