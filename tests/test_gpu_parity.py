@@ -384,3 +384,68 @@ def test_gpu_tangent_generation_matches_reference_loader_arithmetic():
             assert ok.all(), name
     finally:
         dev.close()
+
+
+def test_c_abi_error_codes_and_lifecycle(po):
+    """Error conventions of the boundary: negative codes + axr_last_error text, no crashes, handles reusable after free."""
+    from axiomr_b200 import api
+    with pytest.raises(api.AxrError) as e:
+        api.Device(64, 64, band=(8, 40))          # band start must be a multiple of the reference tile (16)
+    assert e.value.code == -1
+    with pytest.raises(api.AxrError):
+        api.Device(0, 64)
+    dev = api.Device(96, 64)
+    try:
+        v, f = S.quad_grid(2)
+        with pytest.raises(api.AxrError) as e:
+            dev.upload_mesh(v, f + 100)            # index out of range
+        assert e.value.code == -1 and "out of range" in str(e.value)
+        with pytest.raises(api.AxrError) as e:
+            dev.upload_mesh(v, f, groups=[(0, 3), (5, 5)])   # groups must tile the face range
+        assert e.value.code == -1
+        m = dev.upload_mesh(v, f)
+        with pytest.raises(api.AxrError) as e:
+            dev.draw_mesh(m + 7, np.eye(4))        # bad handle
+        assert e.value.code == -1
+        with pytest.raises(api.AxrError) as e:
+            dev.set_shader(9, (0, -1, 0))          # IShader subclass without a device functor
+        assert e.value.code == -6
+        dev.set_shader(api.SHADER_PBR, (0, -1, 0), (1, 1, 1))
+        with pytest.raises(api.AxrError) as e:
+            dev.draw_mesh(m, np.eye(4))            # PBR needs five maps: error code instead of the reference's null deref
+        assert e.value.code == -5
+        t = dev.upload_texture(S.diffuse_texture(8))
+        dev.set_material(m, 0, t, t, t, t, t, 0.3)
+        dev.set_uniforms(*S.default_camera(96, 64))
+        dev.clear()
+        dev.draw_mesh(m, np.eye(4))
+        c, d = dev.resolve()
+        assert np.isfinite(d).any()
+        dev.free_texture(t)                        # materials referencing it lose it
+        with pytest.raises(api.AxrError) as e:
+            dev.draw_mesh(m, np.eye(4))
+        assert e.value.code == -5
+        dev.free_mesh(m)
+        with pytest.raises(api.AxrError):
+            dev.free_mesh(m)
+        m2 = dev.upload_mesh(v, f)                 # the slot is reused
+        assert m2 == m
+        dev.set_shader(api.SHADER_FLAT, (0, 0, -1))
+        dev.clear()
+        dev.draw_mesh(m2, np.eye(4))
+        st = dev.stats()
+        assert st["faces"] == f.shape[0] and st["kernel_launches"] == 5
+        # two contexts on one device do not interfere
+        dev2 = api.Device(96, 64)
+        try:
+            sc = S.Scene("q", 96, 64, v, f, S.SHADER_FLAT)
+            mm = dev2.load_scene(sc)
+            dev2.clear()
+            dev2.draw_mesh(mm, sc.model)
+            c2, d2 = dev2.resolve()
+            c0, d0, _ = po.oracle_render(sc)
+            assert np.array_equal(d2.view(np.uint32), d0.view(np.uint32))
+        finally:
+            dev2.close()
+    finally:
+        dev.close()
