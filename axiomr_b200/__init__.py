@@ -4,9 +4,9 @@ Layout: csrc/ (CUDA kernels + the C ABI of include/axr_b200.h -> libaxr_b200.so)
 host-side mirror of the reference's Pipeline / IShader / Mesh / Framebuffer interface), host/ (C++ adapter with the
 reference's class names), scenes.py (synthetic inputs), multi.py (screen-band / multi-view sharding over torch.distributed).
 """
-from .api import (AxrError, Camera, Color, Device, FlatShader, Framebuffer, IShader, Material, MaterialGroup, Mesh,  # noqa: F401
+from .api import (AxrError, Camera, Color, CutoutShader, Device, FlatShader, Framebuffer, IShader, Material, MaterialGroup, Mesh,  # noqa: F401
                   PBRShader, PhongShader, Pipeline, Texture, TiledPipeline, load_library, render_scene,
-                  SAMPLER_BILINEAR, SAMPLER_NEAREST, SHADER_FLAT, SHADER_PBR, SHADER_PHONG)
+                  SAMPLER_BILINEAR, SAMPLER_NEAREST, SHADER_CUTOUT, SHADER_FLAT, SHADER_PBR, SHADER_PHONG)
 
-__all__ = ["AxrError", "Camera", "Color", "Device", "FlatShader", "Framebuffer", "IShader", "Material", "MaterialGroup",
+__all__ = ["AxrError", "Camera", "Color", "CutoutShader", "Device", "FlatShader", "Framebuffer", "IShader", "Material", "MaterialGroup",
            "Mesh", "PBRShader", "PhongShader", "Pipeline", "Texture", "TiledPipeline", "load_library", "render_scene"]

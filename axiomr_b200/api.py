@@ -32,7 +32,7 @@ from . import scenes as _scenes
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AXR_B200_LIB") or os.path.join(HERE, "libaxr_b200.so")  # AXR_B200_LIB: tuning variants
 
-SHADER_FLAT, SHADER_PHONG, SHADER_PBR = 0, 1, 2
+SHADER_FLAT, SHADER_PHONG, SHADER_PBR, SHADER_CUTOUT = 0, 1, 2, 3
 SAMPLER_NEAREST, SAMPLER_BILINEAR = 0, 1
 NO_TEXTURE = -1
 
@@ -526,6 +526,14 @@ class PBRShader(IShader):
     kind = SHADER_PBR
 
 
+@dataclass
+class CutoutShader(IShader):
+    """Not a reference shader: alpha-tested Lambert written against the reference's IShader contract (oracle/ref_harness.cpp),
+    the one shader here whose fragment() discards (texel alpha < 0.5). Draws with it are depth-peeled (axr_b200.h)."""
+    lightDirection: tuple = (0.0, -1.0, 0.0)
+    kind = SHADER_CUTOUT
+
+
 class Pipeline:
     """AR::Pipeline setters (reference src/pipeline.cpp:16-37)."""
 
@@ -595,7 +603,7 @@ class TiledPipeline(Pipeline):
     def drawMesh(self, modelMatrix, mesh: Mesh):
         if self.m_Shader is None or self.m_Camera is None or self.m_Framebuffer is None:
             return  # reference src/tiled_pipeline.cpp:146
-        if getattr(self.m_Shader, "kind", None) not in (SHADER_FLAT, SHADER_PHONG, SHADER_PBR):
+        if getattr(self.m_Shader, "kind", None) not in (SHADER_FLAT, SHADER_PHONG, SHADER_PBR, SHADER_CUTOUT):
             raise AxrError(-6, "no device functor for this IShader subclass (there is no CPU fallback)")
         self._ensure_device()
         self.last_h2d_bytes = 0

@@ -48,6 +48,7 @@ struct PendingDraw {
 	axr_mesh mesh = -1;
 	float model[16];
 	int redo_depth = 0;
+	bool peel = false;
 };
 
 }  // namespace
@@ -112,6 +113,10 @@ struct axr_ctx {
 	std::vector<std::pair<void*, size_t>> registered;  // host ranges page-locked by axr_draw_mesh_host
 	const float* depth_read_override = nullptr;        // set for the duration of one axr_draw_mesh_host
 	int read_depth = 1;
+
+	// depth peeling (draws with a shader that may discard): per-pixel floor keys + the "another pass" flag; allocated on first use
+	unsigned long long* peel_floor = nullptr;
+	unsigned* peel_again = nullptr;
 };
 
 namespace {
@@ -180,7 +185,7 @@ int sync_materials(axr_ctx* ctx, DeviceMesh& m) {
 	return AXR_OK;
 }
 
-int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si);
+int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel);
 
 // Inspect the status of the draw issued last; if its bins overflowed (its tile kernel then did nothing), grow and re-issue.
 // Every API call that touches the context starts here, so at most one draw is ever unchecked and a later draw is never
@@ -209,7 +214,7 @@ int check_pending(axr_ctx* ctx) {
 	rc = reset_raster_state(ctx, p.slot);
 	if (rc) return rc;
 	CU(cudaStreamSynchronize(ctx->stream));
-	rc = issue_draw(ctx, p.mesh, p.model, p.slot);
+	rc = issue_draw(ctx, p.mesh, p.model, p.slot, p.peel);
 	if (rc) return rc;
 	ctx->pending.redo_depth = p.redo_depth + 1;
 	ctx->stats.redo = 1;
@@ -233,15 +238,20 @@ void launch_tile(axr_ctx* ctx, const MeshView& mv, const Uniforms& u, const Tile
 	else k_tile_shade<Shader, 0><<<grid, TILE_THREADS, 0, ctx->stream>>>(mv, u, ctx->fp, in);
 }
 
-int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si) {
+// One pass of the five kernels. peel: the pass belongs to a depth-peeled draw (draw_peeled below) — the raster sites reject
+// keys at or below the pixel's floor, and everything stays on the main stream (the floor buffer is ordered on it).
+int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel) {
 	DeviceMesh& m = ctx->meshes[mh];
 	axr_ctx::DrawSlot& sl = ctx->slot[si];
+	if (peel != (ctx->shader_kind == AXR_SHADER_CUTOUT)) return fail(ctx, AXR_ERR_INVALID, "internal: peel flag does not match the shader");
 	int rc = sync_materials(ctx, m);
 	if (rc) return rc;
 	// shader / material validation (the reference dereferences null textures, include/shaders/shaders.hpp:178,210)
 	for (const Material& mat : m.materials) {
-		if (ctx->shader_kind >= AXR_SHADER_PHONG && (!mat.tex[0].data || !mat.tex[1].data))
+		if ((ctx->shader_kind == AXR_SHADER_PHONG || ctx->shader_kind == AXR_SHADER_PBR) && (!mat.tex[0].data || !mat.tex[1].data))
 			return fail(ctx, AXR_ERR_MATERIAL, "shader needs diffuse + bump textures on every material group");
+		if (ctx->shader_kind == AXR_SHADER_CUTOUT && !mat.tex[0].data)
+			return fail(ctx, AXR_ERR_MATERIAL, "CutoutShader needs a diffuse texture on every material group");
 		if (ctx->shader_kind == AXR_SHADER_PBR && (!mat.tex[2].data || !mat.tex[3].data || !mat.tex[4].data))
 			return fail(ctx, AXR_ERR_MATERIAL, "PBRShader needs metallic, roughness and ao textures on every material group");
 	}
@@ -266,7 +276,7 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si) {
 
 	// ---- geometry stages on geom_stream. The slot was last used two draws ago: wait until that draw's tile kernel has
 	//      consumed it (it resets the keys, flags and cursors it read).
-	cudaStream_t g = ctx->overlap ? ctx->geom_stream : ctx->stream;
+	cudaStream_t g = (ctx->overlap && !peel) ? ctx->geom_stream : ctx->stream;
 	if (sl.used) CU(cudaStreamWaitEvent(g, sl.shade_done, 0));
 	uint64_t launches = 0;
 	prof_mark(ctx, g);
@@ -285,9 +295,12 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si) {
 	const bool tput = m.n_faces >= SMALL_TPUT_MIN_FACES;
 	so.small_dim = tput ? SMALL_DIM_TPUT : SMALL_DIM_LAT;
 	so.small_area = tput ? SMALL_AREA_TPUT : SMALL_AREA_LAT;
+	so.floor = peel ? ctx->peel_floor : nullptr;
 	if (m.n_faces) {
 		const unsigned long long per_cta = (unsigned long long)SETUP_THREADS * SETUP_FPT;
-		k_setup_raster<<<(unsigned)((m.n_faces + per_cta - 1) / per_cta), SETUP_THREADS, 0, g>>>(mv, m.sv[si], u.mvp, ctx->fp, so);
+		const unsigned grid = (unsigned)((m.n_faces + per_cta - 1) / per_cta);
+		if (peel) k_setup_raster<true><<<grid, SETUP_THREADS, 0, g>>>(mv, m.sv[si], u.mvp, ctx->fp, so);
+		else k_setup_raster<false><<<grid, SETUP_THREADS, 0, g>>>(mv, m.sv[si], u.mvp, ctx->fp, so);
 		++launches;
 	}
 	prof_mark(ctx, g);
@@ -310,10 +323,13 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si) {
 	in.items = sl.items; in.records = sl.records; in.n_records = sl.n_records; in.status = sl.d_status; in.sv = m.sv[si];
 	in.color = ctx->out_color; in.depth = ctx->out_depth; in.read_depth = ctx->read_depth;
 	in.depth_read = ctx->depth_read_override ? ctx->depth_read_override : ctx->out_depth;
+	in.floor = peel ? ctx->peel_floor : nullptr;
+	in.again = peel ? ctx->peel_again : nullptr;
 	switch (ctx->shader_kind) {
 	case AXR_SHADER_FLAT: launch_tile<FlatShader>(ctx, mv, u, in); break;
 	case AXR_SHADER_PHONG: launch_tile<PhongShader>(ctx, mv, u, in); break;
 	case AXR_SHADER_PBR: launch_tile<PBRShader>(ctx, mv, u, in); break;
+	case AXR_SHADER_CUTOUT: launch_tile<CutoutShader>(ctx, mv, u, in); break;
 	default: return fail(ctx, AXR_ERR_UNSUPPORTED, "unknown shader kind %d", ctx->shader_kind);
 	}
 	++launches;
@@ -329,7 +345,49 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si) {
 	ctx->pending.mesh = mh;
 	memcpy(ctx->pending.model, model, sizeof(float) * 16);
 	ctx->pending.redo_depth = 0;
+	ctx->pending.peel = peel;
 	return AXR_OK;
+}
+
+// Draw with a shader whose fragment() may discard (reference src/tiled_pipeline.cpp:569-577: the fragment shader runs for
+// every fragment that passes the early-Z test, in triangle order, and a discarded one leaves depth and colour alone). The
+// pixel's final owner is therefore the smallest (z, order) key among its NON-discarded fragments, which the deferred
+// visibility pass cannot know in advance. Depth peeling finds it without ordering anything: pass n keeps, per pixel, the
+// smallest key above that pixel's floor; the tile kernel shades it; if the shader discards it the key becomes the new
+// floor and another pass is needed, otherwise the pixel is finished (floor = KEY_EMPTY, which no key exceeds). Passes
+// repeat until no winner was discarded: 1 + (deepest run of discarded fragments in front of a pixel's owner) passes.
+constexpr int MAX_PEEL_PASSES = 256;
+int draw_peeled(axr_ctx* ctx, axr_mesh mh, const float* model, int si) {
+	const size_t npx = (size_t)ctx->fp.W * ctx->fp.H;
+	if (!ctx->peel_floor) {
+		CU(cudaMalloc(&ctx->peel_floor, npx * 8));
+		CU(cudaMalloc(&ctx->peel_again, 4));
+	}
+	k_fill_u64<<<grid_for(npx, 256), 256, 0, ctx->stream>>>(ctx->peel_floor, 0ull, npx);  // every key is above 0
+	uint64_t launches = 1;
+	for (int pass = 0; pass < MAX_PEEL_PASSES; ++pass) {
+		CU(cudaMemsetAsync(ctx->peel_again, 0, 4, ctx->stream));
+		int rc = issue_draw(ctx, mh, model, si, true);
+		if (rc) return rc;
+		rc = check_pending(ctx);  // bins overflowed: regrown and this pass re-issued (its tile kernel had done nothing)
+		if (rc) return rc;
+		launches += ctx->stats.kernel_launches;
+		unsigned again = 0;
+		CU(cudaMemcpyAsync(&again, ctx->peel_again, 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CU(cudaStreamSynchronize(ctx->stream));
+		if (!again) {
+			ctx->stats.kernel_launches = launches;
+			return AXR_OK;
+		}
+	}
+	return fail(ctx, AXR_ERR_CAPACITY, "more than %d discarded fragments in front of one pixel", MAX_PEEL_PASSES - 1);
+}
+
+// Entry point of every draw call: picks the raster slot and the plain or the peeled path.
+int draw(axr_ctx* ctx, axr_mesh mh, const float* model) {
+	const int si = (int)(ctx->draw_counter++ & 1u);
+	if (ctx->shader_kind == AXR_SHADER_CUTOUT) return draw_peeled(ctx, mh, model, si);
+	return issue_draw(ctx, mh, model, si, false);
 }
 
 // Every host-visible synchronisation waits for both streams.
@@ -445,6 +503,7 @@ void axr_destroy(axr_ctx* ctx) {
 	for (void* p : ctx->shared_allocs) cudaFree(p);
 	for (auto& r : ctx->registered) cudaHostUnregister(r.first);
 	cudaFree(ctx->color); cudaFree(ctx->depth);
+	cudaFree(ctx->peel_floor); cudaFree(ctx->peel_again);
 	for (auto& sl : ctx->slot) {
 		cudaFree(sl.vis); cudaFree(sl.tile_touched); cudaFree(sl.tile_count); cudaFree(sl.bin_start); cudaFree(sl.items);
 		cudaFree(sl.records); cudaFree(sl.n_records); cudaFree(sl.d_status);
@@ -648,7 +707,7 @@ int axr_set_uniforms(axr_ctx* ctx, const float view_proj[16], const float viewpo
 
 int axr_set_shader(axr_ctx* ctx, int kind, const axr_shader_params* params, size_t params_size) {
 	if (!ctx) return AXR_ERR_INVALID;
-	if (kind != AXR_SHADER_FLAT && kind != AXR_SHADER_PHONG && kind != AXR_SHADER_PBR)
+	if (kind != AXR_SHADER_FLAT && kind != AXR_SHADER_PHONG && kind != AXR_SHADER_PBR && kind != AXR_SHADER_CUTOUT)
 		return fail(ctx, AXR_ERR_UNSUPPORTED, "axr_set_shader: no device functor for shader kind %d", kind);
 	if (!params || params_size != sizeof(axr_shader_params)) return fail(ctx, AXR_ERR_INVALID, "axr_set_shader: bad params");
 	ctx->shader_kind = kind;
@@ -707,7 +766,7 @@ int axr_draw_mesh(axr_ctx* ctx, axr_mesh mh, const float model[16]) {
 	CU(cudaSetDevice(ctx->device));
 	int rc = check_pending(ctx);
 	if (rc) return rc;
-	return issue_draw(ctx, mh, model, (int)(ctx->draw_counter++ & 1u));
+	return draw(ctx, mh, model);
 }
 
 // Device-side alias of a host range, page-locking it on first use. Returns nullptr when the range cannot be mapped.
@@ -735,7 +794,7 @@ int axr_draw_mesh_host(axr_ctx* ctx, axr_mesh mh, const float model[16], uint8_t
 	void* dd = dc ? map_host_range(ctx, depth, npx * 4) : nullptr;
 	if (!dc || !dd) {  // not mappable: the plain round trip
 		rc = upload_framebuffer(ctx, bgra, depth, false);
-		if (!rc) rc = issue_draw(ctx, mh, model, (int)(ctx->draw_counter++ & 1u));
+		if (!rc) rc = draw(ctx, mh, model);
 		if (!rc) rc = axr_resolve(ctx, bgra, depth);
 		return rc;
 	}
@@ -743,7 +802,7 @@ int axr_draw_mesh_host(axr_ctx* ctx, axr_mesh mh, const float model[16], uint8_t
 	CU(cudaMemcpyAsync(ctx->depth + first, depth + first, n * 4, cudaMemcpyHostToDevice, ctx->stream));
 	unsigned* save_c = ctx->out_color; float* save_d = ctx->out_depth;
 	ctx->out_color = (unsigned*)dc; ctx->out_depth = (float*)dd; ctx->depth_read_override = ctx->depth;
-	rc = issue_draw(ctx, mh, model, (int)(ctx->draw_counter++ & 1u));
+	rc = draw(ctx, mh, model);
 	if (!rc) rc = check_pending(ctx);  // a bin overflow re-issues the draw while the host pointers are still installed
 	ctx->out_color = save_c; ctx->out_depth = save_d; ctx->depth_read_override = nullptr;
 	if (rc) return rc;

@@ -15,6 +15,9 @@
 //                                        gather indices -> screen records / positions / attributes / framebuffer depth in one
 //                                        batch -> setup -> barycentrics -> depth test -> IShader::vertex x3 accumulated into
 //                                        varyings -> IShader::fragment (textures from HBM) -> BGRA8 + f32 store
+// A shader whose fragment() may discard (Shader::DISCARDS) makes visibility depend on shading; such a draw is depth-peeled:
+// the same kernels run in passes, every pass only accepts keys above the pixel's `floor` (the key of the fragment discarded
+// there in the previous pass), and the host repeats until no winner was discarded (axr_api.cu: draw_peeled).
 // Nothing here is a dense contraction, so there is no tensor-core work; the path is gather-, latency- and FP32-issue bound.
 #pragma once
 #include <cooperative_groups.h>
@@ -151,6 +154,7 @@ struct SetupOut {
 	unsigned* n_records;         // device counter (also the number wanted when it overflows)
 	DrawStatus* status;
 	int small_dim, small_area;   // direct-raster limits of this draw
+	const unsigned long long* floor;  // depth peeling only (PEEL): per pixel, keys <= floor have been dealt with
 };
 
 struct EmitCounters { unsigned tris, small, binned; };
@@ -165,6 +169,7 @@ __device__ __forceinline__ void touch_tile(const FrameParams& fp, const SetupOut
 
 // touched: when non-null the caller flags the tiles later (warp-aggregated); it receives the tile rect of the pixel box
 // packed as tx0 | ty0<<8 | tx1<<16 | ty1<<24 in units of GPU tiles (frames up to 8192 px), or stays 0xFFFFFFFF.
+template <bool PEEL>
 __device__ __forceinline__ void emit_triangle(const FrameParams& fp, const SetupOut& o, float x0, float y0, float x1, float y1,
                                               float x2, float y2, float z0, float z1, float z2, unsigned ordinal, EmitCounters& cnt,
                                               unsigned* touched) {
@@ -179,7 +184,11 @@ __device__ __forceinline__ void emit_triangle(const FrameParams& fp, const Setup
 			float al, be, ga;
 			const float z = interp_z(s, c0, c1, c2, al, be, ga);
 			if (!z_draws(z)) return;
-			atomicMin(o.vis + (size_t)py * fp.W + px, make_key(z, ordinal));  // result unused -> RED.MIN.64, fire and forget
+			const unsigned long long key = make_key(z, ordinal);
+			if constexpr (PEEL) {
+				if (!(key > o.floor[(size_t)py * fp.W + px])) return;
+			}
+			atomicMin(o.vis + (size_t)py * fp.W + px, key);  // result unused -> RED.MIN.64, fire and forget
 			any = true;
 		});
 		if (any) {
@@ -210,6 +219,7 @@ __device__ __forceinline__ void emit_triangle(const FrameParams& fp, const Setup
 }
 
 // Clip slow path of one face for the visibility pass (positions only): reference src/tiled_pipeline.cpp:210-234
+template <bool PEEL>
 __device__ __noinline__ void setup_clipped_face(const FrameParams& fp, const SetupOut& o, const m4& mvp, float4 p0, float4 p1,
                                                 float4 p2, unsigned face, EmitCounters& cnt) {
 	ClipPos a[MAX_CLIPPED_VERTS], b[MAX_CLIPPED_VERTS];
@@ -225,7 +235,7 @@ __device__ __noinline__ void setup_clipped_face(const FrameParams& fp, const Set
 		to_screen(out[j + 1].clip, fW, fH, x1, y1, z1);
 		to_screen(out[j + 2].clip, fW, fH, x2, y2, z2);
 		if (is_backface(x0, y0, x1, y1, x2, y2)) continue;
-		emit_triangle(fp, o, x0, y0, x1, y1, x2, y2, z0, z1, z2, face * 8u + (unsigned)(j / 3), cnt, nullptr);
+		emit_triangle<PEEL>(fp, o, x0, y0, x1, y1, x2, y2, z0, z1, z2, face * 8u + (unsigned)(j / 3), cnt, nullptr);
 	}
 }
 
@@ -244,6 +254,7 @@ constexpr int SETUP_THREADS = AXR_SETUP_THREADS;
 #endif
 constexpr int SETUP_FPT = AXR_SETUP_FPT;  // faces per thread: index loads and 16 B screen-record gathers of all of them are issued back to back
 
+template <bool PEEL>
 __global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(const __grid_constant__ MeshView mesh, const float4* __restrict__ sv,
                                                                 const __grid_constant__ m4 mvp, const __grid_constant__ FrameParams fp,
                                                                 const __grid_constant__ SetupOut o) {
@@ -280,12 +291,12 @@ __global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(
 			if (((k0 | k1 | k2) & 0x3fu) == 0) {
 				// every vertex inside every plane: clipTriangle returns the triangle unchanged (reference src/pipeline.cpp:322-325)
 				if (!is_backface(s0.x, s0.y, s1.x, s1.y, s2.x, s2.y))
-					emit_triangle(fp, o, s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, (unsigned)f * 8u, cnt, &touched);
+					emit_triangle<PEEL>(fp, o, s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, (unsigned)f * 8u, cnt, &touched);
 			} else if ((k0 & k1 & k2) >> 8) {
 				// all three vertices safely outside one plane: clipTriangle returns nothing (see clip_code_safe_out)
 			} else {
 				clipped++;
-				setup_clipped_face(fp, o, mvp, __ldg(mesh.pos + i0), __ldg(mesh.pos + i1), __ldg(mesh.pos + i2), (unsigned)f, cnt);
+				setup_clipped_face<PEEL>(fp, o, mvp, __ldg(mesh.pos + i0), __ldg(mesh.pos + i1), __ldg(mesh.pos + i2), (unsigned)f, cnt);
 			}
 		}
 		// tile flags of the direct path, warp-aggregated: consecutive faces of a mesh land in the same one or two tiles, so one
@@ -433,6 +444,8 @@ struct TileIn {
 	float* depth;
 	const float* depth_read;        // where the merge test reads fbZ from (== depth unless the output is write-only host memory)
 	int read_depth;                 // 0: the caller guarantees depth == +inf everywhere (freshly cleared single-draw target)
+	unsigned long long* floor;      // depth peeling only (Shader::DISCARDS): per-pixel key of the last discarded winner
+	unsigned* again;                // depth peeling only: set when some winner was discarded in this pass
 };
 
 __device__ __forceinline__ unsigned pack_bgra(v4 c) {
@@ -461,19 +474,21 @@ __device__ __forceinline__ void accumulate_vertex(const Uniforms& u, int k, floa
 	for (int i = 0; i < Shader::NV; ++i) var[i] = (k == 0) ? o[i] * w : var[i] + o[i] * w;
 }
 
+// Returns IShader::fragment's discard flag (reference src/tiled_pipeline.cpp:571-577: a discarded fragment leaves depth and colour).
 template <typename Shader, int SMP>
-__device__ __forceinline__ void finish_pixel(const MeshView& mesh, const Uniforms& u, const TileIn& in, unsigned face, size_t gi, float z,
+__device__ __forceinline__ bool finish_pixel(const MeshView& mesh, const Uniforms& u, const TileIn& in, unsigned face, size_t gi, float z,
                                              const float* var) {
 	v4 col;
-	if (Shader::template fragment<SMP>(u, face_material(mesh, face), var, col)) return;  // true = discard (none of the shipped shaders does)
+	if (Shader::template fragment<SMP>(u, face_material(mesh, face), var, col)) return true;
 	in.depth[gi] = z;
 	in.color[gi] = pack_bgra(col);
+	return false;
 }
 
 // Pixel whose visible triangle comes from a clipped face: re-derive sub-triangle (ordinal & 7) with full attributes
 // (reference src/pipeline.cpp:176-272). Rare; kept out of line so its stack frame does not burden the common path.
 template <typename Shader, int SMP>
-__device__ __noinline__ void shade_pixel_clipped(const MeshView& mesh, const Uniforms& u, const FrameParams& fp, const TileIn& in,
+__device__ __noinline__ bool shade_pixel_clipped(const MeshView& mesh, const Uniforms& u, const FrameParams& fp, const TileIn& in,
                                                  unsigned ordinal, unsigned i0, unsigned i1, unsigned i2, int px, int py) {
 	ClipFull a[MAX_CLIPPED_VERTS], b[MAX_CLIPPED_VERTS];
 	const unsigned vi[3] = {i0, i1, i2};
@@ -490,27 +505,28 @@ __device__ __noinline__ void shade_pixel_clipped(const MeshView& mesh, const Uni
 	ClipFull* out;
 	const int n = clip_triangle(a, b, &out);
 	const int sub = (int)(ordinal & 7u);
-	if (sub * 3 + 2 >= n) return;
+	if (sub * 3 + 2 >= n) return false;
 	const ClipFull* c = out + sub * 3;
 	float sx[3], sy[3], sz[3];
 	for (int k = 0; k < 3; ++k) to_screen(c[k].clip, (float)fp.W, (float)fp.H, sx[k], sy[k], sz[k]);
 	Setup s;
-	if (!setup_triangle(sx[0], sy[0], sx[1], sy[1], sx[2], sy[2], sz[0], sz[1], sz[2], fp.W, fp.y_lo, fp.y_hi, s)) return;
+	if (!setup_triangle(sx[0], sy[0], sx[1], sy[1], sx[2], sy[2], sz[0], sz[1], sz[2], fp.W, fp.y_lo, fp.y_hi, s)) return false;
 	float c0, c1, c2, al, be, ga;
 	coverage(s, px, py, c0, c1, c2);
 	const float z = interp_z(s, c0, c1, c2, al, be, ga);
 	const size_t gi = (size_t)py * fp.W + px;
-	if (!(z < (in.read_depth ? in.depth_read[gi] : INFINITY))) return;
+	if (!(z < (in.read_depth ? in.depth_read[gi] : INFINITY))) return false;
 	float var[Shader::NV];
 	const float w[3] = {al, be, ga};
 	for (int k = 0; k < 3; ++k) accumulate_vertex<Shader>(u, k, w[k], c[k].pos, c[k].n, c[k].t, c[k].b, c[k].uv[0], c[k].uv[1], var);
-	finish_pixel<Shader, SMP>(mesh, u, in, ordinal >> 3, gi, z, var);
+	return finish_pixel<Shader, SMP>(mesh, u, in, ordinal >> 3, gi, z, var);
 }
 
 // One visible pixel: all gathers that depend only on the vertex indices are issued together (screen records, positions,
 // attributes, framebuffer depth), then setup -> barycentrics -> depth test -> IShader::vertex x3 -> IShader::fragment.
+// Returns true when the fragment was discarded by the shader (false also when it lost the depth test).
 template <typename Shader, int SMP>
-__device__ __forceinline__ void shade_pixel(const MeshView& mesh, const Uniforms& u, const FrameParams& fp, const TileIn& in,
+__device__ __forceinline__ bool shade_pixel(const MeshView& mesh, const Uniforms& u, const FrameParams& fp, const TileIn& in,
                                             unsigned ordinal, unsigned i0, unsigned i1, unsigned i2, int px, int py) {
 	const size_t gi = (size_t)py * fp.W + px;
 	const float4 s0 = __ldg(in.sv + i0), s1 = __ldg(in.sv + i1), s2 = __ldg(in.sv + i2);
@@ -523,26 +539,26 @@ __device__ __forceinline__ void shade_pixel(const MeshView& mesh, const Uniforms
 	const float4 a20 = __ldg(ap2), a21 = __ldg(ap2 + 1), a22 = __ldg(ap2 + 2);
 	const float fbz = in.read_depth ? in.depth_read[gi] : INFINITY;
 	if ((__float_as_uint(s0.w) | __float_as_uint(s1.w) | __float_as_uint(s2.w)) & 0x3fu) {
-		shade_pixel_clipped<Shader, SMP>(mesh, u, fp, in, ordinal, i0, i1, i2, px, py);
-		return;
+		return shade_pixel_clipped<Shader, SMP>(mesh, u, fp, in, ordinal, i0, i1, i2, px, py);
 	}
 	Setup s;
-	if (!setup_triangle(s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, fp.W, fp.y_lo, fp.y_hi, s)) return;
+	if (!setup_triangle(s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, fp.W, fp.y_lo, fp.y_hi, s)) return false;
 	float c0, c1, c2, al, be, ga;
 	coverage(s, px, py, c0, c1, c2);
 	const float z = interp_z(s, c0, c1, c2, al, be, ga);
 	// mergeTileResults: strict tileZ < fbZ (reference src/tiled_pipeline.cpp:1148-1156)
-	if (!(z < fbz)) return;
+	if (!(z < fbz)) return false;
 	float var[Shader::NV];
 	accumulate_vertex<Shader>(u, 0, al, V3(p0.x, p0.y, p0.z), V3(a00.z, a00.w, a01.x), V3(a01.y, a01.z, a01.w), V3(a02.x, a02.y, a02.z), a00.x, a00.y, var);
 	accumulate_vertex<Shader>(u, 1, be, V3(p1.x, p1.y, p1.z), V3(a10.z, a10.w, a11.x), V3(a11.y, a11.z, a11.w), V3(a12.x, a12.y, a12.z), a10.x, a10.y, var);
 	accumulate_vertex<Shader>(u, 2, ga, V3(p2.x, p2.y, p2.z), V3(a20.z, a20.w, a21.x), V3(a21.y, a21.z, a21.w), V3(a22.x, a22.y, a22.z), a20.x, a20.y, var);
-	finish_pixel<Shader, SMP>(mesh, u, in, ordinal >> 3, gi, z, var);
+	return finish_pixel<Shader, SMP>(mesh, u, in, ordinal >> 3, gi, z, var);
 }
 
 template <typename Shader, int SMP>
 __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(const __grid_constant__ MeshView mesh, const __grid_constant__ Uniforms u, const __grid_constant__ FrameParams fp,
                                                                              const __grid_constant__ TileIn in) {
+	constexpr bool PEEL = Shader::DISCARDS;
 	__shared__ unsigned long long s_keys[GT_PIX];
 	if (in.status->overflow) return;  // the host grows the bins and re-issues the draw
 	const int tx = blockIdx.x, ty = fp.ty_lo + blockIdx.y;
@@ -610,7 +626,11 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 						if (!coverage(q, px, py, c0, c1, c2)) continue;
 						const float z = interp_z(q, c0, c1, c2, al, be, ga);
 						if (!z_draws(z)) continue;
-						atomicMin(&s_keys[(py - y0) * GT + (px - x0)], make_key(z, qord));
+						const unsigned long long key = make_key(z, qord);
+						if constexpr (PEEL) {
+							if (!(key > in.floor[(size_t)py * fp.W + px])) continue;
+						}
+						atomicMin(&s_keys[(py - y0) * GT + (px - x0)], key);
 					}
 			}
 		}
@@ -631,7 +651,16 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 		const unsigned ord = (unsigned)(k & 0xFFFFFFFFull);
 		const unsigned* ip = mesh.idx + (size_t)(ord >> 3) * 3;
 		const unsigned i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
-		shade_pixel<Shader, SMP>(mesh, u, fp, in, ord, i0, i1, i2, x0 + (p & (GT - 1)), y0 + (p / GT));
+		const int px = x0 + (p & (GT - 1)), py = y0 + (p / GT);
+		const bool discarded = shade_pixel<Shader, SMP>(mesh, u, fp, in, ord, i0, i1, i2, px, py);
+		if constexpr (PEEL) {
+			// discarded: the next pass looks for this pixel's next key above k. Otherwise the pixel is finished (the winner
+			// was drawn, or it lost against the framebuffer and everything behind it would too): no key passes KEY_EMPTY.
+			in.floor[(size_t)py * fp.W + px] = discarded ? k : KEY_EMPTY;
+			if (discarded && *in.again == 0u) *in.again = 1u;
+		} else {
+			(void)discarded;
+		}
 	}
 }
 

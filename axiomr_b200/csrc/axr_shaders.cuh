@@ -37,6 +37,7 @@ struct Uniforms {
 //   Phong / PBR: [0..1] uv, [2..4] worldPos, [5..13] tbn columns T,B,N
 constexpr int VARY_FLAT = 3;
 constexpr int VARY_TBN = 14;
+constexpr int VARY_CUTOUT = 5;  // CutoutShader: [0..1] uv, [2..4] normal
 
 // ------------------------------------------------------------------ Texture::sample (reference include/texture.hpp:12-34)
 __device__ __forceinline__ v4 texel(const TexRef& t, int x, int y) {
@@ -92,6 +93,7 @@ __device__ __forceinline__ void vertex_tbn(const Uniforms& u, v3 pos, v3 n, v3 t
 // --------------------------------------------------------------------------------------------- FlatShader :19-61
 struct FlatShader {
 	static constexpr int NV = VARY_FLAT;
+	static constexpr bool DISCARDS = false;  // fragment() never returns true: visibility does not depend on shading
 	__device__ __forceinline__ static void vertex(const Uniforms& u, v3 pos, v3 n, v3 t, v3 b, float uvx, float uvy, float* o) {
 		v3 r = mul(u.normal_mat, n);
 		o[0] = r.x; o[1] = r.y; o[2] = r.z;
@@ -109,6 +111,7 @@ struct FlatShader {
 // --------------------------------------------------------------------------------------------- PhongShader :136-250
 struct PhongShader {
 	static constexpr int NV = VARY_TBN;
+	static constexpr bool DISCARDS = false;
 	__device__ __forceinline__ static void vertex(const Uniforms& u, v3 pos, v3 n, v3 t, v3 b, float uvx, float uvy, float* o) {
 		vertex_tbn(u, pos, n, t, b, uvx, uvy, o);
 	}
@@ -144,6 +147,7 @@ struct PhongShader {
 // --------------------------------------------------------------------------------------------- PBRShader :252-423
 struct PBRShader {
 	static constexpr int NV = VARY_TBN;
+	static constexpr bool DISCARDS = false;
 	__device__ __forceinline__ static void vertex(const Uniforms& u, v3 pos, v3 n, v3 t, v3 b, float uvx, float uvy, float* o) {
 		vertex_tbn(u, pos, n, t, b, uvx, uvy, o);
 	}
@@ -197,6 +201,31 @@ struct PBRShader {
 		fc = fc / (fc + one);
 		const float g = 1.0f / 2.2f;
 		color = V4(powf(fc.x, g), powf(fc.y, g), powf(fc.z, g), 1.0f);
+		return false;
+	}
+};
+
+// --------------------------------------------------------------------------------------------- CutoutShader
+// Not a reference shader: the reference ships none whose fragment() returns true, so its discard branch
+// (src/tiled_pipeline.cpp:571-577) is exercised with an IShader of our own, defined against the reference's plugin
+// contract in oracle/ref_harness.cpp (struct CutoutShader) and restated here: FlatShader's vertex stage plus uv, Lambert
+// times the diffuse texel, fragments whose texel alpha is below 0.5 are discarded. DISCARDS = true makes the draw take the
+// depth-peeling path (k_setup_raster<true> + the peel branch of k_tile_shade).
+struct CutoutShader {
+	static constexpr int NV = VARY_CUTOUT;
+	static constexpr bool DISCARDS = true;
+	__device__ __forceinline__ static void vertex(const Uniforms& u, v3 pos, v3 n, v3 t, v3 b, float uvx, float uvy, float* o) {
+		v3 r = mul(u.normal_mat, n);
+		o[0] = uvx; o[1] = uvy;
+		o[2] = r.x; o[3] = r.y; o[4] = r.z;
+	}
+	template <int SMP>
+	__device__ __forceinline__ static bool fragment(const Uniforms& u, const Material& m, const float* var, v4& color) {
+		v4 texl = sample<SMP>(m.tex[0], var[0], var[1]);
+		if (texl.w < 0.5f) return true;
+		v3 n = normalize(V3(var[2], var[3], var[4]));
+		float intensity = clampf(dot(-u.light_dir, n), 0.0f, 1.0f);
+		color = V4(texl.x * intensity, texl.y * intensity, texl.z * intensity, 1.0f);
 		return false;
 	}
 };

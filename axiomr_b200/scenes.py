@@ -97,6 +97,18 @@ def diffuse_texture(size: int) -> np.ndarray:
     return t
 
 
+def cutout_texture(size: int, cell: int = 8) -> np.ndarray:
+    """Diffuse map with an alpha channel for the discard test (alpha < 0.5 is cut): holes on a checkerboard of `cell` texels,
+    plus a band of alpha values 120..135 that straddle the threshold (127/255 < 0.5 <= 128/255)."""
+    t = diffuse_texture(size)
+    y, x = np.mgrid[0:size, 0:size].astype(np.int64)
+    a = np.where((((x // cell) + (y // cell)) & 1) == 1, 255, 0)
+    band = (y >= size // 2) & (y < size // 2 + max(1, size // 16))
+    a = np.where(band, 120 + (x & 15), a)
+    t[..., 3] = a.astype(np.uint8)
+    return t
+
+
 def normal_texture(size: int, bumps: int = 8, strength: float = 4.0) -> np.ndarray:
     y, x = np.mgrid[0:size, 0:size].astype(np.float64)
     kx = 2.0 * math.pi * bumps / size
@@ -250,7 +262,7 @@ def random_triangles(n: int, seed: int, extent: float = 3.0, size: float = 0.5, 
 
 
 # --------------------------------------------------------------------------- scene container
-SHADER_FLAT, SHADER_PHONG, SHADER_PBR = 0, 1, 2
+SHADER_FLAT, SHADER_PHONG, SHADER_PBR, SHADER_CUTOUT = 0, 1, 2, 3  # 3: alpha-tested Lambert, the one shader that discards
 SAMPLER_NEAREST, SAMPLER_BILINEAR = 0, 1
 
 
@@ -321,6 +333,20 @@ def config4(n: int = 3162, w: int = 3840, h: int = 2160) -> Scene:
     """C4: torus n x n (20 M sub-pixel tris) at 4K, FlatShader."""
     v, f = torus(n, n)
     return Scene(f"c4_torus{n}_flat_{w}x{h}", w, h, v, f, SHADER_FLAT, model=_f32(rotate_y(0.5)))
+
+
+def cutout_layers(w: int = 320, h: int = 240, layers: int = 5, grid: int = 6, tex: int = 64, size: float = 2.6,
+                  sampler: int = SAMPLER_NEAREST) -> Scene:
+    """Discard test scene: `layers` textured quad grids stacked in depth (nearest drawn LAST, so every layer's fragments reach the
+    shader in the reference), alpha-tested; through the holes of one layer the next one shows, through all of them the clear."""
+    vs, fs, base = [], [], 0
+    for i in range(layers):
+        v, f = quad_grid(grid, size=size - 0.2 * i, z=-1.0 + 0.45 * i)
+        v = v.copy()
+        v[:, 3:5] = v[:, 3:5] * (0.55 + 0.05 * i) + 0.04 * i  # a different uv window per layer, inside [0, 1]
+        vs.append(v); fs.append(f + base); base += v.shape[0]
+    return Scene(f"cutout_{layers}layers_{w}x{h}", w, h, np.concatenate(vs), np.concatenate(fs), SHADER_CUTOUT, sampler,
+                 model=_f32(rotate_y(0.35)), textures=[cutout_texture(tex), None, None, None, None])
 
 
 def view_matrix_for(i: int, n_views: int, w: int, h: int):

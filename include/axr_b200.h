@@ -39,8 +39,12 @@ typedef enum axr_status {
 	AXR_ERR_UNSUPPORTED = -6  /* unknown shader kind (reference: any IShader subclass; device functors exist for the shipped ones) */
 } axr_status;
 
-/* IShader implementations with a device functor (reference include/shaders/shaders.hpp:19-58, 136-250, 252-423). */
-typedef enum axr_shader_kind { AXR_SHADER_FLAT = 0, AXR_SHADER_PHONG = 1, AXR_SHADER_PBR = 2 } axr_shader_kind;
+/* IShader implementations with a device functor (reference include/shaders/shaders.hpp:19-58, 136-250, 252-423).
+ * AXR_SHADER_CUTOUT is not a reference shader: none of the shipped ones ever returns true (= discard) from fragment()
+ * (include/IShader.hpp:38), so the discard branch of the raster loop (src/tiled_pipeline.cpp:571-577) is covered with an
+ * alpha-tested Lambert shader written against the reference's IShader contract (oracle/ref_harness.cpp: CutoutShader;
+ * needs the diffuse texture, discards where its alpha < 0.5). A draw with it is depth-peeled and synchronous. */
+typedef enum axr_shader_kind { AXR_SHADER_FLAT = 0, AXR_SHADER_PHONG = 1, AXR_SHADER_PBR = 2, AXR_SHADER_CUTOUT = 3 } axr_shader_kind;
 
 /* Texture::sample mode. NEAREST is the reference (include/texture.hpp:12-34). BILINEAR is an extension
  * (BASELINE.json config 3) with no reference counterpart; it is checked against oracle/axr_oracle.c only. */

@@ -348,8 +348,9 @@ typedef struct {
 /* FlatShader::vertex :26-40, PhongShader::vertex :147-168, PBRShader::vertex :259-282 */
 static void shader_vertex(const uniforms_t* u, const vertex_t* vin, vsout_t* o) {
 	memset(o, 0, sizeof *o);
-	if (u->kind == 0) {
+	if (u->kind == 0 || u->kind == 3) {
 		o->normal = m3_mul_v3(&u->normal_mat, ld3(vin->normal));
+		if (u->kind == 3) { o->uv[0] = vin->uv[0]; o->uv[1] = vin->uv[1]; }
 		return;
 	}
 	o->uv[0] = vin->uv[0]; o->uv[1] = vin->uv[1];
@@ -455,10 +456,24 @@ static void fragment_pbr(const uniforms_t* u, const float bar[3], const vsout_t*
 	const float g = 1.0f / 2.2f;
 	out[0] = powf(fc.x, g); out[1] = powf(fc.y, g); out[2] = powf(fc.z, g); out[3] = 1.0f;
 }
-static inline void shader_fragment(const uniforms_t* u, const float bar[3], const vsout_t* vs, float out[4]) {
+/* CutoutShader (oracle/ref_harness.cpp; not a reference shader): alpha-tested Lambert, returns 1 = discard */
+static int fragment_cutout(const uniforms_t* u, const float bar[3], const vsout_t* vs, float out[4]) {
+	float uvx = bar[0] * vs[0].uv[0] + bar[1] * vs[1].uv[0] + bar[2] * vs[2].uv[0];
+	float uvy = bar[0] * vs[0].uv[1] + bar[1] * vs[1].uv[1] + bar[2] * vs[2].uv[1];
+	v4 texl = sample(&u->tex[0], uvx, uvy, u->sampler);
+	if (texl.w < 0.5f) return 1;
+	v3 n = norm3(bary3(bar, vs[0].normal, vs[1].normal, vs[2].normal));
+	float intensity = clampf(dot3(neg3(u->light_dir), n), 0.0f, 1.0f);
+	out[0] = texl.x * intensity; out[1] = texl.y * intensity; out[2] = texl.z * intensity; out[3] = 1.0f;
+	return 0;
+}
+/* returns the reference's `discard` flag (IShader::fragment, include/IShader.hpp:38) */
+static inline int shader_fragment(const uniforms_t* u, const float bar[3], const vsout_t* vs, float out[4]) {
 	if (u->kind == 0) fragment_flat(u, bar, vs, out);
 	else if (u->kind == 1) fragment_phong(u, bar, vs, out);
-	else fragment_pbr(u, bar, vs, out);
+	else if (u->kind == 2) fragment_pbr(u, bar, vs, out);
+	else return fragment_cutout(u, bar, vs, out);
+	return 0;
 }
 
 /* ------------------------------------------------------------------ per-tile raster: src/tiled_pipeline.cpp:427-594 */
@@ -504,7 +519,7 @@ static void raster_tri_in_tile(const uniforms_t* u, const tri_t* tri, int tsx, i
 				int idx = (py - tsy) * TILE_SIZE + (curX - tsx);
 				if (z < buf->depth[idx]) {
 					float col[4];
-					shader_fragment(u, bar, tri->vs, col);  /* none of the shipped shaders discards */
+					if (shader_fragment(u, bar, tri->vs, col)) continue;  /* :571-577: discard keeps depth and colour */
 					buf->depth[idx] = z;
 					for (int c = 0; c < 4; ++c) buf->color[idx * 4 + c] = (uint8_t)cvtt(clampf(col[c], 0.0f, 1.0f) * 255.0f);
 				}
@@ -650,7 +665,9 @@ int axo_render(const axo_scene* sc, const float* vertices, uint64_t n_verts, con
 	u.light_color = ld3(sc->light_color);
 	u.specular_exponent = sc->specular_exponent;
 	for (int i = 0; i < 5; ++i) { u.tex[i].data = sc->tex[i]; u.tex[i].w = sc->tex_w[i]; u.tex[i].h = sc->tex_h[i]; }
-	if (u.kind >= 1 && (!u.tex[0].data || !u.tex[1].data)) return -2;
+	if (u.kind < 0 || u.kind > 3) return -2;
+	if ((u.kind == 1 || u.kind == 2) && (!u.tex[0].data || !u.tex[1].data)) return -2;
+	if (u.kind == 3 && !u.tex[0].data) return -2;
 	if (u.kind == 2 && (!u.tex[2].data || !u.tex[3].data || !u.tex[4].data)) return -2;
 	struct timespec t0, t1;
 	clock_gettime(CLOCK_MONOTONIC, &t0);

@@ -10,7 +10,7 @@ extern "C" {
 typedef struct axo_scene {
 	int width, height;
 	int threads;              /* tile workers (results do not depend on it) */
-	int shader_kind;          /* 0 FlatShader, 1 PhongShader, 2 PBRShader */
+	int shader_kind;          /* 0 FlatShader, 1 PhongShader, 2 PBRShader, 3 CutoutShader (ref_harness.cpp: discards) */
 	float light_dir[3];
 	float light_color[3];
 	float specular_exponent;

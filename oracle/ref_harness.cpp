@@ -78,6 +78,31 @@ std::unique_ptr<AR::Texture> make_texture(const uint8_t* rgba, int w, int h, int
 	return t;
 }
 
+// A fourth IShader, written for this harness: the reference ships no shader that returns true (= discard) from fragment(),
+// so its discard branch (reference src/tiled_pipeline.cpp:571-577) would otherwise have no parity target. Alpha-tested
+// Lambert: FlatShader's normal handling (include/shaders/shaders.hpp:26-57) plus the diffuse texel; fragments whose texel
+// alpha is below 0.5 are discarded. It runs inside the UNMODIFIED reference pipeline through the IShader plugin contract
+// (include/IShader.hpp:30-46); oracle/axr_oracle.c (kind 3) and the CUDA CutoutShader functor restate it.
+struct CutoutShader : public AR::IShader {
+	glm::vec3 lightDirection;
+	AR::VertexOutput vertex(const AR::Vertex& v, int) override {
+		AR::VertexOutput o;
+		o.uv = v.uv;
+		o.normal = glm::mat3(glm::transpose(glm::inverse(model))) * v.normal;
+		return o;
+	}
+	bool fragment(glm::vec3& bar, glm::vec4& color, const AR::VSTransformedTriangle& tri) override {
+		glm::vec2 uv = bar.x * tri[0].uv + bar.y * tri[1].uv + bar.z * tri[2].uv;
+		glm::vec4 texel = material->diffuseTexture->sample(uv);
+		if (texel.a < 0.5f) return true;
+		glm::vec3 n = bar.x * tri[0].normal + bar.y * tri[1].normal + bar.z * tri[2].normal;
+		n = glm::normalize(n);
+		float intensity = std::clamp(glm::dot(-lightDirection, n), 0.0f, 1.0f);
+		color = glm::vec4(glm::vec3(texel) * intensity, 1.0f);
+		return false;
+	}
+};
+
 glm::mat4 to_mat4(const float* m) {
 	glm::mat4 r;
 	for (int c = 0; c < 4; ++c) r[c] = glm::vec4(m[c * 4 + 0], m[c * 4 + 1], m[c * 4 + 2], m[c * 4 + 3]);
@@ -94,7 +119,7 @@ extern "C" {
 struct axr_ref_scene {
 	int width, height;
 	int threads;             // TiledPipeline(threads, ...) (reference src/renderer.cpp:71 passes hardware_concurrency)
-	int shader_kind;         // 0 FlatShader, 1 PhongShader, 2 PBRShader
+	int shader_kind;         // 0 FlatShader, 1 PhongShader, 2 PBRShader, 3 CutoutShader (above; needs the diffuse texture)
 	float light_dir[3];
 	float light_color[3];
 	float specular_exponent; // Material::specularExponent ("Ns")
@@ -147,8 +172,11 @@ int axr_ref_render(const axr_ref_scene* sc, const float* vertices, uint64_t n_ve
 		flat.lightDirection = L;
 		phong.lightDirection = L; phong.lightColor = LC;
 		pbr.lightDirection = L; pbr.lightColor = LC;
+		CutoutShader cutout;
+		cutout.lightDirection = L;
 		AR::IShader* shader = sc->shader_kind == 0 ? (AR::IShader*)&flat
-		                    : sc->shader_kind == 1 ? (AR::IShader*)&phong : (AR::IShader*)&pbr;
+		                    : sc->shader_kind == 1 ? (AR::IShader*)&phong
+		                    : sc->shader_kind == 2 ? (AR::IShader*)&pbr : (AR::IShader*)&cutout;
 
 		// heap: the object embeds a 32 MB arena (include/tiled_pipeline.hpp:103)
 		std::unique_ptr<AR::TiledPipeline> pipe(new AR::TiledPipeline((size_t)std::max(1, sc->threads), &cam, &fb));
@@ -166,7 +194,8 @@ int axr_ref_render(const axr_ref_scene* sc, const float* vertices, uint64_t n_ve
 		mat->metallicTexture = make_texture(sc->tex[2], sc->tex_w[2], sc->tex_h[2], 2);
 		mat->roughnessTexture = make_texture(sc->tex[3], sc->tex_w[3], sc->tex_h[3], 3);
 		mat->aoTexture = make_texture(sc->tex[4], sc->tex_w[4], sc->tex_h[4], 4);
-		if (sc->shader_kind >= 1 && (!mat->diffuseTexture || !mat->bumpTexture)) return -2;
+		if ((sc->shader_kind == 1 || sc->shader_kind == 2) && (!mat->diffuseTexture || !mat->bumpTexture)) return -2;
+		if (sc->shader_kind == 3 && !mat->diffuseTexture) return -2;
 		if (sc->shader_kind == 2 && (!mat->metallicTexture || !mat->roughnessTexture || !mat->aoTexture)) return -2;
 		mesh.m_Materials["m0"] = std::move(mat);
 

@@ -25,6 +25,10 @@ def cases():
     out["subpixel_phong_256x192"] = S.Scene("subpixel_phong", 256, 192, v, f, S.SHADER_PHONG, textures=_tex())
     v, f = S.torus(40, 40)
     out["torus40_pbr_240x160"] = S.Scene("torus40_pbr", 240, 160, v, f, S.SHADER_PBR, model=S._f32(S.rotate_y(0.5)), textures=_tex(64))
+    # the discard branch (reference src/tiled_pipeline.cpp:571-577) through the harness's CutoutShader (oracle/ref_harness.cpp):
+    # five alpha-tested layers of small triangles; nine layers of frame-filling, side-clipped quads
+    out["cutout_5layers_320x240"] = S.cutout_layers()
+    out["cutout_9layers_clipped_200x150"] = S.cutout_layers(w=200, h=150, layers=9, grid=2, size=8.5, tex=32)
     return out
 
 
@@ -55,7 +59,8 @@ def clip_cases():
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CASE_NAMES = ["head_phong_200", "icosphere3_flat_160x120", "random_clip_flat_192x144", "random_clip_phong_192x144",
-              "random_clip_pbr_192x144", "huge_clip_pbr_101x77", "subpixel_phong_256x192", "torus40_pbr_240x160"]
+              "random_clip_pbr_192x144", "huge_clip_pbr_101x77", "subpixel_phong_256x192", "torus40_pbr_240x160", "cutout_5layers_320x240",
+              "cutout_9layers_clipped_200x150"]
 
 
 def save_case(name, sc, color, depth):

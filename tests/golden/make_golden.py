@@ -1,7 +1,8 @@
 """Regenerates tests/golden/*.npz by running the UNMODIFIED reference (oracle/_ref, built from /root/reference by
 oracle/Makefile) on the deterministic cases of cases.py. Run here (the reference tree is not on the GPU box):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py            # everything
+    python tests/golden/make_golden.py CASE ...   # only the named scene fixtures (existing files are left alone)
 """
 import os
 import sys
@@ -19,10 +20,16 @@ po.build(ref=True)
 assert po.ref_available(), "oracle/_ref/libaxr_ref.so is needed (requires /root/reference)"
 all_cases = C.cases()
 assert list(all_cases) == C.CASE_NAMES
+only = sys.argv[1:]
+assert all(n in all_cases for n in only), only
 for name, sc in all_cases.items():
+    if only and name not in only:
+        continue
     c, d, _ = po.ref_render(sc, threads=3)
     C.save_case(name, sc, c, d)
     print(name, int(np.isfinite(d).sum()), "px covered")
+if only:
+    sys.exit(0)
 # stage-level known answers
 tris = C.clip_cases()
 clip_out = [po.ref_clip_triangle(t) for t in tris]

@@ -449,3 +449,80 @@ def test_c_abi_error_codes_and_lifecycle(po):
             dev2.close()
     finally:
         dev.close()
+
+
+_CUTOUT_CASES = {
+    "small_tris": dict(),
+    "clipped_binned": dict(size=8.5, grid=3),
+    "huge_9_layers": dict(size=6.0, grid=1, layers=9),
+    "dense_640x480": dict(size=5.0, grid=40, tex=256, w=640, h=480),
+    "odd_size": dict(w=333, h=217, size=7.0, grid=5, layers=4),
+}
+
+
+@pytest.mark.parametrize("case", list(_CUTOUT_CASES))
+def test_discard_shader_depth_peeling(po, case):
+    """A shader whose fragment() discards (reference src/tiled_pipeline.cpp:571-577), run through the unmodified reference
+    pipeline by the harness's CutoutShader: the owner of a pixel is the nearest NON-discarded fragment. The CUDA path finds it
+    by depth peeling; coverage / depth must stay bit-identical, and more than one pass must have run."""
+    sc = S.cutout_layers(**_CUTOUT_CASES[case])
+    m, st = _check(po, sc, use_ref=True)
+    assert m["color_max_diff"] <= 1, m
+    assert 0 < m["covered"], m
+    assert st["kernel_launches"] > 6, st  # 1 fill + 5 kernels per pass
+
+
+def test_discard_shader_bilinear_and_random_clip(po):
+    """Discard with the bilinear sampler (vs the oracle) and on randomly clipped, interpenetrating triangles (deep peels)."""
+    sc = S.cutout_layers(size=5.0, sampler=1)
+    m, _ = _check(po, sc)
+    assert m["color_max_diff"] <= 1, m
+    v, f = S.random_triangles(400, 11)
+    sc = S.Scene("random_clip_cutout", 192, 144, v, f, S.SHADER_CUTOUT, textures=[S.cutout_texture(32, 4), None, None, None, None])
+    m, st = _check(po, sc, use_ref=True)
+    assert m["color_max_diff"] <= 1, m
+
+
+def test_discard_shader_composites_bands_and_host_framebuffer(po):
+    """Peeled draws composite onto earlier draws through the depth test, work on a band context and through drawMesh on a
+    host framebuffer (axr_draw_mesh_host: zero-copy stores, depth read from the uploaded copy)."""
+    from axiomr_b200 import api
+    a = S.config2(level=4, w=320, h=240)                 # opaque sphere first
+    b = S.cutout_layers(size=5.0, layers=4)              # then alpha-tested layers, some in front of it, some behind
+    c0, d0, _ = po.oracle_render(a)
+    c0, d0, _ = po.oracle_render(b, color=c0, depth=d0)
+    c1, d1, _ = api.render_scene(a)
+    c1, d1, st = api.render_scene(b, color=c1, depth=d1)
+    m = po.compare(c1, d1, c0, d0)
+    assert m["coverage_mismatch"] == 0 and m["depth_bit_mismatch"] == 0 and m["color_max_diff"] <= 1, m
+    # bands
+    cb_full, db_full, _ = api.render_scene(b)
+    c = np.zeros_like(cb_full)
+    d = np.full_like(db_full, np.inf)
+    for y0, y1 in ((0, 80), (80, 176), (176, 240)):
+        cb, db, _ = api.render_scene(b, band=(y0, y1))
+        c[y0:y1], d[y0:y1] = cb[y0:y1], db[y0:y1]
+    assert np.array_equal(c, cb_full) and np.array_equal(d.view(np.uint32), db_full.view(np.uint32))
+    # reference-shaped host call, drawn twice (idempotent), after an opaque mesh
+    fb = api.Framebuffer(b.width, b.height, True)
+    fb.clearColor(api.Color(0, 0, 0, 255))
+    fb.clearDepth()
+    cam = api.Camera()
+    cam.setViewport(0, 0, b.width, b.height)
+    cam.setViewProjectionMatrix(b.view_proj)
+    cam._pos = b.cam_pos
+    pipe = api.TiledPipeline(8, cam, fb)
+    pipe.setShader(api.FlatShader(tuple(a.light_dir)))
+    pipe.drawMesh(a.model, api.Mesh(a.vertices, a.indices, {"m0": api.Material("m0")}))
+    pipe.setShader(api.CutoutShader(tuple(b.light_dir)))
+    mesh = api.Mesh(b.vertices, b.indices, {"m0": api.Material("m0", api.Texture(b.textures[0]))})
+    pipe.drawMesh(b.model, mesh)
+    m = po.compare(fb.getColorData(), fb.getDepthData(), c0, d0)
+    assert m["coverage_mismatch"] == 0 and m["depth_bit_mismatch"] == 0 and m["color_max_diff"] <= 1, m
+    before = fb.getColorData().copy()
+    pipe.drawMesh(b.model, mesh)
+    assert np.array_equal(before, fb.getColorData())
+    # a cutout material without its diffuse texture is an error code
+    with pytest.raises(api.AxrError) as e:
+        pipe.drawMesh(b.model, api.Mesh(b.vertices, b.indices, {"m0": api.Material("m0")}))
+    assert e.value.code == -5
