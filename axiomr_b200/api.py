@@ -250,6 +250,12 @@ class Device:
         self._check(self.lib.axr_resolve(self.h, color.ctypes.data, depth.ctypes.data))
         return color, depth
 
+    def present(self, path: str) -> None:
+        """Read the colour plane back (depth is not needed for display) and write it as a PNG; see api.present."""
+        color = np.zeros((self.height, self.width, 4), dtype=np.uint8)
+        self._check(self.lib.axr_resolve(self.h, color.ctypes.data, None))
+        present(color, path)
+
     # --- hot path
     def draw_mesh(self, mesh: int, model):
         m = _mat(model)
@@ -337,6 +343,31 @@ class Device:
         return mesh
 
 
+# ------------------------------------------------------------------------------------------- present
+def present(color_bgra, path: str) -> None:
+    """Window::present for a headless run (reference src/window.cpp:70-84): the reference copies Framebuffer::getColorData()
+    into a bottom-up 32-bit DIB (biHeight > 0, src/windows_bitmap.cpp:19-23), i.e. row 0 of the framebuffer is the BOTTOM row
+    of the picture and the bytes are B,G,R,A. This writes the same picture as a PNG (top-down, R,G,B,A); zlib only."""
+    import struct
+    import zlib
+    a = np.asarray(color_bgra, dtype=np.uint8)
+    if a.ndim != 3 or a.shape[2] != 4:
+        raise ValueError("present: expected an HxWx4 BGRA8 array")
+    h, w = a.shape[:2]
+    rgba = a[::-1, :, [2, 1, 0, 3]]
+    raw = np.empty((h, 1 + w * 4), dtype=np.uint8)
+    raw[:, 0] = 0  # filter type None for every scanline
+    raw[:, 1:] = rgba.reshape(h, w * 4)
+
+    def chunk(tag: bytes, data: bytes) -> bytes:
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+    png = (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 0))
+           + chunk(b"IDAT", zlib.compress(raw.tobytes(), 6)) + chunk(b"IEND", b""))
+    with open(path, "wb") as f:
+        f.write(png)
+
+
 # ------------------------------------------------------------------------------------------- reference-shaped classes
 @dataclass
 class Color:
@@ -409,6 +440,10 @@ class Framebuffer:
 
     def isDepthBufferEnabled(self) -> bool:
         return self._use_depth
+
+    def present(self, path: str) -> None:
+        """Window::present(framebuffer) without a window: PNG of the colour plane (api.present)."""
+        present(self._color, path)
 
 
 class Camera:

@@ -157,3 +157,23 @@ def test_bench_reference_arm_line_and_no_cpu_fallback():
     if not torch.cuda.is_available():
         r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "tiny", "--steps", "1"], capture_output=True, text=True, timeout=300)
         assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_present_writes_bottom_up_bgra_as_png(tmp_path):
+    """Window::present semantics (reference src/window.cpp:70-84 + the bottom-up DIB of src/windows_bitmap.cpp:19-23): framebuffer
+    row 0 is the bottom row of the picture, bytes are B,G,R,A. Decoded independently with PIL."""
+    Image = pytest.importorskip("PIL.Image")
+    fb = api.Framebuffer(5, 3, True, pinned=False)
+    fb.clearColor(api.Color(10, 20, 30, 255))
+    c = fb.getColorData()
+    c[0, 0] = (1, 2, 3, 255)      # B,G,R,A at the bottom-left corner
+    c[2, 4] = (200, 100, 50, 128)  # top-right corner
+    path = str(tmp_path / "frame.png")
+    fb.present(path)
+    img = np.asarray(Image.open(path))
+    assert img.shape == (3, 5, 4)
+    assert tuple(img[2, 0]) == (3, 2, 1, 255)       # bottom-left, R,G,B,A
+    assert tuple(img[0, 4]) == (50, 100, 200, 128)  # top-right
+    assert tuple(img[1, 2]) == (10, 20, 30, 255)    # clear colour: packed (a<<24)|(r<<16)|(g<<8)|b
+    with pytest.raises(ValueError):
+        api.present(np.zeros((4, 4), dtype=np.uint8), path)
