@@ -49,3 +49,39 @@ def test_cuda_equals_oracle_on_random_pixel_space_triangles(po, tris):
     assert np.array_equal(np.isfinite(d0), np.isfinite(d1))
     assert np.array_equal(d0.view(np.uint32), d1.view(np.uint32))
     assert int(np.abs(c0.astype(np.int16) - c1.astype(np.int16)).max()) <= 1
+
+
+# ---- the discard branch (reference src/tiled_pipeline.cpp:571-577) with the harness's CutoutShader: overlapping triangles, ties
+#      in z, fragments discarded in front of kept ones and the other way round
+_CUT_TEX = None
+
+
+def _cutout(tris):
+    global _CUT_TEX
+    from axiomr_b200 import scenes as S
+    if _CUT_TEX is None:
+        _CUT_TEX = S.cutout_texture(16, 2)
+    return _ortho_scene("prop_cutout", np.asarray(tris, dtype=np.float64), W, H, S.SHADER_CUTOUT, textures=[_CUT_TEX, None, None, None, None])
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/tiled_pipeline.cpp"), reason="reference tree not present")
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@given(tris=_scene)
+def test_oracle_equals_reference_with_discarding_shader(po, tris):
+    sc = _cutout(tris)
+    c0, d0, _ = po.ref_render(sc, threads=2, chunk=5)
+    c1, d1, _ = po.oracle_render(sc, threads=1)
+    assert np.array_equal(d0.view(np.uint32), d1.view(np.uint32))
+    assert np.array_equal(c0, c1)
+
+
+@pytest.mark.gpu
+@settings(max_examples=30, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@given(tris=_scene)
+def test_cuda_equals_oracle_with_discarding_shader(po, tris):
+    from axiomr_b200 import api
+    sc = _cutout(tris)
+    c1, d1, _ = api.render_scene(sc)
+    c0, d0, _ = po.oracle_render(sc, threads=1)
+    assert np.array_equal(d0.view(np.uint32), d1.view(np.uint32))
+    assert int(np.abs(c0.astype(np.int16) - c1.astype(np.int16)).max()) <= 1

@@ -57,4 +57,12 @@ def torture_scenes():
     z = [[[4, 4, 0.0], [60, 4, 0.0], [60, 44, 0.0]], [[4, 4, -0.0], [60, 44, -0.0], [4, 44, -0.0]],
          [[10, 10, -0.0], [50, 10, -0.0], [30, 40, -0.0]]]
     out.append(_ortho_scene("signed_zero_depth", z, 64, 48))
+    # 7. discarding shader (harness CutoutShader): exact duplicates (equal keys up to the ordinal: each copy is peeled in turn), ties
+    #    in z between a discarded and a kept fragment in both orders, signed zeros, the perspective / clip cases of scene 5
+    cut = [S.cutout_texture(16, 2), None, None, None, None]
+    out.append(_ortho_scene("cutout_duplicates_then_nearer", [t, t, t, t2, t], 64, 48, shader=S.SHADER_CUTOUT, textures=cut))
+    shifted = [[[a + 2.0, b, c] for a, b, c in tri] for tri in q]  # same z, texture window moved by two pixels
+    out.append(_ortho_scene("cutout_equal_z_ties", q + shifted + q, 64, 48, shader=S.SHADER_CUTOUT, textures=cut))
+    out.append(_ortho_scene("cutout_signed_zero_depth", z + z, 64, 48, shader=S.SHADER_CUTOUT, textures=cut))
+    out.append(S.Scene("cutout_w_zero_near_far", 96, 64, v, f, S.SHADER_CUTOUT, textures=cut))
     return out
