@@ -114,6 +114,16 @@ struct axr_ctx {
 	const float* depth_read_override = nullptr;        // set for the duration of one axr_draw_mesh_host
 	int read_depth = 1;
 
+	// axr_draw_mesh_host: the host depth goes up in row chunks on its own stream and the tile kernel is launched once per chunk,
+	// so that the upload of chunk b+1 (PCIe host -> device) runs beside the tile kernel of chunk b, whose zero-copy stores use the
+	// other PCIe direction
+	static constexpr int MAX_HOST_CHUNKS = 4;
+	cudaStream_t up_stream = nullptr;
+	cudaEvent_t up_done[MAX_HOST_CHUNKS] = {};
+	cudaEvent_t depth_free = nullptr;  // main stream: the previous user of the device depth copy is done
+	int host_chunks = 0;               // > 0 only while axr_draw_mesh_host issues its draw
+	int chunk_ty[MAX_HOST_CHUNKS + 1] = {};  // GPU tile rows [chunk_ty[b], chunk_ty[b+1]) of chunk b
+
 	// depth peeling (draws with a shader that may discard): per-pixel floor keys + the "another pass" flag; allocated on first use
 	unsigned long long* peel_floor = nullptr;
 	unsigned* peel_again = nullptr;
@@ -231,11 +241,21 @@ cudaEvent_t prof_mark(axr_ctx* ctx, cudaStream_t s) {
 	return e;
 }
 
+// One launch over all tile rows of the band, or (axr_draw_mesh_host) one launch per uploaded row chunk, each behind its upload.
 template <typename Shader>
-void launch_tile(axr_ctx* ctx, const MeshView& mv, const Uniforms& u, const TileIn& in) {
-	dim3 grid(ctx->fp.ntx, ctx->fp.ty_hi - ctx->fp.ty_lo);
-	if (u.sampler) k_tile_shade<Shader, 1><<<grid, TILE_THREADS, 0, ctx->stream>>>(mv, u, ctx->fp, in);
-	else k_tile_shade<Shader, 0><<<grid, TILE_THREADS, 0, ctx->stream>>>(mv, u, ctx->fp, in);
+int launch_tile(axr_ctx* ctx, const MeshView& mv, const Uniforms& u, const TileIn& in) {
+	const int chunks = ctx->host_chunks > 0 ? ctx->host_chunks : 1;
+	for (int b = 0; b < chunks; ++b) {
+		FrameParams fp = ctx->fp;
+		if (ctx->host_chunks > 0) {
+			fp.ty_lo = ctx->chunk_ty[b]; fp.ty_hi = ctx->chunk_ty[b + 1];
+			cudaStreamWaitEvent(ctx->stream, ctx->up_done[b], 0);
+		}
+		dim3 grid(fp.ntx, fp.ty_hi - fp.ty_lo);
+		if (u.sampler) k_tile_shade<Shader, 1><<<grid, TILE_THREADS, 0, ctx->stream>>>(mv, u, fp, in);
+		else k_tile_shade<Shader, 0><<<grid, TILE_THREADS, 0, ctx->stream>>>(mv, u, fp, in);
+	}
+	return chunks;
 }
 
 // One pass of the five kernels. peel: the pass belongs to a depth-peeled draw (draw_peeled below) — the raster sites reject
@@ -323,16 +343,16 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 	in.items = sl.items; in.records = sl.records; in.n_records = sl.n_records; in.status = sl.d_status; in.sv = m.sv[si];
 	in.color = ctx->out_color; in.depth = ctx->out_depth; in.read_depth = ctx->read_depth;
 	in.depth_read = ctx->depth_read_override ? ctx->depth_read_override : ctx->out_depth;
+	in.row_major = ctx->host_chunks > 0 ? 1 : 0;
 	in.floor = peel ? ctx->peel_floor : nullptr;
 	in.again = peel ? ctx->peel_again : nullptr;
 	switch (ctx->shader_kind) {
-	case AXR_SHADER_FLAT: launch_tile<FlatShader>(ctx, mv, u, in); break;
-	case AXR_SHADER_PHONG: launch_tile<PhongShader>(ctx, mv, u, in); break;
-	case AXR_SHADER_PBR: launch_tile<PBRShader>(ctx, mv, u, in); break;
-	case AXR_SHADER_CUTOUT: launch_tile<CutoutShader>(ctx, mv, u, in); break;
+	case AXR_SHADER_FLAT: launches += launch_tile<FlatShader>(ctx, mv, u, in); break;
+	case AXR_SHADER_PHONG: launches += launch_tile<PhongShader>(ctx, mv, u, in); break;
+	case AXR_SHADER_PBR: launches += launch_tile<PBRShader>(ctx, mv, u, in); break;
+	case AXR_SHADER_CUTOUT: launches += launch_tile<CutoutShader>(ctx, mv, u, in); break;
 	default: return fail(ctx, AXR_ERR_UNSUPPORTED, "unknown shader kind %d", ctx->shader_kind);
 	}
-	++launches;
 	prof_mark(ctx, ctx->stream);
 	CU(cudaEventRecord(sl.shade_done, ctx->stream));
 	sl.used = true;
@@ -466,6 +486,9 @@ int axr_create(const axr_config* cfg, axr_ctx** out) {
 		(void)lo;
 		CUC(cudaStreamCreateWithPriority(&c->geom_stream, cudaStreamNonBlocking, hi));
 	}
+	CUC(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+	for (auto& e : c->up_done) CUC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	CUC(cudaEventCreateWithFlags(&c->depth_free, cudaEventDisableTiming));
 	for (int si = 0; si < 2; ++si) {
 		axr_ctx::DrawSlot& sl = c->slot[si];
 		CUC(cudaMalloc(&sl.vis, npx * 8));
@@ -513,6 +536,9 @@ void axr_destroy(axr_ctx* ctx) {
 		if (sl.shade_done) cudaEventDestroy(sl.shade_done);
 	}
 	if (ctx->geom_stream) cudaStreamDestroy(ctx->geom_stream);
+	if (ctx->up_stream) { cudaStreamSynchronize(ctx->up_stream); cudaStreamDestroy(ctx->up_stream); }
+	for (cudaEvent_t e : ctx->up_done) if (e) cudaEventDestroy(e);
+	if (ctx->depth_free) cudaEventDestroy(ctx->depth_free);
 	for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
 	for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
 	if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -798,12 +824,32 @@ int axr_draw_mesh_host(axr_ctx* ctx, axr_mesh mh, const float model[16], uint8_t
 		if (!rc) rc = axr_resolve(ctx, bgra, depth);
 		return rc;
 	}
-	// host depth -> device copy for the merge test; the geometry stages do not wait for it when overlap is on
-	CU(cudaMemcpyAsync(ctx->depth + first, depth + first, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+	// host depth -> device copy for the merge test, in chunks of whole GPU tile rows on the upload stream; the geometry stages do
+	// not wait for it, and the tile kernel of chunk b only waits for chunk b (launch_tile)
+	(void)first; (void)n;
+	const int ty_lo = ctx->fp.ty_lo, ty_hi = ctx->fp.ty_hi;
+	int chunks = ctx->shader_kind == AXR_SHADER_CUTOUT ? 1 : (ty_hi - ty_lo) / 16;  // >= 16 tile rows (512 px) per chunk (C3 e2e: 1.22 / 1.04 / 1.06 / 1.09 ms with 1 / 2 / 4 / 8 chunks); peeled draws re-read the copy
+	if (chunks > axr_ctx::MAX_HOST_CHUNKS) chunks = axr_ctx::MAX_HOST_CHUNKS;
+	if (chunks < 1) chunks = 1;
+	CU(cudaEventRecord(ctx->depth_free, ctx->stream));
+	CU(cudaStreamWaitEvent(ctx->up_stream, ctx->depth_free, 0));
+	for (int b = 0; b <= chunks; ++b) ctx->chunk_ty[b] = ty_lo + (int)((long long)(ty_hi - ty_lo) * b / chunks);
+	for (int b = 0; b < chunks; ++b) {
+		int r0 = ctx->chunk_ty[b] * GT, r1 = ctx->chunk_ty[b + 1] * GT;
+		if (r0 < ctx->fp.y_lo) r0 = ctx->fp.y_lo;
+		if (r1 > ctx->fp.y_hi) r1 = ctx->fp.y_hi;
+		if (r1 > r0) {
+			const size_t off = (size_t)r0 * ctx->fp.W, cnt = (size_t)(r1 - r0) * ctx->fp.W;
+			CU(cudaMemcpyAsync(ctx->depth + off, depth + off, cnt * 4, cudaMemcpyHostToDevice, ctx->up_stream));
+		}
+		CU(cudaEventRecord(ctx->up_done[b], ctx->up_stream));
+	}
 	unsigned* save_c = ctx->out_color; float* save_d = ctx->out_depth;
 	ctx->out_color = (unsigned*)dc; ctx->out_depth = (float*)dd; ctx->depth_read_override = ctx->depth;
+	ctx->host_chunks = chunks;
 	rc = draw(ctx, mh, model);
 	if (!rc) rc = check_pending(ctx);  // a bin overflow re-issues the draw while the host pointers are still installed
+	ctx->host_chunks = 0;
 	ctx->out_color = save_c; ctx->out_depth = save_d; ctx->depth_read_override = nullptr;
 	if (rc) return rc;
 	return sync_all(ctx);  // complete on return: the kernel's stores have landed in the host arrays

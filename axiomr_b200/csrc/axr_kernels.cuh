@@ -446,6 +446,7 @@ struct TileIn {
 	int read_depth;                 // 0: the caller guarantees depth == +inf everywhere (freshly cleared single-draw target)
 	unsigned long long* floor;      // depth peeling only (Shader::DISCARDS): per-pixel key of the last discarded winner
 	unsigned* again;                // depth peeling only: set when some winner was discarded in this pass
+	int row_major;                  // 1: a warp shades one 32 x 1 pixel row (128 B contiguous stores: output in host memory over PCIe)
 };
 
 __device__ __forceinline__ unsigned pack_bgra(v4 c) {
@@ -645,7 +646,7 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 		// a warp = one compact 8x4 pixel block (neighbouring pixels share triangle vertices); the stores still fill whole 32 B
 		// sectors (8 px x 4 B per row). Measured equal to 32x1 rows on C3.
 		const int blk = i * (TILE_THREADS / 32) + (tid >> 5);
-		const int p = ((blk >> 2) * 4 + ((tid & 31) >> 3)) * GT + (blk & 3) * 8 + (tid & 7);
+		const int p = in.row_major ? blk * GT + (tid & 31) : ((blk >> 2) * 4 + ((tid & 31) >> 3)) * GT + (blk & 3) * 8 + (tid & 7);
 		const unsigned long long k = s_keys[p];
 		if (k == KEY_EMPTY) continue;
 		const unsigned ord = (unsigned)(k & 0xFFFFFFFFull);

@@ -462,7 +462,8 @@ def main():
                            "h2d_bytes_per_step": int(pipe.last_h2d_bytes), "d2h_bytes_per_step": int(covered) * 8,
                            "call": "TiledPipeline.drawMesh(model, mesh) on a pinned host Framebuffer (axr_draw_mesh_host): H2D of the host "
                                    "depth (4 B/px, the kernel never reads colour), draw, the pixels that pass the depth test stored by the tile "
-                                   "kernel straight into the host arrays (zero-copy, 8 B per updated pixel), complete on return; host-side "
+                                   "kernel straight into the host arrays (zero-copy, 8 B per updated pixel, 128 B row stores; upload and tile kernel "
+                                   "pipelined in up to 4 row chunks), complete on return; host-side "
                                    "clearColor/clearDepth before the call are the caller's and untimed, as in the CPU arm; mesh/textures cached "
                                    "on the device after the first call",
                            "mesh_upload_bytes_first_call": int(sc.vertices.nbytes + sc.indices.nbytes)}
