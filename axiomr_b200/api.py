@@ -90,6 +90,10 @@ def load_library():
         raise ImportError(f"{LIB_PATH} is missing: run `python -m axiomr_b200.build` (nvcc, sm_100a). "
                           "There is no CPU fallback for the raster path.")
     lib = C.CDLL(LIB_PATH)
+    if hasattr(lib, "axr_simt_interpreter_marker") and os.environ.get("AXR_SIMT_TESTS_ONLY") != "1":
+        # tests/simt builds the kernels for a CPU-side SIMT interpreter (kernel unit tests without a GPU); it is not a device
+        raise ImportError(f"{LIB_PATH} is the test-only SIMT interpreter build, not the CUDA library. "
+                          "There is no CPU fallback for the raster path.")
     vp = C.c_void_p
     lib.axr_create.argtypes = [C.POINTER(_Config), C.POINTER(vp)]
     lib.axr_destroy.argtypes = [vp]

@@ -1,0 +1,59 @@
+"""CPU-side execution of the CUDA sources (kernels + C ABI layer) under the SIMT interpreter in tests/simt.
+
+The interpreter compiles the *unmodified* files of axiomr_b200/csrc with g++ (threads of a CTA are fibers; __syncthreads and the
+warp collectives are rendezvous points; device allocations carry canaries) and this test then runs the GPU parity tests against
+that build in a subprocess: same scenes, same checks, same oracle. It pins kernel logic — indexing, bins, warp-level code,
+depth peeling, the C ABI's error paths — on every CPU run, and lets a kernel change be checked for bit-exactness before GPU time
+is spent on it. It says nothing about speed and it is not a product path: axiomr_b200.api refuses to load this build unless
+AXR_SIMT_TESTS_ONLY=1 (set here only), and nothing outside tests/ refers to it.
+
+AXR_SIMT_FULL=1 also runs the slow cases (bin overflow + regrow, overlapped draws, the dense depth-peeling scenes): ~6 min.
+"""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SKIP_ALWAYS = ["full_config", "full_c3", "multi_gpu", "cpp_dropin"]  # full-size BASELINE configs, NCCL, nvcc-built adapter
+SKIP_FAST = ["bin_overflow", "overlapped", "dense_640x480", "huge_9_layers", "composites_bands_and_host"]
+
+
+def _run(extra_env=None, k_extra=()):
+    sys.path.insert(0, os.path.join(ROOT, "tests", "simt"))
+    try:
+        import build as simt_build
+    finally:
+        sys.path.pop(0)
+    lib = simt_build.build()
+    skip = SKIP_ALWAYS + ([] if os.environ.get("AXR_SIMT_FULL") == "1" else SKIP_FAST) + list(k_extra)
+    env = dict(os.environ, AXR_B200_LIB=lib, AXR_SIMT_TESTS_ONLY="1", **(extra_env or {}))
+    cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_property.py", "-m", "gpu", "-q", "-x",
+           "-p", "no:cacheprovider", "-n", "4", "-k", " and ".join("not " + s for s in skip)]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=3000)
+    tail = (r.stdout + r.stderr)[-6000:]
+    assert r.returncode == 0, tail
+    m = re.search(r"(\d+) passed", r.stdout)
+    assert m and int(m.group(1)) >= 30, tail
+    assert "failed" not in r.stdout and "error" not in r.stdout.lower().replace("error_codes", ""), tail
+
+
+def test_cuda_sources_under_simt_interpreter_pass_the_gpu_parity_tests():
+    _run()
+
+
+def test_product_loader_refuses_the_interpreter_build():
+    sys.path.insert(0, os.path.join(ROOT, "tests", "simt"))
+    try:
+        import build as simt_build
+    finally:
+        sys.path.pop(0)
+    lib = simt_build.build()
+    env = {k: v for k, v in os.environ.items() if k != "AXR_SIMT_TESTS_ONLY"}
+    env["AXR_B200_LIB"] = lib
+    code = "from axiomr_b200 import api\ntry:\n    api.load_library()\nexcept ImportError as e:\n    print('REFUSED', e)\n"
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
+    assert "REFUSED" in r.stdout and "no CPU fallback" in r.stdout, r.stdout + r.stderr
