@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "axr_api.cu")
 OUT = os.path.join(HERE, "libaxr_b200.so")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("axr_api.cu", "axr_kernels.cuh", "axr_raster.cuh", "axr_shaders.cuh", "axr_math.cuh")]
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("axr_api.cu", "axr_kernels.cuh", "axr_raster.cuh", "axr_shaders.cuh", "axr_math.cuh", "axr_tangents.cuh")]
 DEPS.append(os.path.join(HERE, "..", "include", "axr_b200.h"))
 
 NVCC_FLAGS = [

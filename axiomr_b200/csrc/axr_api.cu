@@ -715,6 +715,7 @@ int axr_set_material(axr_ctx* ctx, axr_mesh mh, uint32_t group, axr_tex diffuse,
 		mat.tex[i] = TexRef{t.data, t.w, t.h};
 	}
 	mat.specular_exponent = specular_exponent;
+	CU(cudaSetDevice(ctx->device));
 	int rc = check_pending(ctx);
 	if (rc) return rc;
 	m.materials[group] = mat;
@@ -866,6 +867,7 @@ int axr_sync(axr_ctx* ctx) {
 
 int axr_get_stats(axr_ctx* ctx, axr_stats* out) {
 	if (!ctx || !out) return AXR_ERR_INVALID;
+	CU(cudaSetDevice(ctx->device));
 	int rc = check_pending(ctx);
 	if (rc) return rc;
 	*out = ctx->stats;
@@ -962,6 +964,7 @@ int axr_framebuffer_device(axr_ctx* ctx, void** bgra_dev, void** depth_dev) {
 
 int axr_set_output(axr_ctx* ctx, void* bgra_dev, void* depth_dev) {
 	if (!ctx) return AXR_ERR_INVALID;
+	CU(cudaSetDevice(ctx->device));
 	int rc = check_pending(ctx);
 	if (rc) return rc;
 	if ((bgra_dev == nullptr) != (depth_dev == nullptr)) return fail(ctx, AXR_ERR_INVALID, "axr_set_output: pass both pointers or neither");
@@ -983,6 +986,7 @@ int axr_set_overlap(axr_ctx* ctx, int enabled) {
 
 int axr_set_depth_read(axr_ctx* ctx, int enabled) {
 	if (!ctx) return AXR_ERR_INVALID;
+	CU(cudaSetDevice(ctx->device));
 	int rc = check_pending(ctx);
 	if (rc) return rc;
 	ctx->read_depth = enabled ? 1 : 0;

@@ -56,6 +56,32 @@ struct Cta {
 };
 
 Cta g_cta;
+// AXR_SIMT_ORDER = fwd (default) | rev | shuffle:<seed> — the order in which the scheduler visits the threads of a CTA and the
+// CTAs of a grid. Every order is a legal execution of the same launch, so results that differ between orders mean the kernels
+// depend on a schedule (a race, or an order assumption the hardware does not guarantee).
+int g_order = -1;  // 0 fwd, 1 rev, 2 shuffle
+unsigned long long g_seed = 1;
+std::vector<unsigned> g_thread_order, g_cta_order;
+
+void read_order() {
+	if (g_order >= 0) return;
+	const char* e = getenv("AXR_SIMT_ORDER");
+	g_order = 0;
+	if (e && !strcmp(e, "rev")) g_order = 1;
+	else if (e && !strncmp(e, "shuffle", 7)) { g_order = 2; if (e[7] == ':') g_seed = strtoull(e + 8, nullptr, 10) * 2654435761ull + 1; }
+}
+void make_order(std::vector<unsigned>& v, size_t n, unsigned long long salt) {
+	v.resize(n);
+	for (size_t i = 0; i < n; ++i) v[i] = (unsigned)(g_order == 1 ? n - 1 - i : i);
+	if (g_order == 2) {
+		unsigned long long x = g_seed ^ (salt * 0x9E3779B97F4A7C15ull);
+		for (size_t i = n; i > 1; --i) {  // Fisher-Yates with xorshift64*
+			x ^= x >> 12; x ^= x << 25; x ^= x >> 27;
+			const size_t j = (size_t)((x * 2685821657736338717ull) >> 11) % i;
+			std::swap(v[i - 1], v[j]);
+		}
+	}
+}
 char* g_stacks = nullptr;
 void* g_sched_sp = nullptr;
 const std::function<void()>* g_body = nullptr;
@@ -122,10 +148,12 @@ void run_cta(unsigned nthreads) {
 		f.sp = top - 8;
 	}
 	unsigned remaining = nthreads;
+	if (g_thread_order.size() != nthreads || g_order == 2)
+		make_order(g_thread_order, nthreads, ((unsigned long long)blockIdx.z << 40) ^ ((unsigned long long)blockIdx.y << 20) ^ blockIdx.x);
 	while (remaining) {
 		const unsigned long long before = g_progress;
-		for (unsigned i = 0; i < nthreads; ++i) {
-			Fiber& f = c.fibers[i];
+		for (unsigned k = 0; k < nthreads; ++k) {
+			Fiber& f = c.fibers[g_thread_order[k]];
 			if (f.done) continue;
 			g_cur = &f;
 			simt_switch(&g_sched_sp, f.sp);
@@ -187,12 +215,15 @@ void run_grid(dim3 grid, dim3 block, const std::function<void()>& body, const ch
 		if (g_stacks == MAP_FAILED) { perror("simt: mmap"); abort(); }
 	}
 	g_body = &body;
-	for (unsigned z = 0; z < grid.z; ++z)
-		for (unsigned y = 0; y < grid.y; ++y)
-			for (unsigned x = 0; x < grid.x; ++x) {
-				blockIdx = {x, y, z};
-				run_cta((unsigned)nthreads);
-			}
+	read_order();
+	const size_t nctas = (size_t)grid.x * grid.y * grid.z;
+	if (g_cta_order.size() != nctas || g_order == 2) make_order(g_cta_order, nctas, nctas);
+	g_thread_order.clear();
+	for (size_t k = 0; k < nctas; ++k) {
+		const size_t id = g_cta_order[k];
+		blockIdx = {(unsigned)(id % grid.x), (unsigned)(id / grid.x % grid.y), (unsigned)(id / ((size_t)grid.x * grid.y))};
+		run_cta((unsigned)nthreads);
+	}
 	g_body = nullptr;
 	check_canaries("after a kernel");
 }

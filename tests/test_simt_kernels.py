@@ -22,7 +22,7 @@ SKIP_ALWAYS = ["full_config", "full_c3", "multi_gpu", "cpp_dropin"]  # full-size
 SKIP_FAST = ["bin_overflow", "overlapped", "dense_640x480", "huge_9_layers", "composites_bands_and_host"]
 
 
-def _run(extra_env=None, k_extra=()):
+def _run(extra_env=None, k_extra=(), only=None, min_passed=30):
     sys.path.insert(0, os.path.join(ROOT, "tests", "simt"))
     try:
         import build as simt_build
@@ -32,17 +32,25 @@ def _run(extra_env=None, k_extra=()):
     skip = SKIP_ALWAYS + ([] if os.environ.get("AXR_SIMT_FULL") == "1" else SKIP_FAST) + list(k_extra)
     env = dict(os.environ, AXR_B200_LIB=lib, AXR_SIMT_TESTS_ONLY="1", **(extra_env or {}))
     cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_property.py", "-m", "gpu", "-q", "-x",
-           "-p", "no:cacheprovider", "-n", "4", "-k", " and ".join("not " + s for s in skip)]
+           "-p", "no:cacheprovider", "-n", "4", "-k", " and ".join("not " + s for s in skip) + (f" and ({only})" if only else "")]
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=3000)
     tail = (r.stdout + r.stderr)[-6000:]
     assert r.returncode == 0, tail
     m = re.search(r"(\d+) passed", r.stdout)
-    assert m and int(m.group(1)) >= 30, tail
+    assert m and int(m.group(1)) >= min_passed, tail
     assert "failed" not in r.stdout and "error" not in r.stdout.lower().replace("error_codes", ""), tail
 
 
 def test_cuda_sources_under_simt_interpreter_pass_the_gpu_parity_tests():
     _run()
+
+
+@pytest.mark.parametrize("order", ["rev", "shuffle:3"])
+def test_results_do_not_depend_on_the_thread_or_cta_schedule(order):
+    """The same launches with the CTAs and the threads of each CTA visited in reverse / shuffled order: bins filled by unordered
+    atomics, the 64-bit visibility keys and the depth-peeling floor must give bit-identical frames under any legal schedule."""
+    _run({"AXR_SIMT_ORDER": order}, only="random_clipped or golden or clipped_binned or bands_equal or composite_two or torture "
+         "or multi_material or small_tris or random_pixel_space", min_passed=15)
 
 
 def test_product_loader_refuses_the_interpreter_build():
