@@ -65,3 +65,28 @@ def test_product_loader_refuses_the_interpreter_build():
     code = "from axiomr_b200 import api\ntry:\n    api.load_library()\nexcept ImportError as e:\n    print('REFUSED', e)\n"
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
     assert "REFUSED" in r.stdout and "no CPU fallback" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("shader", [0, 1, 2])
+def test_cpp_dropin_adapter_vs_reference_in_one_process_on_the_interpreter(tmp_path, shader):
+    """oracle/_ref/dropin_demo = the UNMODIFIED reference's AR::TiledPipeline and the C++ adapter AR::B200TiledPipeline
+    (axiomr_b200/host -> C ABI) in one process, scene loaded by the reference's own OBJ / MTL / texture loaders. The GPU suite runs
+    it against libaxr_b200.so; here the dynamic linker is pointed at the interpreter build instead (the demo links by soname)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "dropin_demo")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/dropin_demo not built (needs /root/reference at build time)")
+    sys.path.insert(0, os.path.join(ROOT, "tests", "simt"))
+    try:
+        import build as simt_build
+    finally:
+        sys.path.pop(0)
+    lib = simt_build.build()
+    os.symlink(lib, tmp_path / "libaxr_b200.so")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from objutil import write_obj_scene
+    from axiomr_b200 import scenes as S
+    v, f = S.head_like(24, 23)
+    obj = write_obj_scene(str(tmp_path), "head", v, f, S._pbr_textures(64))
+    r = subprocess.run([exe, obj, "400", "300", str(shader)], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, LD_LIBRARY_PATH=str(tmp_path)))
+    assert r.returncode == 0 and "PARITY OK" in r.stdout and "coverage_mismatch=0 depth_bit_mismatch=0" in r.stdout, (r.stdout, r.stderr)
