@@ -56,6 +56,8 @@ struct dim3 {
 };
 struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(4) uchar4 { unsigned char x, y, z, w; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 
 // ------------------------------------------------------------------------------------------------ interpreter core (simt.cpp)
@@ -107,6 +109,7 @@ static inline unsigned __float_as_uint(float f) { return simt::from_bits<unsigne
 static inline float __uint_as_float(unsigned u) { return simt::from_bits<float>(simt::to_bits(u)); }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 template <typename T>
 static inline T __ldg(const T* p) { return *p; }
 static inline void __threadfence() {}
@@ -167,6 +170,8 @@ static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
 // Fibers are cooperative (one OS thread), so a plain read-modify-write is atomic.
 template <typename T>
 static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
+template <typename T>
+static inline T atomicCAS(T* p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
 template <typename T>
 static inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
 
