@@ -37,19 +37,14 @@ constexpr int GT_PIX = GT * GT;
 // C1 0.111 -> 0.122 ms). Results are identical either way.
 constexpr int SMALL_DIM_LAT = 8, SMALL_AREA_LAT = 32, SMALL_DIM_TPUT = 12, SMALL_AREA_TPUT = 64;
 constexpr unsigned long long SMALL_TPUT_MIN_FACES = 500000ull;
+// 8 warps per CTA, 4 CTAs per SM (64 registers). 4 warps x 8 CTAs is the same occupancy in finer scheduling units and was measured:
+// C3 201 -> 198 us, but C1 58 -> 65 us and C2 20 -> 25 us (half as many warps walk a tile's bins / pixels); 4 x 9 or 4 x 10 spill
+// (C3: 219 / 231 us).
 #ifndef AXR_TILE_THREADS
 #define AXR_TILE_THREADS 256
 #endif
 constexpr int TILE_THREADS = AXR_TILE_THREADS;
 static_assert(TILE_THREADS % 32 == 0 && GT_PIX % TILE_THREADS == 0, "whole warps, whole pixel batches");
-// Experimental variant of the shading phase, off by default (build with -DAXR_TILE_VCACHE=1 -DAXR_TILE_THREADS=128
-// -DAXR_TILE_MINB=5; not yet timed on a B200): a warp-level post-transform vertex cache, see shade_batch_cached below.
-#ifndef AXR_TILE_VCACHE
-#define AXR_TILE_VCACHE 0
-#endif
-#ifndef AXR_SETUP_FLAT
-#define AXR_SETUP_FLAT 0
-#endif
 
 // 40-byte setup record of a triangle that goes through the tile bins
 struct __align__(8) TriRecord {
@@ -153,7 +148,10 @@ __global__ void __launch_bounds__(256) k_vertex_xform(const float4* __restrict__
 	v4 c = mul(mvp, V4(p.x, p.y, p.z, 1.0f));
 	float sx, sy, z;
 	to_screen(c, fW, fH, sx, sy, z);
-	sv[i] = make_float4(sx, sy, z, __uint_as_float(clip_code(c) | (clip_code_safe_out(c) << 8)));
+	// a "safely outside" bit implies the exact bit of the same plane, so the margins are only evaluated for the few vertices
+	// that are outside some plane at all
+	const unsigned code = clip_code(c);
+	sv[i] = make_float4(sx, sy, z, __uint_as_float(code ? (code | (clip_code_safe_out(c) << 8)) : 0u));
 }
 
 // ------------------------------------------------------------------------------------------------ setup + small raster
@@ -179,15 +177,15 @@ __device__ __forceinline__ void touch_tile(const FrameParams& fp, const SetupOut
 	if (*tf == 0u) *tf = 1u;
 }
 
-// touched: when non-null the caller flags the tiles later (warp-aggregated); it receives the tile rect of the pixel box
-// packed as tx0 | ty0<<8 | tx1<<16 | ty1<<24 in units of GPU tiles (frames up to 8192 px), or stays 0xFFFFFFFF.
-template <bool PEEL>
-__device__ __forceinline__ void emit_triangle(const FrameParams& fp, const SetupOut& o, float x0, float y0, float x1, float y1,
-                                              float x2, float y2, float z0, float z1, float z2, unsigned ordinal, EmitCounters& cnt,
-                                              unsigned* touched) {
+// DEFER_TOUCH: the caller flags the tiles later (warp-aggregated); the return value is the tile rect of the pixel box packed as
+// tx0 | ty0<<8 | tx1<<16 | ty1<<24 in units of GPU tiles (frames up to 8192 px), or NO_TOUCH when there is nothing to flag.
+constexpr unsigned NO_TOUCH = 0xFFFFFFFFu;
+template <bool PEEL, bool DEFER_TOUCH>
+__device__ __forceinline__ unsigned emit_triangle(const FrameParams& fp, const SetupOut& o, float x0, float y0, float x1, float y1,
+                                                  float x2, float y2, float z0, float z1, float z2, unsigned ordinal, EmitCounters& cnt) {
 	cnt.tris++;
 	Setup s;
-	if (!setup_triangle(x0, y0, x1, y1, x2, y2, z0, z1, z2, fp.W, fp.y_lo, fp.y_hi, s)) return;
+	if (!setup_triangle(x0, y0, x1, y1, x2, y2, z0, z1, z2, fp.W, fp.y_lo, fp.y_hi, s)) return NO_TOUCH;
 	const int bw = s.X1 - s.X0, bh = s.Y1 - s.Y0;
 	if (bw <= o.small_dim && bh <= o.small_dim && bw * bh <= o.small_area) {
 		cnt.small++;
@@ -203,10 +201,9 @@ __device__ __forceinline__ void emit_triangle(const FrameParams& fp, const Setup
 			atomicMin(o.vis + (size_t)py * fp.W + px, key);  // result unused -> RED.MIN.64, fire and forget
 			any = true;
 		};
-#if AXR_SETUP_FLAT
-		// Variant (off by default, not yet timed on a B200): one counter over the whole pixel box instead of rows x 16-px segments x
-		// pixels. The lanes of a warp then run max(box) iterations instead of the union of their differently shaped nested loops
-		// (equal on regular grids such as C3, smaller on irregular meshes), at the price of the un-hoisted closed form per pixel.
+		// One counter over the whole pixel box (<= 64 px) with the closed-form coverage() per pixel, instead of rows x 16-px
+		// segments x pixels with hoisted row terms: the hoisted form keeps ~8 more values live, which at this kernel's register
+		// budget meant spills inside the loop (68 B), and its nested trip counts diverge between lanes. C3: 198 -> 175 us.
 		{
 			int px = s.X0, py = s.Y0;
 			for (int i = bw * bh; i > 0; --i) {
@@ -215,19 +212,14 @@ __device__ __forceinline__ void emit_triangle(const FrameParams& fp, const Setup
 				if (++px == s.X1) { px = s.X0; ++py; }
 			}
 		}
-#else
-		for_each_covered(s, s.X0, s.X1, s.Y0, s.Y1, hit);
-#endif
 		if (any) {
 			const int tx0 = s.X0 / GT, ty0 = s.Y0 / GT, tx1 = (s.X1 - 1) / GT, ty1 = (s.Y1 - 1) / GT;  // box <= 12x12 px: at most 2x2 tiles
-			if (touched && fp.ntx <= 256 && fp.nty <= 256) {
-				*touched = (unsigned)tx0 | ((unsigned)ty0 << 8) | ((unsigned)tx1 << 16) | ((unsigned)ty1 << 24);
-			} else {
-				for (int ty = ty0; ty <= ty1; ++ty)
-					for (int tx = tx0; tx <= tx1; ++tx) touch_tile(fp, o, tx, ty);
-			}
+			if (DEFER_TOUCH && fp.ntx <= 256 && fp.nty <= 256)
+				return (unsigned)tx0 | ((unsigned)ty0 << 8) | ((unsigned)tx1 << 16) | ((unsigned)ty1 << 24);
+			for (int ty = ty0; ty <= ty1; ++ty)
+				for (int tx = tx0; tx <= tx1; ++tx) touch_tile(fp, o, tx, ty);
 		}
-		return;
+		return NO_TOUCH;
 	}
 	cnt.binned++;
 	// warp-aggregated append of the setup record
@@ -243,12 +235,16 @@ __device__ __forceinline__ void emit_triangle(const FrameParams& fp, const Setup
 	int tx0 = s.X0 / GT, tx1 = (s.X1 - 1) / GT, ty0 = s.Y0 / GT, ty1 = (s.Y1 - 1) / GT;
 	for (int ty = ty0; ty <= ty1; ++ty)
 		for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(o.tile_count + ty * fp.ntx + tx, 1u);
+	return NO_TOUCH;
 }
 
-// Clip slow path of one face for the visibility pass (positions only): reference src/tiled_pipeline.cpp:210-234
+// Clip slow path of one face for the visibility pass (positions only): reference src/tiled_pipeline.cpp:210-234.
+// Returns its counters packed as tris | small << 8 | binned << 16 (at most 8 sub-triangles per face): handing the caller's
+// counters to this out-of-line function by reference would pin them in local memory on the hot path as well.
 template <bool PEEL>
-__device__ __noinline__ void setup_clipped_face(const FrameParams& fp, const SetupOut& o, const m4& mvp, float4 p0, float4 p1,
-                                                float4 p2, unsigned face, EmitCounters& cnt) {
+__device__ __noinline__ unsigned setup_clipped_face(const FrameParams& fp, const SetupOut& o, const m4& mvp, float4 p0, float4 p1,
+                                                    float4 p2, unsigned face) {
+	EmitCounters cnt = {0, 0, 0};
 	ClipPos a[MAX_CLIPPED_VERTS], b[MAX_CLIPPED_VERTS];
 	a[0].clip = mul(mvp, V4(p0.x, p0.y, p0.z, 1.0f));
 	a[1].clip = mul(mvp, V4(p1.x, p1.y, p1.z, 1.0f));
@@ -262,8 +258,9 @@ __device__ __noinline__ void setup_clipped_face(const FrameParams& fp, const Set
 		to_screen(out[j + 1].clip, fW, fH, x1, y1, z1);
 		to_screen(out[j + 2].clip, fW, fH, x2, y2, z2);
 		if (is_backface(x0, y0, x1, y1, x2, y2)) continue;
-		emit_triangle<PEEL>(fp, o, x0, y0, x1, y1, x2, y2, z0, z1, z2, face * 8u + (unsigned)(j / 3), cnt, nullptr);
+		emit_triangle<PEEL, false>(fp, o, x0, y0, x1, y1, x2, y2, z0, z1, z2, face * 8u + (unsigned)(j / 3), cnt);
 	}
+	return cnt.tris | (cnt.small << 8) | (cnt.binned << 16);
 }
 
 #ifndef AXR_SETUP_THREADS
@@ -274,7 +271,7 @@ constexpr int SETUP_THREADS = AXR_SETUP_THREADS;
 #define AXR_SETUP_FPT 1
 #endif
 #ifndef AXR_SETUP_MINB
-#define AXR_SETUP_MINB 12
+#define AXR_SETUP_MINB 16  // 32 registers, 64 resident warps: the kernel is latency-bound (C3: 12 -> 175 us, 14 / 16 -> 169 us, 10 -> 186 us)
 #endif
 #ifndef AXR_TILE_MINB
 #define AXR_TILE_MINB 4
@@ -312,25 +309,26 @@ __global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(
 #pragma unroll
 		for (int j = 1; j < SETUP_FPT; ++j)
 			if (k == j) { s0 = s[j][0]; s1 = s[j][1]; s2 = s[j][2]; i0 = vi[j][0]; i1 = vi[j][1]; i2 = vi[j][2]; }
-		unsigned touched = 0xFFFFFFFFu;
+		unsigned touched = NO_TOUCH;
 		if (f < mesh.n_faces) {
 			const unsigned k0 = __float_as_uint(s0.w), k1 = __float_as_uint(s1.w), k2 = __float_as_uint(s2.w);
 			if (((k0 | k1 | k2) & 0x3fu) == 0) {
 				// every vertex inside every plane: clipTriangle returns the triangle unchanged (reference src/pipeline.cpp:322-325)
 				if (!is_backface(s0.x, s0.y, s1.x, s1.y, s2.x, s2.y))
-					emit_triangle<PEEL>(fp, o, s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, (unsigned)f * 8u, cnt, &touched);
+					touched = emit_triangle<PEEL, true>(fp, o, s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, (unsigned)f * 8u, cnt);
 			} else if ((k0 & k1 & k2) >> 8) {
 				// all three vertices safely outside one plane: clipTriangle returns nothing (see clip_code_safe_out)
 			} else {
 				clipped++;
-				setup_clipped_face<PEEL>(fp, o, mvp, __ldg(mesh.pos + i0), __ldg(mesh.pos + i1), __ldg(mesh.pos + i2), (unsigned)f, cnt);
+				const unsigned c = setup_clipped_face<PEEL>(fp, o, mvp, __ldg(mesh.pos + i0), __ldg(mesh.pos + i1), __ldg(mesh.pos + i2), (unsigned)f);
+				cnt.tris += c & 255u; cnt.small += (c >> 8) & 255u; cnt.binned += c >> 16;
 			}
 		}
 		// tile flags of the direct path, warp-aggregated: consecutive faces of a mesh land in the same one or two tiles, so one
 		// lane per distinct tile rect does the test-and-set (correct for any input; merely slower when faces are scattered)
 		__syncwarp();
 		const unsigned peers = __match_any_sync(0xffffffffu, touched);
-		if (touched != 0xFFFFFFFFu && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) {
+		if (touched != NO_TOUCH && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) {
 			const int tx0 = touched & 255, ty0 = (touched >> 8) & 255, tx1 = (touched >> 16) & 255, ty1 = touched >> 24;
 			for (int ty = ty0; ty <= ty1; ++ty)
 				for (int tx = tx0; tx <= tx1; ++tx) touch_tile(fp, o, tx, ty);
@@ -386,10 +384,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(unsigned* tile_coun
 	const unsigned nrec = *n_records;
 	if (nrec == 0) {  // k_tile_shade does not read bin_start in this case
 		__syncthreads();
-		if (tid == 0) {
-			status->bin_refs = 0; status->overflow = 0;
-			publish_status(status, host_status);
-		}
+		// six threads, one 8-byte word each (a single thread's volatile copies are six dependent L2 round trips);
+		// bin_refs, overflow and pad are still the zeros k_vertex_xform wrote
+		if (tid < 6) reinterpret_cast<volatile unsigned long long*>(host_status)[tid] = reinterpret_cast<const volatile unsigned long long*>(status)[tid];
 		return;
 	}
 	if (tid == 0) s_carry = 0;
@@ -583,112 +580,6 @@ __device__ __forceinline__ bool shade_pixel(const MeshView& mesh, const Uniforms
 	return finish_pixel<Shader, SMP>(mesh, u, in, ordinal >> 3, gi, z, var);
 }
 
-#if AXR_TILE_VCACHE
-// ---- warp-level post-transform vertex cache (variant) ---------------------------------------------------------------------------
-// The 32 pixels a warp shades together (an 8x4 block) are owned by up to 32 triangles, i.e. 96 vertex references, but neighbouring
-// triangles share vertices and a triangle larger than a pixel owns several lanes: C3 has ~28 distinct vertices per batch, scenes
-// with larger triangles far fewer. The plain path gathers 80 B and runs IShader::vertex per REFERENCE (15 LDG.128 + 3 vertex shaders
-// per pixel); here the warp
-//   1. inserts its references into a 128-slot open-addressing table in shared memory (atomicCAS on the vertex index; 96 keys always fit),
-//   2. compacts the occupied slots (ballots) so that distinct vertex u belongs to lane u mod 32,
-//   3. loads each DISTINCT vertex once (screen record, position, attributes), runs IShader::vertex once and parks
-//      {screen record, VertexOutput} in shared memory,
-//   4. every lane then reads its three entries and continues exactly like shade_pixel: setup -> coverage -> z -> depth test ->
-//      ((v0*al) + (v1*be)) + v2*ga -> IShader::fragment -> store.
-// The values and the order of every floating-point operation are those of the plain path (a VertexOutput is a pure function of the
-// vertex and the uniforms), so the frame is bit-identical. Pixels owned by a clipped face still take shade_pixel_clipped.
-constexpr unsigned VC_SLOTS = 128, VC_EMPTY = 0xFFFFFFFFu, VC_CAP = 96;
-template <typename Shader>
-struct VCache {
-	static constexpr int ENTRY = (4 + Shader::NV + 3) & ~3;  // floats per entry: screen record (4) + varyings, padded to 16 B
-	unsigned tab[VC_SLOTS];        // vertex index per slot
-	unsigned char cidx[VC_SLOTS];  // slot -> compact entry
-	unsigned char list[VC_CAP];    // compact entry -> slot
-	alignas(16) float data[VC_CAP * ENTRY];
-};
-
-template <typename Shader, int SMP>
-__device__ __forceinline__ bool shade_batch_cached(const MeshView& mesh, const Uniforms& u, const FrameParams& fp, const TileIn& in,
-                                                   VCache<Shader>& vc, bool valid, unsigned ord, int px, int py) {
-	constexpr int ENTRY = VCache<Shader>::ENTRY;
-	const unsigned lane = threadIdx.x & 31;
-	// 1. table reset + insert
-	reinterpret_cast<uint4*>(vc.tab)[lane] = make_uint4(VC_EMPTY, VC_EMPTY, VC_EMPTY, VC_EMPTY);
-	unsigned vi[3] = {0, 0, 0}, slot[3] = {0, 0, 0};
-	if (valid) {
-		const unsigned* ip = mesh.idx + (size_t)(ord >> 3) * 3;
-		vi[0] = __ldg(ip); vi[1] = __ldg(ip + 1); vi[2] = __ldg(ip + 2);
-	}
-	__syncwarp();
-	if (valid) {
-#pragma unroll
-		for (int k = 0; k < 3; ++k) {
-			unsigned h = (vi[k] * 2654435761u) >> 25;  // 7 bits
-			for (;;) {
-				const unsigned old = atomicCAS(&vc.tab[h], VC_EMPTY, vi[k]);
-				if (old == VC_EMPTY || old == vi[k]) break;
-				h = (h + 1) & (VC_SLOTS - 1);
-			}
-			slot[k] = h;
-		}
-	}
-	__syncwarp();
-	// 2. compact the occupied slots: lane l owns slots 4l..4l+3
-	const uint4 mine = reinterpret_cast<const uint4*>(vc.tab)[lane];
-	const unsigned keys[4] = {mine.x, mine.y, mine.z, mine.w};
-	const unsigned lt = (1u << lane) - 1u;
-	unsigned base = 0;
-#pragma unroll
-	for (int j = 0; j < 4; ++j) {
-		const bool occ = keys[j] != VC_EMPTY;
-		const unsigned b = __ballot_sync(0xffffffffu, occ);
-		if (occ) {
-			const unsigned pos = base + __popc(b & lt);
-			vc.list[pos] = (unsigned char)(lane * 4 + j);
-			vc.cidx[lane * 4 + j] = (unsigned char)pos;
-		}
-		base += __popc(b);
-	}
-	const unsigned n_unique = base;
-	__syncwarp();
-	// 3. one load + one IShader::vertex per distinct vertex
-	for (unsigned e = lane; e < n_unique; e += 32) {
-		const unsigned v = vc.tab[vc.list[e]];
-		const float4 sv = __ldg(in.sv + v);
-		const float4 p = __ldg(mesh.pos + v);
-		const float4* ap = reinterpret_cast<const float4*>(mesh.attr + v);
-		const float4 a0 = __ldg(ap), a1 = __ldg(ap + 1), a2 = __ldg(ap + 2);
-		float* d = vc.data + e * ENTRY;
-		*reinterpret_cast<float4*>(d) = sv;
-		float o[Shader::NV];
-		Shader::vertex(u, V3(p.x, p.y, p.z), V3(a0.z, a0.w, a1.x), V3(a1.y, a1.z, a1.w), V3(a2.x, a2.y, a2.z), a0.x, a0.y, o);
-#pragma unroll
-		for (int i = 0; i < Shader::NV; ++i) d[4 + i] = o[i];
-	}
-	__syncwarp();
-	// 4. per pixel: the tail of shade_pixel on cached entries
-	if (!valid) return false;
-	const float* e0 = vc.data + vc.cidx[slot[0]] * ENTRY;
-	const float* e1 = vc.data + vc.cidx[slot[1]] * ENTRY;
-	const float* e2 = vc.data + vc.cidx[slot[2]] * ENTRY;
-	const float4 s0 = *reinterpret_cast<const float4*>(e0), s1 = *reinterpret_cast<const float4*>(e1), s2 = *reinterpret_cast<const float4*>(e2);
-	if ((__float_as_uint(s0.w) | __float_as_uint(s1.w) | __float_as_uint(s2.w)) & 0x3fu)
-		return shade_pixel_clipped<Shader, SMP>(mesh, u, fp, in, ord, vi[0], vi[1], vi[2], px, py);
-	const size_t gi = (size_t)py * fp.W + px;
-	const float fbz = in.read_depth ? in.depth_read[gi] : INFINITY;
-	Setup s;
-	if (!setup_triangle(s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, fp.W, fp.y_lo, fp.y_hi, s)) return false;
-	float c0, c1, c2, al, be, ga;
-	coverage(s, px, py, c0, c1, c2);
-	const float z = interp_z(s, c0, c1, c2, al, be, ga);
-	if (!(z < fbz)) return false;  // mergeTileResults: strict tileZ < fbZ (reference src/tiled_pipeline.cpp:1148-1156)
-	float var[Shader::NV];
-#pragma unroll
-	for (int i = 0; i < Shader::NV; ++i) var[i] = ((e0[4 + i] * al) + (e1[4 + i] * be)) + e2[4 + i] * ga;
-	return finish_pixel<Shader, SMP>(mesh, u, in, ord >> 3, gi, z, var);
-}
-#endif  // AXR_TILE_VCACHE
-
 template <typename Shader, int SMP>
 __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(const __grid_constant__ MeshView mesh, const __grid_constant__ Uniforms u, const __grid_constant__ FrameParams fp,
                                                                              const __grid_constant__ TileIn in) {
@@ -772,9 +663,6 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 	}
 	// 3. deferred shading of the visible triangle of each pixel + framebuffer resolve.
 	constexpr int PPT = GT_PIX / TILE_THREADS;
-#if AXR_TILE_VCACHE
-	__shared__ VCache<Shader> s_vc[TILE_THREADS / 32];
-#endif
 	//    Not unrolled: one copy of the shading code keeps the kernel inside the instruction cache (unrolled x4 with prefetched
 	//    indices: +12 % time; prefetched indices selected inside a rolled loop: +2 %).
 #pragma unroll 1
@@ -784,21 +672,12 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 		const int blk = i * (TILE_THREADS / 32) + (tid >> 5);
 		const int p = in.row_major ? blk * GT + (tid & 31) : ((blk >> 2) * 4 + ((tid & 31) >> 3)) * GT + (blk & 3) * 8 + (tid & 7);
 		const unsigned long long k = s_keys[p];
-#if AXR_TILE_VCACHE
-		const int px = x0 + (p & (GT - 1)), py = y0 + (p / GT);
-		const bool valid = k != KEY_EMPTY;
-		if (__ballot_sync(0xffffffffu, valid) == 0u) continue;  // warp-uniform: the whole batch is empty
-		const unsigned ord = (unsigned)(k & 0xFFFFFFFFull);
-		const bool discarded = shade_batch_cached<Shader, SMP>(mesh, u, fp, in, s_vc[tid >> 5], valid, ord, px, py);
-		if (!valid) continue;
-#else
 		if (k == KEY_EMPTY) continue;
 		const unsigned ord = (unsigned)(k & 0xFFFFFFFFull);
 		const unsigned* ip = mesh.idx + (size_t)(ord >> 3) * 3;
 		const unsigned i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
 		const int px = x0 + (p & (GT - 1)), py = y0 + (p / GT);
 		const bool discarded = shade_pixel<Shader, SMP>(mesh, u, fp, in, ord, i0, i1, i2, px, py);
-#endif
 		if constexpr (PEEL) {
 			// discarded: the next pass looks for this pixel's next key above k. Otherwise the pixel is finished (the winner
 			// was drawn, or it lost against the framebuffer and everything behind it would too): no key passes KEY_EMPTY.

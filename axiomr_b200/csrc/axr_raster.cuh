@@ -230,35 +230,6 @@ __device__ __forceinline__ bool coverage(const Setup& s, int px, int py, float& 
 	c2 = r2 + s.a2 * fi;
 	return c0 >= 0.f && c1 >= 0.f && c2 >= 0.f;  // _CMP_GE_OQ: NaN fails
 }
-// The same closed form, hoisted for a thread that walks a sub-box [xa,xb) x [ya,yb) of the triangle's pixel box: the row start
-// values are computed once per row and per 16-px reference-tile segment; per pixel only (+ a*8.0f)? + a*(float)i remains.
-// Bit-identical to coverage() (same operations in the same order). f(px, py, c0, c1, c2) is called for covered pixels.
-template <typename F>
-__device__ __forceinline__ void for_each_covered(const Setup& s, int xa, int xb, int ya, int yb, F&& f) {
-	const float a08 = s.a0 * 8.0f, a18 = s.a1 * 8.0f, a28 = s.a2 * 8.0f;
-	for (int py = ya; py < yb; ++py) {
-		const float pyc = (float)py + 0.5f;
-		const float t0 = s.b0 * pyc, t1 = s.b1 * pyc, t2 = s.b2 * pyc;
-		for (int seg = xa; seg < xb;) {
-			const int tile0 = seg & ~(REF_TILE - 1);
-			const int seg_end = min(xb, tile0 + REF_TILE);
-			const int startX = max(tile0, s.fminx);
-			const float sxc = (float)startX + 0.5f;
-			const float r0 = s.a0 * sxc + t0 + s.c0, r1 = s.a1 * sxc + t1 + s.c1, r2 = s.a2 * sxc + t2 + s.c2;
-			const float q0 = r0 + a08, q1 = r1 + a18, q2 = r2 + a28;  // second group of eight (:535-537)
-			for (int px = seg; px < seg_end; ++px) {
-				const int d = px - startX;  // 0..15
-				const bool hi = d >= 8;
-				const float fi = (float)(d & 7);
-				const float c0 = (hi ? q0 : r0) + s.a0 * fi;
-				const float c1 = (hi ? q1 : r1) + s.a1 * fi;
-				const float c2 = (hi ? q2 : r2) + s.a2 * fi;
-				if (c0 >= 0.f && c1 >= 0.f && c2 >= 0.f) f(px, py, c0, c1, c2);
-			}
-			seg = seg_end;
-		}
-	}
-}
 // :555-562
 __device__ __forceinline__ float interp_z(const Setup& s, float c0, float c1, float c2, float& al, float& be, float& ga) {
 	al = c0 * s.inv_area;
