@@ -7,21 +7,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from axiomr_b200 import build as b  # noqa: E402
 
-F = ["AXR_SETUP_FLAT=1"]
-B = F + ["AXR_SETUP_MINB=16", "AXR_TILE_THREADS=128", "AXR_TILE_MINB=8"]  # best launch shapes of batch 2
+# Compile-time knobs of axr_kernels.cuh (launch shapes). The defaults are the winners of the round-1 A/B runs
+# (profiles/r01_ab_*.jsonl); these variants bracket them.
 VARIANTS = {
-    # warp-level post-transform vertex cache in the shading phase (axr_kernels.cuh: shade_batch_cached), 4 warps per CTA
-    "vcache": ["AXR_TILE_VCACHE=1", "AXR_TILE_THREADS=128", "AXR_TILE_MINB=5"],
-    "nested": ["AXR_SETUP_FLAT=0"],
-    "best": B,
-    "best_et": B + ["AXR_TILE_EARLY_TEX=1"],
-    "best_et_mb7": F + ["AXR_SETUP_MINB=16", "AXR_TILE_THREADS=128", "AXR_TILE_MINB=7", "AXR_TILE_EARLY_TEX=1"],
-    "best_et_s256": F + ["AXR_SETUP_MINB=16", "AXR_TILE_THREADS=256", "AXR_TILE_MINB=4", "AXR_TILE_EARLY_TEX=1"],
-    "best_u1": B + ["AXR_FLAT_UNROLL=1"],
-    "best_t256": F + ["AXR_SETUP_THREADS=256", "AXR_SETUP_MINB=8", "AXR_TILE_THREADS=128", "AXR_TILE_MINB=8"],
-    "best_t64": F + ["AXR_SETUP_THREADS=64", "AXR_SETUP_MINB=32", "AXR_TILE_THREADS=128", "AXR_TILE_MINB=8"],
-    "best_s128mb9": F + ["AXR_SETUP_MINB=16", "AXR_TILE_THREADS=128", "AXR_TILE_MINB=9"],
-    "best_s128mb10": F + ["AXR_SETUP_MINB=16", "AXR_TILE_THREADS=128", "AXR_TILE_MINB=10"],
+    "setup_mb12": ["AXR_SETUP_MINB=12"],
+    "setup_mb14": ["AXR_SETUP_MINB=14"],
+    "setup_t256": ["AXR_SETUP_THREADS=256", "AXR_SETUP_MINB=8"],
+    "setup_t64": ["AXR_SETUP_THREADS=64", "AXR_SETUP_MINB=32"],
+    "setup_fpt2": ["AXR_SETUP_FPT=2"],
+    "tile_128x8": ["AXR_TILE_THREADS=128", "AXR_TILE_MINB=8"],
+    "tile_256x3": ["AXR_TILE_THREADS=256", "AXR_TILE_MINB=3"],
 }
 
 if __name__ == "__main__":
