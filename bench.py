@@ -414,6 +414,8 @@ def main():
             t_hbm = per_stage.get(k, 0) / (peak * 1e9) * 1e3
             per_kernel[k] = {"warp_inst": c["warp_inst"], "t_issue_ms": t_issue, "t_hbm_ms": t_hbm, "binding": "fp32_issue" if t_issue > t_hbm else "hbm",
                              "measured_ms": kavg.get(k), "frac_of_binding": (max(t_issue, t_hbm) / kavg[k]) if kavg.get(k) else None}
+            if c.get("note"):
+                per_kernel[k]["note"] = c["note"]
         issue["per_kernel"] = per_kernel
         if per_kernel:
             t_bind = sum(max(v["t_issue_ms"], v["t_hbm_ms"]) for v in per_kernel.values())
