@@ -276,6 +276,9 @@ constexpr int SETUP_THREADS = AXR_SETUP_THREADS;
 #ifndef AXR_TILE_MINB
 #define AXR_TILE_MINB 4
 #endif
+#ifndef AXR_TILE_SPLIT
+#define AXR_TILE_SPLIT 0
+#endif
 constexpr int SETUP_FPT = AXR_SETUP_FPT;  // faces per thread: index loads and 16 B screen-record gathers of all of them are issued back to back
 
 template <bool PEEL>
@@ -580,6 +583,35 @@ __device__ __forceinline__ bool shade_pixel(const MeshView& mesh, const Uniforms
 	return finish_pixel<Shader, SMP>(mesh, u, in, ordinal >> 3, gi, z, var);
 }
 
+#if AXR_TILE_SPLIT
+// ---- variant (off by default, not yet timed on a B200): the shading phase in two steps ------------------------------------------
+// The plain path walks, per pixel, the dependent chain key -> indices -> vertex records -> (setup, depth test, vertex shaders)
+// -> texels -> (fragment) -> store, four pixels one after the other per thread: three global-memory latencies in series per pixel
+// at 32 resident warps per SM (the A/B series of round 1 showed the phase to be bound by that chain, not by issue slots or gather
+// wavefronts). Here every thread first RESOLVES all of its pixels — all index loads in flight together, then all screen-record
+// gathers and depth reads, then setup / coverage / z / depth test — and parks {indices, ordinal, barycentrics, z} in its own 32 B
+// shared-memory slots; the SHADE step then starts from those slots, so its chain is attributes -> texels only and it no longer
+// carries the screen records and the setup. Same arithmetic in the same order per pixel: bit-identical frames.
+struct __align__(16) PixRec { unsigned i0, i1, i2, ord; float al, be, ga, z; };
+constexpr unsigned REC_DEAD = 0xFFFFFFFFu;  // no ordinal reaches it (faces < 2^29, see axr_upload_mesh)
+
+template <typename Shader, int SMP>
+__device__ __forceinline__ bool shade_resolved(const MeshView& mesh, const Uniforms& u, const TileIn& in, const PixRec& r, size_t gi) {
+	const float4 p0 = __ldg(mesh.pos + r.i0), p1 = __ldg(mesh.pos + r.i1), p2 = __ldg(mesh.pos + r.i2);
+	const float4* ap0 = reinterpret_cast<const float4*>(mesh.attr + r.i0);
+	const float4* ap1 = reinterpret_cast<const float4*>(mesh.attr + r.i1);
+	const float4* ap2 = reinterpret_cast<const float4*>(mesh.attr + r.i2);
+	const float4 a00 = __ldg(ap0), a01 = __ldg(ap0 + 1), a02 = __ldg(ap0 + 2);
+	const float4 a10 = __ldg(ap1), a11 = __ldg(ap1 + 1), a12 = __ldg(ap1 + 2);
+	const float4 a20 = __ldg(ap2), a21 = __ldg(ap2 + 1), a22 = __ldg(ap2 + 2);
+	float var[Shader::NV];
+	accumulate_vertex<Shader>(u, 0, r.al, V3(p0.x, p0.y, p0.z), V3(a00.z, a00.w, a01.x), V3(a01.y, a01.z, a01.w), V3(a02.x, a02.y, a02.z), a00.x, a00.y, var);
+	accumulate_vertex<Shader>(u, 1, r.be, V3(p1.x, p1.y, p1.z), V3(a10.z, a10.w, a11.x), V3(a11.y, a11.z, a11.w), V3(a12.x, a12.y, a12.z), a10.x, a10.y, var);
+	accumulate_vertex<Shader>(u, 2, r.ga, V3(p2.x, p2.y, p2.z), V3(a20.z, a20.w, a21.x), V3(a21.y, a21.z, a21.w), V3(a22.x, a22.y, a22.z), a20.x, a20.y, var);
+	return finish_pixel<Shader, SMP>(mesh, u, in, r.ord >> 3, gi, r.z, var);
+}
+#endif  // AXR_TILE_SPLIT
+
 template <typename Shader, int SMP>
 __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(const __grid_constant__ MeshView mesh, const __grid_constant__ Uniforms u, const __grid_constant__ FrameParams fp,
                                                                              const __grid_constant__ TileIn in) {
@@ -663,6 +695,72 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 	}
 	// 3. deferred shading of the visible triangle of each pixel + framebuffer resolve.
 	constexpr int PPT = GT_PIX / TILE_THREADS;
+#if AXR_TILE_SPLIT
+	{
+		__shared__ PixRec s_rec[GT_PIX];  // slot p is written and read by the one thread that owns pixel p: no barrier in between
+		const auto pixel_of = [&](int i) {
+			const int blk = i * (TILE_THREADS / 32) + (tid >> 5);
+			return in.row_major ? blk * GT + (tid & 31) : ((blk >> 2) * 4 + ((tid & 31) >> 3)) * GT + (blk & 3) * 8 + (tid & 7);
+		};
+		// 3a. resolve: index loads of all pixels first, then per pixel the gathers that depend on them
+		unsigned long long k[PPT];
+		unsigned vi[PPT][3];
+#pragma unroll
+		for (int i = 0; i < PPT; ++i) {
+			k[i] = s_keys[pixel_of(i)];
+			if (k[i] != KEY_EMPTY) {
+				const unsigned* ip = mesh.idx + (size_t)((unsigned)(k[i] & 0xFFFFFFFFull) >> 3) * 3;
+				vi[i][0] = __ldg(ip); vi[i][1] = __ldg(ip + 1); vi[i][2] = __ldg(ip + 2);
+			}
+		}
+#pragma unroll
+		for (int i = 0; i < PPT; ++i) {
+			if (k[i] == KEY_EMPTY) continue;
+			const int p = pixel_of(i);
+			const int px = x0 + (p & (GT - 1)), py = y0 + (p / GT);
+			const size_t gi = (size_t)py * fp.W + px;
+			PixRec r;
+			r.i0 = vi[i][0]; r.i1 = vi[i][1]; r.i2 = vi[i][2];
+			r.ord = REC_DEAD;
+			r.al = r.be = r.ga = r.z = 0.0f;
+			const float4 s0 = __ldg(in.sv + r.i0), s1 = __ldg(in.sv + r.i1), s2 = __ldg(in.sv + r.i2);
+			const float fbz = in.read_depth ? in.depth_read[gi] : INFINITY;
+			if ((__float_as_uint(s0.w) | __float_as_uint(s1.w) | __float_as_uint(s2.w)) & 0x3fu) {
+				r.ord = (unsigned)(k[i] & 0xFFFFFFFFull);
+				r.z = __uint_as_float(0x7fc00000u);  // NaN marks "owned by a clipped face": shade_pixel_clipped redoes everything
+			} else {
+				Setup s;
+				if (setup_triangle(s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, fp.W, fp.y_lo, fp.y_hi, s)) {
+					float c0, c1, c2;
+					coverage(s, px, py, c0, c1, c2);
+					const float z = interp_z(s, c0, c1, c2, r.al, r.be, r.ga);
+					if (z < fbz) { r.ord = (unsigned)(k[i] & 0xFFFFFFFFull); r.z = z; }  // mergeTileResults: strict tileZ < fbZ
+				}
+			}
+			s_rec[p] = r;
+		}
+		// 3b. shade
+#pragma unroll 1
+		for (int i = 0; i < PPT; ++i) {
+			if (k[i] == KEY_EMPTY) continue;
+			const int p = pixel_of(i);
+			const int px = x0 + (p & (GT - 1)), py = y0 + (p / GT);
+			const PixRec r = s_rec[p];
+			bool discarded = false;
+			if (r.ord != REC_DEAD) {
+				if (r.z != r.z) discarded = shade_pixel_clipped<Shader, SMP>(mesh, u, fp, in, r.ord, r.i0, r.i1, r.i2, px, py);
+				else discarded = shade_resolved<Shader, SMP>(mesh, u, in, r, (size_t)py * fp.W + px);
+			}
+			if constexpr (PEEL) {
+				in.floor[(size_t)py * fp.W + px] = discarded ? k[i] : KEY_EMPTY;
+				if (discarded && *in.again == 0u) *in.again = 1u;
+			} else {
+				(void)discarded;
+			}
+		}
+		return;
+	}
+#endif
 	//    Not unrolled: one copy of the shading code keeps the kernel inside the instruction cache (unrolled x4 with prefetched
 	//    indices: +12 % time; prefetched indices selected inside a rolled loop: +2 %).
 #pragma unroll 1

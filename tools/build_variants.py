@@ -17,6 +17,11 @@ VARIANTS = {
     "setup_fpt2": ["AXR_SETUP_FPT=2"],
     "tile_128x8": ["AXR_TILE_THREADS=128", "AXR_TILE_MINB=8"],
     "tile_256x3": ["AXR_TILE_THREADS=256", "AXR_TILE_MINB=3"],
+    # shading phase in two steps (resolve all pixels of a thread, then shade from shared-memory slots): bit-exact on the SIMT
+    # interpreter, NOT yet timed — the first thing to A/B in the next round
+    "tile_split": ["AXR_TILE_SPLIT=1"],
+    "tile_split_mb5": ["AXR_TILE_SPLIT=1", "AXR_TILE_MINB=5"],
+    "tile_split_128x8": ["AXR_TILE_SPLIT=1", "AXR_TILE_THREADS=128", "AXR_TILE_MINB=8"],
 }
 
 if __name__ == "__main__":
