@@ -22,13 +22,16 @@ SKIP_ALWAYS = ["full_config", "full_c3", "multi_gpu", "cpp_dropin"]  # full-size
 SKIP_FAST = ["bin_overflow", "overlapped", "dense_640x480", "huge_9_layers", "composites_bands_and_host"]
 
 
-def _run(extra_env=None, k_extra=(), only=None, min_passed=30):
+def _run(extra_env=None, k_extra=(), only=None, min_passed=30, defines=(), tag=None):
     sys.path.insert(0, os.path.join(ROOT, "tests", "simt"))
     try:
         import build as simt_build
     finally:
         sys.path.pop(0)
-    lib = simt_build.build()
+    if defines:
+        lib = simt_build.build(force=True, defines=list(defines), out=os.path.join(simt_build.OUT_DIR, f"libaxr_simt_{tag}.so"))
+    else:
+        lib = simt_build.build()
     skip = SKIP_ALWAYS + ([] if os.environ.get("AXR_SIMT_FULL") == "1" else SKIP_FAST) + list(k_extra)
     env = dict(os.environ, AXR_B200_LIB=lib, AXR_SIMT_TESTS_ONLY="1", **(extra_env or {}))
     cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "tests/test_property.py", "-m", "gpu", "-q", "-x",
@@ -51,6 +54,13 @@ def test_results_do_not_depend_on_the_thread_or_cta_schedule(order):
     atomics, the 64-bit visibility keys and the depth-peeling floor must give bit-identical frames under any legal schedule."""
     _run({"AXR_SIMT_ORDER": order}, only="random_clipped or golden or clipped_binned or bands_equal or composite_two or torture "
          "or multi_material or small_tris or random_pixel_space", min_passed=15)
+
+
+@pytest.mark.parametrize("tag,defines", [("split", ["AXR_TILE_SPLIT=1"]), ("shapes", ["AXR_TILE_THREADS=128", "AXR_SETUP_THREADS=256"])])
+def test_opt_in_kernel_variants_stay_bit_exact(tag, defines):
+    """The compile-time variants tools/build_variants.py offers for A/B timing (axr_kernels.cuh) must render the same frames."""
+    _run(defines=defines, tag=tag, only="random_clipped or golden or clipped_binned or bands_equal or composite_two or torture "
+         "or multi_material or small_tris or host_framebuffer or huge_triangles", min_passed=15)
 
 
 def test_product_loader_refuses_the_interpreter_build():
