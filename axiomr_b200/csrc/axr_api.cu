@@ -122,6 +122,9 @@ struct axr_ctx {
 	cudaEvent_t up_done[MAX_HOST_CHUNKS] = {};
 	cudaEvent_t depth_free = nullptr;  // main stream: the previous user of the device depth copy is done
 	int host_chunks = 0;               // > 0 only while axr_draw_mesh_host issues its draw
+	// Experiment knob (environment variable AXR_B200_HOST_DEPTH_ZEROCOPY=1 at axr_create; not yet timed): no depth upload at all,
+	// the merge test reads the host depth of the visible pixels through the zero-copy mapping (128 B row reads over PCIe)
+	bool host_depth_zero_copy = false;
 	int chunk_ty[MAX_HOST_CHUNKS + 1] = {};  // GPU tile rows [chunk_ty[b], chunk_ty[b+1]) of chunk b
 
 	// depth peeling (draws with a shader that may discard): per-pixel floor keys + the "another pass" flag; allocated on first use
@@ -456,6 +459,7 @@ int axr_create(const axr_config* cfg, axr_ctx** out) {
 	c->fp.ty_lo = y0 / GT;
 	c->fp.ty_hi = (y1 + GT - 1) / GT;
 	c->sampler = cfg->sampler ? 1 : 0;
+	if (const char* e = getenv("AXR_B200_HOST_DEPTH_ZEROCOPY")) c->host_depth_zero_copy = e[0] == '1';
 	// identity uniforms until axr_set_uniforms
 	memset(c->view_proj, 0, sizeof c->view_proj);
 	memset(c->viewport, 0, sizeof c->viewport);
@@ -831,7 +835,7 @@ int axr_draw_mesh_host(axr_ctx* ctx, axr_mesh mh, const float model[16], uint8_t
 	const int ty_lo = ctx->fp.ty_lo, ty_hi = ctx->fp.ty_hi;
 	int chunks = ctx->shader_kind == AXR_SHADER_CUTOUT ? 1 : (ty_hi - ty_lo) / 16;  // >= 16 tile rows (512 px) per chunk (C3 e2e: 1.22 / 1.04 / 1.06 / 1.09 ms with 1 / 2 / 4 / 8 chunks); peeled draws re-read the copy
 	if (chunks > axr_ctx::MAX_HOST_CHUNKS) chunks = axr_ctx::MAX_HOST_CHUNKS;
-	if (chunks < 1) chunks = 1;
+	if (chunks < 1 || ctx->host_depth_zero_copy) chunks = 1;
 	CU(cudaEventRecord(ctx->depth_free, ctx->stream));
 	CU(cudaStreamWaitEvent(ctx->up_stream, ctx->depth_free, 0));
 	for (int b = 0; b <= chunks; ++b) ctx->chunk_ty[b] = ty_lo + (int)((long long)(ty_hi - ty_lo) * b / chunks);
@@ -841,12 +845,13 @@ int axr_draw_mesh_host(axr_ctx* ctx, axr_mesh mh, const float model[16], uint8_t
 		if (r1 > ctx->fp.y_hi) r1 = ctx->fp.y_hi;
 		if (r1 > r0) {
 			const size_t off = (size_t)r0 * ctx->fp.W, cnt = (size_t)(r1 - r0) * ctx->fp.W;
-			CU(cudaMemcpyAsync(ctx->depth + off, depth + off, cnt * 4, cudaMemcpyHostToDevice, ctx->up_stream));
+			if (!ctx->host_depth_zero_copy) CU(cudaMemcpyAsync(ctx->depth + off, depth + off, cnt * 4, cudaMemcpyHostToDevice, ctx->up_stream));
 		}
 		CU(cudaEventRecord(ctx->up_done[b], ctx->up_stream));
 	}
 	unsigned* save_c = ctx->out_color; float* save_d = ctx->out_depth;
-	ctx->out_color = (unsigned*)dc; ctx->out_depth = (float*)dd; ctx->depth_read_override = ctx->depth;
+	ctx->out_color = (unsigned*)dc; ctx->out_depth = (float*)dd;
+	ctx->depth_read_override = ctx->host_depth_zero_copy ? (const float*)dd : ctx->depth;
 	ctx->host_chunks = chunks;
 	rc = draw(ctx, mh, model);
 	if (!rc) rc = check_pending(ctx);  // a bin overflow re-issues the draw while the host pointers are still installed
