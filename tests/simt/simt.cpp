@@ -230,7 +230,13 @@ void run_grid(dim3 grid, dim3 block, const std::function<void()>& body, const ch
 
 // ------------------------------------------------------------------------------------------------ memory
 namespace {
+// Built with -fsanitize=address (build.py sanitize="address") the allocations carry no zones of their own: AddressSanitizer's
+// redzones then sit right behind the requested size and catch out-of-bounds READS by kernels as well, not only stores.
+#if defined(__SANITIZE_ADDRESS__)
+constexpr size_t GUARD = 0;
+#else
 constexpr size_t GUARD = 256;
+#endif
 constexpr unsigned char CANARY = 0xA5;
 std::map<char*, size_t> g_dev;                 // user pointer -> bytes
 std::map<char*, size_t> g_host;                // host ranges a device pointer can be asked for
@@ -253,7 +259,7 @@ void check_canaries(const char* when) {
 using namespace simt;
 
 cudaError_t simt_malloc(void** p, size_t bytes) {
-	char* base = static_cast<char*>(aligned_alloc(256, (bytes + 2 * GUARD + 255) / 256 * 256));
+	char* base = static_cast<char*>(GUARD ? aligned_alloc(256, (bytes + 2 * GUARD + 255) / 256 * 256) : malloc(bytes ? bytes : 1));
 	if (!base) return cudaErrorMemoryAllocation;
 	memset(base, CANARY, GUARD);
 	memset(base + GUARD, 0xCD, bytes);  // device memory is not zero-initialised
