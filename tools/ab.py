@@ -44,12 +44,39 @@ def smoke_scene() -> S.Scene:
                    textures=S._phong_textures(128))
 
 
+def e2e_ms(sc: S.Scene, steps: int) -> float:
+    """The reference-facing call: TiledPipeline.drawMesh(model, mesh) on a host framebuffer, complete on return (bench.py's e2e)."""
+    fb = api.Framebuffer(sc.width, sc.height, True)
+    cam = api.Camera()
+    cam.setViewport(0, 0, sc.width, sc.height)
+    cam.setViewProjectionMatrix(sc.view_proj)
+    cam._pos = np.asarray(sc.cam_pos, dtype=np.float32)
+    pipe = api.TiledPipeline(os.cpu_count() or 1, cam, fb, device=0, sampler=sc.sampler)
+    pipe.setShader([api.FlatShader(tuple(sc.light_dir)), api.PhongShader(tuple(sc.light_dir), tuple(sc.light_color)),
+                    api.PBRShader(tuple(sc.light_dir), tuple(sc.light_color))][sc.shader])
+    tex = [api.Texture(t) if t is not None else None for t in sc.textures]
+    mesh = api.Mesh(sc.vertices, sc.indices, {"m0": api.Material("m0", tex[0], tex[2], tex[1], tex[3], tex[4], sc.specular_exponent)})
+    total = 0.0
+    n = max(3, min(steps, 10))
+    for i in range(n + 2):  # the first call uploads and caches the mesh
+        fb.clearColor(api.Color(0, 0, 0, 255))
+        fb.clearDepth()
+        t0 = time.perf_counter()
+        pipe.drawMesh(sc.model, mesh)
+        if i >= 2:
+            total += time.perf_counter() - t0
+    pipe.device.close()
+    return total / n * 1e3
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--e2e", action="store_true", help="also time TiledPipeline.drawMesh on a pinned host framebuffer (axr_draw_mesh_host), "
+                    "with and without AXR_B200_HOST_DEPTH_ZEROCOPY")
     ap.add_argument("variants", nargs="*")
     a = ap.parse_args()
     libs = {"default": os.path.join(ROOT, "axiomr_b200", "libaxr_b200.so")}
@@ -93,6 +120,12 @@ def main():
             st = dev.stats()
             rec["stats"] = {k: st[k] for k in ("triangles", "small_triangles", "binned_triangles", "bin_refs")}
             dev.close()
+            if a.e2e:
+                rec["e2e_ms"] = {}
+                for knob in ("0", "1"):
+                    os.environ["AXR_B200_HOST_DEPTH_ZEROCOPY"] = knob  # read by axr_create
+                    rec["e2e_ms"]["zerocopy_depth" if knob == "1" else "upload_depth"] = round(e2e_ms(sc, a.steps), 4)
+                os.environ.pop("AXR_B200_HOST_DEPTH_ZEROCOPY", None)
         except Exception as e:  # a variant that fails must not hide the others
             rec["error"] = repr(e)
         line = json.dumps(rec)
