@@ -279,6 +279,9 @@ constexpr int SETUP_THREADS = AXR_SETUP_THREADS;
 #ifndef AXR_TILE_SPLIT
 #define AXR_TILE_SPLIT 0
 #endif
+#ifndef AXR_SETUP_PREFETCH
+#define AXR_SETUP_PREFETCH 0
+#endif
 constexpr int SETUP_FPT = AXR_SETUP_FPT;  // faces per thread: index loads and 16 B screen-record gathers of all of them are issued back to back
 
 template <bool PEEL>
@@ -286,6 +289,16 @@ __global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(
                                                                 const __grid_constant__ m4 mvp, const __grid_constant__ FrameParams fp,
                                                                 const __grid_constant__ SetupOut o) {
 	const unsigned long long base = (unsigned long long)blockIdx.x * (SETUP_THREADS * SETUP_FPT) + threadIdx.x;
+#if AXR_SETUP_PREFETCH && defined(__CUDA_ARCH__)
+	// Variant (off by default, not yet timed): pull the index lines of the CTA AXR_SETUP_PREFETCH positions ahead into L2, so that its
+	// first-level loads are L2 hits instead of DRAM round trips (one 128 B line per thread, 12 B x SETUP_THREADS x SETUP_FPT per CTA).
+	{
+		const unsigned long long first = ((unsigned long long)blockIdx.x + AXR_SETUP_PREFETCH) * (SETUP_THREADS * SETUP_FPT) * 3ull;  // in u32
+		const unsigned long long line = first + (unsigned long long)threadIdx.x * 32ull;
+		if (threadIdx.x * 32u < SETUP_THREADS * SETUP_FPT * 3u && line < mesh.n_faces * 3ull)
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(mesh.idx + line));
+	}
+#endif
 	unsigned vi[SETUP_FPT][3];
 	float4 s[SETUP_FPT][3];
 #pragma unroll

@@ -17,6 +17,9 @@ VARIANTS = {
     "setup_fpt2": ["AXR_SETUP_FPT=2"],
     "tile_128x8": ["AXR_TILE_THREADS=128", "AXR_TILE_MINB=8"],
     "tile_256x3": ["AXR_TILE_THREADS=256", "AXR_TILE_MINB=3"],
+    # L2 prefetch of the index stream one / two waves of CTAs ahead (148 SMs x 16 CTAs = 2368 resident CTAs); not yet timed
+    "setup_pf2368": ["AXR_SETUP_PREFETCH=2368"],
+    "setup_pf4736": ["AXR_SETUP_PREFETCH=4736"],
     # shading phase in two steps (resolve all pixels of a thread, then shade from shared-memory slots): bit-exact on the SIMT
     # interpreter, NOT yet timed — the first thing to A/B in the next round
     "tile_split": ["AXR_TILE_SPLIT=1"],
