@@ -244,6 +244,20 @@ cudaEvent_t prof_mark(axr_ctx* ctx, cudaStream_t s) {
 	return e;
 }
 
+#if AXR_PDL
+// Variant: launch with programmatic stream serialization (see AXR_PDL in axr_kernels.cuh)
+template <typename... KP, typename... A>
+cudaError_t launch_pdl(void (*kernel)(KP...), dim3 grid, dim3 block, cudaStream_t stream, A&&... args) {
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr; cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, kernel, KP(args)...);
+}
+#endif
+
 // One launch over all tile rows of the band, or (axr_draw_mesh_host) one launch per uploaded row chunk, each behind its upload.
 template <typename Shader>
 int launch_tile(axr_ctx* ctx, const MeshView& mv, const Uniforms& u, const TileIn& in) {
@@ -255,8 +269,13 @@ int launch_tile(axr_ctx* ctx, const MeshView& mv, const Uniforms& u, const TileI
 			cudaStreamWaitEvent(ctx->stream, ctx->up_done[b], 0);
 		}
 		dim3 grid(fp.ntx, fp.ty_hi - fp.ty_lo);
+#if AXR_PDL
+		if (u.sampler) launch_pdl(k_tile_shade<Shader, 1>, grid, dim3(TILE_THREADS), ctx->stream, mv, u, fp, in);
+		else launch_pdl(k_tile_shade<Shader, 0>, grid, dim3(TILE_THREADS), ctx->stream, mv, u, fp, in);
+#else
 		if (u.sampler) k_tile_shade<Shader, 1><<<grid, TILE_THREADS, 0, ctx->stream>>>(mv, u, fp, in);
 		else k_tile_shade<Shader, 0><<<grid, TILE_THREADS, 0, ctx->stream>>>(mv, u, fp, in);
+#endif
 	}
 	return chunks;
 }
@@ -306,8 +325,13 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 	{
 		// at least sizeof(DrawStatus)/4 threads: the kernel also zeroes the draw's counters
 		const unsigned long long threads = m.n_verts > sizeof(DrawStatus) / 4 ? m.n_verts : sizeof(DrawStatus) / 4;
+#if AXR_PDL
+		launch_pdl(k_vertex_xform, dim3((unsigned)((threads + 255) / 256)), dim3(256), g, m.pos, m.n_verts, u.mvp, (float)ctx->fp.W, (float)ctx->fp.H,
+		           m.sv[si], sl.d_status, sl.n_records);
+#else
 		k_vertex_xform<<<(unsigned)((threads + 255) / 256), 256, 0, g>>>(m.pos, m.n_verts, u.mvp, (float)ctx->fp.W, (float)ctx->fp.H, m.sv[si],
 		                                                                sl.d_status, sl.n_records);
+#endif
 		++launches;
 	}
 	prof_mark(ctx, g);
@@ -322,19 +346,34 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 	if (m.n_faces) {
 		const unsigned long long per_cta = (unsigned long long)SETUP_THREADS * SETUP_FPT;
 		const unsigned grid = (unsigned)((m.n_faces + per_cta - 1) / per_cta);
+#if AXR_PDL
+		if (peel) launch_pdl(k_setup_raster<true>, dim3(grid), dim3(SETUP_THREADS), g, mv, (const float4*)m.sv[si], u.mvp, ctx->fp, so);
+		else launch_pdl(k_setup_raster<false>, dim3(grid), dim3(SETUP_THREADS), g, mv, (const float4*)m.sv[si], u.mvp, ctx->fp, so);
+#else
 		if (peel) k_setup_raster<true><<<grid, SETUP_THREADS, 0, g>>>(mv, m.sv[si], u.mvp, ctx->fp, so);
 		else k_setup_raster<false><<<grid, SETUP_THREADS, 0, g>>>(mv, m.sv[si], u.mvp, ctx->fp, so);
+#endif
 		++launches;
 	}
 	prof_mark(ctx, g);
 	prof_mark(ctx, g);
+#if AXR_PDL
+	launch_pdl(k_scan_tiles, dim3(1), dim3(SCAN_THREADS), g, sl.tile_count, sl.bin_start, n_tiles(ctx), sl.ref_cap, (const unsigned*)sl.n_records,
+	           sl.rec_cap, sl.d_status, sl.h_status_dev);
+#else
 	k_scan_tiles<<<1, SCAN_THREADS, 0, g>>>(sl.tile_count, sl.bin_start, n_tiles(ctx), sl.ref_cap, sl.n_records, sl.rec_cap, sl.d_status,
 	                                       sl.h_status_dev);
+#endif
 	++launches;
 	prof_mark(ctx, g);
 	CU(cudaEventRecord(sl.status_event, g));  // the scan kernel has stored the status into mapped host memory
 	prof_mark(ctx, g);
+#if AXR_PDL
+	launch_pdl(k_bin_scatter, dim3(148 * 4), dim3(256), g, (const TriRecord*)sl.records, (const unsigned*)sl.n_records, ctx->fp,
+	           (const unsigned*)sl.bin_start, sl.tile_count, sl.items, (const DrawStatus*)sl.d_status);
+#else
 	k_bin_scatter<<<148 * 4, 256, 0, g>>>(sl.records, sl.n_records, ctx->fp, sl.bin_start, sl.tile_count, sl.items, sl.d_status);
+#endif
 	++launches;
 	prof_mark(ctx, g);
 	CU(cudaEventRecord(sl.geom_done, g));

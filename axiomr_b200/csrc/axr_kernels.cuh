@@ -26,6 +26,26 @@
 
 namespace cg = cooperative_groups;
 
+// Variant (off by default, not yet run on a GPU): programmatic dependent launch of the five draw kernels (axr_api.cu launches them
+// with cudaLaunchAttributeProgrammaticStreamSerialization). Every kernel starts with griddepcontrol.wait — all memory operations of
+// the previous kernel on the stream are complete and visible from there on, so the data dependencies are those of plain stream order —
+// followed by griddepcontrol.launch_dependents, which lets the next kernel's CTAs be placed on SMs as this kernel's last wave drains:
+// what it hides is launch latency and the ramp between kernels (~15 us of gaps per C3 frame).
+#ifndef AXR_PDL
+#define AXR_PDL 0
+#endif
+#if AXR_PDL && defined(__CUDA_ARCH__)
+#define AXR_PDL_SYNC()                                              \
+	do {                                                            \
+		asm volatile("griddepcontrol.wait;" ::: "memory");          \
+		asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+	} while (0)
+#else
+#define AXR_PDL_SYNC() \
+	do {               \
+	} while (0)
+#endif
+
 namespace axr {
 
 constexpr int GT = 32;            // GPU tile edge in pixels (a multiple of REF_TILE; keeps rows 128 B wide for the resolve)
@@ -140,6 +160,7 @@ __global__ void __launch_bounds__(256) k_fp32_peak(float* out, float a, float b,
 // saves two memset nodes per draw.
 __global__ void __launch_bounds__(256) k_vertex_xform(const float4* __restrict__ pos, unsigned long long n, m4 mvp, float fW,
                                                       float fH, float4* __restrict__ sv, DrawStatus* status, unsigned* n_records) {
+	AXR_PDL_SYNC();
 	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < sizeof(DrawStatus) / 4) reinterpret_cast<unsigned*>(status)[i] = 0u;
 	if (i == 0) *n_records = 0u;
@@ -282,12 +303,14 @@ constexpr int SETUP_THREADS = AXR_SETUP_THREADS;
 #ifndef AXR_SETUP_PREFETCH
 #define AXR_SETUP_PREFETCH 0
 #endif
+
 constexpr int SETUP_FPT = AXR_SETUP_FPT;  // faces per thread: index loads and 16 B screen-record gathers of all of them are issued back to back
 
 template <bool PEEL>
 __global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(const __grid_constant__ MeshView mesh, const float4* __restrict__ sv,
                                                                 const __grid_constant__ m4 mvp, const __grid_constant__ FrameParams fp,
                                                                 const __grid_constant__ SetupOut o) {
+	AXR_PDL_SYNC();
 	const unsigned long long base = (unsigned long long)blockIdx.x * (SETUP_THREADS * SETUP_FPT) + threadIdx.x;
 #if AXR_SETUP_PREFETCH && defined(__CUDA_ARCH__)
 	// Variant (off by default, not yet timed): pull the index lines of the CTA AXR_SETUP_PREFETCH positions ahead into L2, so that its
@@ -381,6 +404,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(unsigned* tile_coun
                                                              const unsigned* n_records, unsigned rec_cap, DrawStatus* status, DrawStatus* host_status) {
 	__shared__ unsigned s_warp[32];
 	__shared__ unsigned s_carry;
+	AXR_PDL_SYNC();
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	{  // fold the striped counters of k_setup_raster: 256 threads per counter, 16 stripes each, then shuffle + shared reduction
 		__shared__ unsigned long long s_fold[32];
@@ -453,6 +477,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(unsigned* tile_coun
 __global__ void __launch_bounds__(256) k_bin_scatter(const TriRecord* __restrict__ records, const unsigned* __restrict__ n_records,
                                                      FrameParams fp, const unsigned* __restrict__ bin_start, unsigned* cursor,
                                                      unsigned* __restrict__ items, const DrawStatus* status) {
+	AXR_PDL_SYNC();
 	if (status->overflow) return;
 	unsigned n = *n_records;
 	for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
@@ -630,6 +655,7 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
                                                                              const __grid_constant__ TileIn in) {
 	constexpr bool PEEL = Shader::DISCARDS;
 	__shared__ unsigned long long s_keys[GT_PIX];
+	AXR_PDL_SYNC();
 	if (in.status->overflow) return;  // the host grows the bins and re-issues the draw
 	const int tx = blockIdx.x, ty = fp.ty_lo + blockIdx.y;
 	const int tile = ty * fp.ntx + tx;

@@ -20,6 +20,8 @@ VARIANTS = {
     # L2 prefetch of the index stream one / two waves of CTAs ahead (148 SMs x 16 CTAs = 2368 resident CTAs); not yet timed
     "setup_pf2368": ["AXR_SETUP_PREFETCH=2368"],
     "setup_pf4736": ["AXR_SETUP_PREFETCH=4736"],
+    # programmatic dependent launch of the five draw kernels; NOT yet run on a GPU: check parity first (tools/ab.py does)
+    "pdl": ["AXR_PDL=1"],
     # shading phase in two steps (resolve all pixels of a thread, then shade from shared-memory slots): bit-exact on the SIMT
     # interpreter, NOT yet timed — the first thing to A/B in the next round
     "tile_split": ["AXR_TILE_SPLIT=1"],
