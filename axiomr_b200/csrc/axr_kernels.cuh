@@ -742,6 +742,7 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 			return in.row_major ? blk * GT + (tid & 31) : ((blk >> 2) * 4 + ((tid & 31) >> 3)) * GT + (blk & 3) * 8 + (tid & 7);
 		};
 		// 3a. resolve: index loads of all pixels first, then per pixel the gathers that depend on them
+		constexpr int RESOLVE_UNROLL = AXR_TILE_SPLIT == 1 ? PPT : 1;
 		unsigned long long k[PPT];
 		unsigned vi[PPT][3];
 #pragma unroll
@@ -752,7 +753,8 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 				vi[i][0] = __ldg(ip); vi[i][1] = __ldg(ip + 1); vi[i][2] = __ldg(ip + 2);
 			}
 		}
-#pragma unroll
+		// AXR_TILE_SPLIT=1: unrolled (the gathers of all four pixels may be in flight together); =2: one pixel at a time
+#pragma unroll RESOLVE_UNROLL
 		for (int i = 0; i < PPT; ++i) {
 			if (k[i] == KEY_EMPTY) continue;
 			const int p = pixel_of(i);

@@ -26,6 +26,7 @@ VARIANTS = {
     # interpreter, NOT yet timed — the first thing to A/B in the next round
     "tile_split": ["AXR_TILE_SPLIT=1"],
     "tile_split_mb5": ["AXR_TILE_SPLIT=1", "AXR_TILE_MINB=5"],
+    "tile_split2": ["AXR_TILE_SPLIT=2"],  # resolve step one pixel at a time (rolled)
     "tile_split_128x8": ["AXR_TILE_SPLIT=1", "AXR_TILE_THREADS=128", "AXR_TILE_MINB=8"],
 }
 
