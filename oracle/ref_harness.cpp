@@ -15,6 +15,8 @@
 #include "prelude.hpp"
 #include <chrono>
 #include <cstdio>
+#include <map>
+#include <mutex>
 #include <unistd.h>
 
 #define private public
@@ -147,6 +149,31 @@ int axr_ref_camera(const float pos[3], const float target[3], float fov_deg, flo
 // mvp = viewProj * model exactly as reference src/tiled_pipeline.cpp:149 computes it.
 void axr_ref_mat4_mul(const float a[16], const float b[16], float out[16]) { from_mat4(to_mat4(a) * to_mat4(b), out); }
 
+// One AR::TiledPipeline per thread count, kept for the life of the process — like the application, which builds its pipeline once
+// (reference src/renderer.cpp:71) and never destroys it before exit. Destroying one right after a draw can hang: AR::ThreadPool's
+// destructor (reference src/thread_pool.cpp:24-29) sets `stop` and notifies WITHOUT holding the queue mutex, so a worker that has
+// just evaluated the wait predicate and not yet blocked misses the wake-up and the join never returns (observed: three of three
+// fuzz campaigns of ~10^4 short renders each ended in that futex wait). The reference sources are not ours to change, so the
+// harness simply does not run that destructor on the fast path; when a pipeline has to be replaced (arena overflow below) it first
+// gives the idle workers time to park.
+static std::mutex g_pipes_mutex;
+static std::map<int, AR::TiledPipeline*> g_pipes;
+
+static AR::TiledPipeline* pipeline_for(int threads, AR::Camera* cam, AR::Framebuffer* fb, AR::IShader* shader, bool replace) {
+	std::lock_guard<std::mutex> lock(g_pipes_mutex);
+	AR::TiledPipeline*& p = g_pipes[threads];
+	if (p && replace) {
+		std::this_thread::sleep_for(std::chrono::milliseconds(5));
+		delete p;
+		p = nullptr;
+	}
+	if (!p) p = new AR::TiledPipeline((size_t)threads, cam, fb);  // heap: the object embeds a 32 MB arena (include/tiled_pipeline.hpp:103)
+	p->setCamera(cam);
+	p->setFramebuffer(fb);
+	p->setShader(shader);
+	return p;
+}
+
 // Renders `n_faces` triangles through the reference's TiledPipeline in chunks, compositing onto
 // color_inout (BGRA8) / depth_inout (f32) exactly as consecutive Renderer::drawMesh calls would.
 // seconds_out (optional) receives the wall time spent inside drawMesh calls only.
@@ -178,9 +205,8 @@ int axr_ref_render(const axr_ref_scene* sc, const float* vertices, uint64_t n_ve
 		                    : sc->shader_kind == 1 ? (AR::IShader*)&phong
 		                    : sc->shader_kind == 2 ? (AR::IShader*)&pbr : (AR::IShader*)&cutout;
 
-		// heap: the object embeds a 32 MB arena (include/tiled_pipeline.hpp:103)
-		std::unique_ptr<AR::TiledPipeline> pipe(new AR::TiledPipeline((size_t)std::max(1, sc->threads), &cam, &fb));
-		pipe->setShader(shader);
+		const int threads = std::max(1, sc->threads);
+		AR::TiledPipeline* pipe = pipeline_for(threads, &cam, &fb, shader, false);
 
 		AR::Mesh mesh;
 		mesh.m_Vertices.resize(n_verts);
@@ -221,8 +247,7 @@ int axr_ref_render(const axr_ref_scene* sc, const float* vertices, uint64_t n_ve
 				// monotonic arena never gives memory back), half the chunk. Time of the failed attempt is not counted.
 				if (chunk == 1) throw;
 				chunk = std::max<uint64_t>(1, chunk / 2);
-				pipe.reset(new AR::TiledPipeline((size_t)std::max(1, sc->threads), &cam, &fb));
-				pipe->setShader(shader);
+				pipe = pipeline_for(threads, &cam, &fb, shader, true);
 				continue;
 			}
 			secs += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -231,6 +256,8 @@ int axr_ref_render(const axr_ref_scene* sc, const float* vertices, uint64_t n_ve
 		std::memcpy(color_inout, fb.getColorData(), (size_t)W * H * 4);
 		std::memcpy(depth_inout, fb.getDepthData(), (size_t)W * H * sizeof(float));
 		if (seconds_out) *seconds_out = secs;
+		// the cached pipeline must not keep pointers to this call's stack objects
+		pipe->setCamera(nullptr); pipe->setFramebuffer(nullptr); pipe->setShader(nullptr);
 		return 0;
 	} catch (const std::exception& e) {
 		fprintf(stderr, "axr_ref_render: %s\n", e.what());
