@@ -144,3 +144,20 @@ def test_fuzz_under_sanitizers(san, runtime):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "simt", "fuzz.py"), "--seconds", "15", "--seed", "8"], cwd=ROOT,
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "FUZZ OK" in r.stdout, (r.stdout[-2000:], r.stderr[-3000:])
+
+
+def test_obj_ingestion_fuzz_with_cuda_tangent_kernels():
+    """tests/simt/fuzz_obj_loader.py for 10 s: random, irregular OBJ text through axiomr_b200/obj.py with the tangent / bitangent pass
+    run by the CUDA kernels (interpreter build), against the reference's own loader — vertices, order, faces bit for bit."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libaxr_ref.so")):
+        pytest.skip("reference build not available")
+    sys.path.insert(0, os.path.join(ROOT, "tests", "simt"))
+    try:
+        import build as simt_build
+    finally:
+        sys.path.pop(0)
+    lib = simt_build.build()
+    env = dict(os.environ, AXR_B200_LIB=lib, AXR_SIMT_TESTS_ONLY="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "simt", "fuzz_obj_loader.py"), "--seconds", "10", "--seed", "4"], cwd=ROOT,
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "FUZZ OK" in r.stdout and "CUDA tangent kernels" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
