@@ -107,6 +107,22 @@ def test_cpp_dropin_adapter_vs_reference_in_one_process_on_the_interpreter(tmp_p
     assert r.returncode == 0 and "PARITY OK" in r.stdout and "coverage_mismatch=0 depth_bit_mismatch=0" in r.stdout, (r.stdout, r.stderr)
 
 
+def test_stateful_c_abi_fuzz():
+    """tests/simt/fuzz_api.py for 15 s: random sequences of C-ABI calls on long-lived contexts (mesh / texture slot reuse, overlap
+    mode, clears to finite depths, device and host framebuffer draws, misuse that must be refused) against a framebuffer model the
+    oracle advances."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "simt"))
+    try:
+        import build as simt_build
+    finally:
+        sys.path.pop(0)
+    lib = simt_build.build()
+    env = dict(os.environ, AXR_B200_LIB=lib, AXR_SIMT_TESTS_ONLY="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "simt", "fuzz_api.py"), "--seconds", "15", "--seed", "6"], cwd=ROOT,
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "FUZZ OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
 def test_short_fuzz_campaign_against_the_oracle():
     """tests/simt/fuzz.py for 20 s: random soups / meshes / frame sizes / shaders / samplers / composites / bands, every frame
     bit-identical to the oracle. Longer campaigns (4 x 10 min, also on the opt-in variants and under shuffled schedules) were run by
