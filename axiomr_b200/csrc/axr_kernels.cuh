@@ -736,7 +736,14 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 	constexpr int PPT = GT_PIX / TILE_THREADS;
 #if AXR_TILE_SPLIT
 	{
-		__shared__ PixRec s_rec[GT_PIX];  // slot p is written and read by the one thread that owns pixel p: no barrier in between
+		// slot p is written and read by the one thread that owns pixel p: no barrier in between.
+		// AXR_TILE_SPLIT=3: 16 B slots {al, be, ga, z} (24 KB of shared memory per CTA with the keys instead of 40 KB, which leaves L1 more
+		// room); the shade step re-reads the three indices, which the resolve step has just pulled into L1.
+#if AXR_TILE_SPLIT == 3
+		__shared__ float4 s_rec[GT_PIX];
+#else
+		__shared__ PixRec s_rec[GT_PIX];
+#endif
 		const auto pixel_of = [&](int i) {
 			const int blk = i * (TILE_THREADS / 32) + (tid >> 5);
 			return in.row_major ? blk * GT + (tid & 31) : ((blk >> 2) * 4 + ((tid & 31) >> 3)) * GT + (blk & 3) * 8 + (tid & 7);
@@ -778,7 +785,11 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 					if (z < fbz) { r.ord = (unsigned)(k[i] & 0xFFFFFFFFull); r.z = z; }  // mergeTileResults: strict tileZ < fbZ
 				}
 			}
+#if AXR_TILE_SPLIT == 3
+			s_rec[p] = make_float4(r.al, r.be, r.ga, r.ord == REC_DEAD ? INFINITY : r.z);  // +inf: nothing to shade (no drawn z reaches it)
+#else
 			s_rec[p] = r;
+#endif
 		}
 		// 3b. shade
 #pragma unroll 1
@@ -786,7 +797,19 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 			if (k[i] == KEY_EMPTY) continue;
 			const int p = pixel_of(i);
 			const int px = x0 + (p & (GT - 1)), py = y0 + (p / GT);
+#if AXR_TILE_SPLIT == 3
+			const float4 q = s_rec[p];
+			PixRec r;
+			r.al = q.x; r.be = q.y; r.ga = q.z; r.z = q.w;
+			r.ord = (q.w == INFINITY) ? REC_DEAD : (unsigned)(k[i] & 0xFFFFFFFFull);
+			r.i0 = r.i1 = r.i2 = 0u;
+			if (r.ord != REC_DEAD) {
+				const unsigned* ip = mesh.idx + (size_t)(r.ord >> 3) * 3;
+				r.i0 = __ldg(ip); r.i1 = __ldg(ip + 1); r.i2 = __ldg(ip + 2);
+			}
+#else
 			const PixRec r = s_rec[p];
+#endif
 			bool discarded = false;
 			if (r.ord != REC_DEAD) {
 				if (r.z != r.z) discarded = shade_pixel_clipped<Shader, SMP>(mesh, u, fp, in, r.ord, r.i0, r.i1, r.i2, px, py);

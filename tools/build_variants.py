@@ -27,6 +27,7 @@ VARIANTS = {
     "tile_split": ["AXR_TILE_SPLIT=1"],
     "tile_split_mb5": ["AXR_TILE_SPLIT=1", "AXR_TILE_MINB=5"],
     "tile_split2": ["AXR_TILE_SPLIT=2"],  # resolve step one pixel at a time (rolled)
+    "tile_split3": ["AXR_TILE_SPLIT=3"],  # 16 B shared-memory slots (24 KB per CTA instead of 40 KB), indices re-read in the shade step
     "tile_split_128x8": ["AXR_TILE_SPLIT=1", "AXR_TILE_THREADS=128", "AXR_TILE_MINB=8"],
 }
 
