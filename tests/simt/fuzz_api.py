@@ -48,7 +48,7 @@ def main():
         host = Model(W, H)
         host_c = np.ascontiguousarray(host.c.copy())
         host_d = np.ascontiguousarray(host.d.copy())
-        meshes = {}                          # handle -> Scene (as uploaded, with its textures)
+        meshes = {}                          # handle -> [Scene per material group] (as uploaded, with their textures)
         sampler = dev_sampler = None
         for _ in range(int(rng.integers(5, 60))):
             if time.time() > t_end:
@@ -60,7 +60,24 @@ def main():
                 sc.width, sc.height = W, H
                 vp, cam = S.default_camera(W, H, eye=(float(rng.uniform(-1, 1)), float(rng.uniform(-1, 1)), float(rng.uniform(1, 6))))
                 sc.view_proj, sc.cam_pos = vp, cam
-                meshes[dev.load_scene(sc)] = sc
+                if rng.random() < 0.35 and sc.n_faces >= 3:  # several material groups: contiguous face ranges, own textures and Ns each
+                    cuts = sorted(set(int(c) for c in rng.integers(1, sc.n_faces, int(rng.integers(1, 3)))))
+                    bounds = [0] + cuts + [sc.n_faces]
+                    parts = []
+                    for g in range(len(bounds) - 1):
+                        tsz = int(rng.choice([1, 4, 16]))
+                        tex = ([S.cutout_texture(max(tsz, 2), 2), None, None, None, None] if sc.shader == S.SHADER_CUTOUT else
+                               S._pbr_textures(tsz) if sc.shader == S.SHADER_PBR else S._phong_textures(tsz) if sc.shader == S.SHADER_PHONG else [None] * 5)
+                        parts.append(S.Scene(f"{sc.name}_g{g}", W, H, sc.vertices, sc.indices[bounds[g]:bounds[g + 1]], sc.shader, sc.sampler,
+                                             view_proj=vp, cam_pos=cam, light_dir=sc.light_dir, light_color=sc.light_color,
+                                             specular_exponent=float(rng.choice([0.1, 0.2, 0.7])), textures=tex))
+                    h = dev.upload_mesh(sc.vertices, sc.indices, groups=[(bounds[g], bounds[g + 1] - bounds[g]) for g in range(len(parts))])
+                    for g, part in enumerate(parts):
+                        th = [dev.upload_texture(t) if t is not None else api.NO_TEXTURE for t in part.textures]
+                        dev.set_material(h, g, *th, specular_exponent=part.specular_exponent)
+                    meshes[h] = parts
+                else:
+                    meshes[dev.load_scene(sc)] = [sc]
             elif op == 2 and len(meshes) > 1:  # free one; its handle must be refused afterwards
                 h = list(meshes)[int(rng.integers(0, len(meshes)))]
                 dev.free_mesh(h)
@@ -87,29 +104,35 @@ def main():
                 dev.stats()
             elif op in (7, 8, 9) and fb_valid:  # draw onto the device framebuffer
                 h = list(meshes)[int(rng.integers(0, len(meshes)))]
-                sc = meshes[h]
+                parts = meshes[h]
+                sc = parts[0]
                 model = S._f32(S.mat_mul(S.rotate_y(float(rng.uniform(0, 6.3))), S.translate(*(rng.uniform(-1, 1, 3)))))
                 smp = int(rng.integers(0, 2))
                 dev.set_sampler(smp)
                 dev.set_uniforms(sc.view_proj, sc.cam_pos)
                 dev.set_shader(sc.shader, sc.light_dir, sc.light_color)
                 dev.draw_mesh(h, model)
-                sc2 = S.Scene(sc.name, W, H, sc.vertices, sc.indices, sc.shader, smp, model=model, view_proj=sc.view_proj, cam_pos=sc.cam_pos,
-                              light_dir=sc.light_dir, light_color=sc.light_color, specular_exponent=sc.specular_exponent, textures=sc.textures)
-                fb.c, fb.d, _ = po.oracle_render(sc2, threads=2, color=fb.c, depth=fb.d)
+                for part in parts:  # groups in face order: the same per-pixel winner as the single draw
+                    sc2 = S.Scene(part.name, W, H, part.vertices, part.indices, part.shader, smp, model=model, view_proj=part.view_proj,
+                                  cam_pos=part.cam_pos, light_dir=part.light_dir, light_color=part.light_color,
+                                  specular_exponent=part.specular_exponent, textures=part.textures)
+                    fb.c, fb.d, _ = po.oracle_render(sc2, threads=2, color=fb.c, depth=fb.d)
                 n_draws += 1
             elif op == 10:                   # the reference's calling convention: composite onto a host framebuffer, complete on return
                 h = list(meshes)[int(rng.integers(0, len(meshes)))]
-                sc = meshes[h]
+                parts = meshes[h]
+                sc = parts[0]
                 model = S._f32(S.rotate_y(float(rng.uniform(0, 6.3))))
                 smp = int(rng.integers(0, 2))
                 dev.set_sampler(smp)
                 dev.set_uniforms(sc.view_proj, sc.cam_pos)
                 dev.set_shader(sc.shader, sc.light_dir, sc.light_color)
                 dev.draw_mesh_host(h, model, host_c, host_d)
-                sc2 = S.Scene(sc.name, W, H, sc.vertices, sc.indices, sc.shader, smp, model=model, view_proj=sc.view_proj, cam_pos=sc.cam_pos,
-                              light_dir=sc.light_dir, light_color=sc.light_color, specular_exponent=sc.specular_exponent, textures=sc.textures)
-                host.c, host.d, _ = po.oracle_render(sc2, threads=2, color=host.c, depth=host.d)
+                for part in parts:
+                    sc2 = S.Scene(part.name, W, H, part.vertices, part.indices, part.shader, smp, model=model, view_proj=part.view_proj,
+                                  cam_pos=part.cam_pos, light_dir=part.light_dir, light_color=part.light_color,
+                                  specular_exponent=part.specular_exponent, textures=part.textures)
+                    host.c, host.d, _ = po.oracle_render(sc2, threads=2, color=host.c, depth=host.d)
                 m = po.compare(host_c, host_d, host.c, host.d)
                 if m["coverage_mismatch"] or m["depth_bit_mismatch"] or m["color_max_diff"] or not np.array_equal(host_c, host.c):
                     raise SystemExit(f"MISMATCH (host draw) seed={a.seed} ctx #{n_ctx} op #{n_ops}: {m}")
