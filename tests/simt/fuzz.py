@@ -25,6 +25,8 @@ from oracle import pyoracle as po  # noqa: E402  (checker)
 def random_scene(rng: np.random.Generator, i: int) -> S.Scene:
     W = int(rng.choice([33, 64, 97, 128, 161, 200, 256, 320]))
     H = int(rng.choice([17, 48, 63, 96, 100, 144, 200]))
+    if rng.random() < 0.03:  # more than 256 GPU tiles across / down: the packed tile rect of the direct raster path does not apply
+        W, H = (8256, 33) if rng.random() < 0.5 else (33, 8256)
     shader = int(rng.choice([S.SHADER_FLAT, S.SHADER_PHONG, S.SHADER_PBR, S.SHADER_CUTOUT]))
     sampler = int(rng.integers(0, 2))
     kind = int(rng.integers(0, 6))
