@@ -179,3 +179,24 @@ def test_obj_ingestion_fuzz_with_cuda_tangent_kernels():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "simt", "fuzz_obj_loader.py"), "--seconds", "10", "--seed", "4"], cwd=ROOT,
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "FUZZ OK" in r.stdout and "CUDA tangent kernels" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+def test_ab_harness_dry_run(tmp_path):
+    """tools/ab.py (the A/B timing harness the GPU calls use) end to end on the interpreter build: variant discovery, parity spot
+    check, timed loop, per-kernel times, e2e column, JSON records. Times mean nothing here; the point is that the tool still runs."""
+    import json
+    import shutil
+    sys.path.insert(0, os.path.join(ROOT, "tests", "simt"))
+    try:
+        import build as simt_build
+    finally:
+        sys.path.pop(0)
+    shutil.copy(simt_build.build(), tmp_path / "lib_simt.so")
+    env = dict(os.environ, AXR_SIMT_TESTS_ONLY="1", AXR_AB_DIR=str(tmp_path), AXR_AB_OUT=str(tmp_path))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ab.py"), "--workload", "c1", "--steps", "1", "--warmup", "0", "--e2e", "simt"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    rec = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert rec["variant"] == "simt" and "error" not in rec, rec
+    assert rec["parity"] == {"coverage_mismatch": 0, "depth_bit_mismatch": 0, "color_max_diff": 0}, rec
+    assert set(rec["kernel_us"]) == {"vertex_xform", "setup_raster", "scan_tiles", "bin_scatter", "tile_shade"} and set(rec["e2e_ms"]) == {"upload_depth", "zerocopy_depth"}, rec

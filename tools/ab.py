@@ -80,7 +80,7 @@ def main():
     ap.add_argument("variants", nargs="*")
     a = ap.parse_args()
     libs = {"default": os.path.join(ROOT, "axiomr_b200", "libaxr_b200.so")}
-    for p in sorted(glob.glob(os.path.join(ROOT, "variants_tmp", "lib_*.so"))):
+    for p in sorted(glob.glob(os.path.join(os.environ.get("AXR_AB_DIR") or os.path.join(ROOT, "variants_tmp"), "lib_*.so"))):
         libs[os.path.basename(p)[4:-3]] = p
     if a.variants:
         libs = {k: libs[k] for k in a.variants}
@@ -92,8 +92,9 @@ def main():
         from oracle import pyoracle as po  # checker only
         sm = smoke_scene()
         ref = po.oracle_render(sm, threads=os.cpu_count() or 4)[:2]
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    out = open(os.path.join(ROOT, "gpurun_out", f"ab_{a.workload}.jsonl"), "a")
+    out_dir = os.environ.get("AXR_AB_OUT") or os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    out = open(os.path.join(out_dir, f"ab_{a.workload}.jsonl"), "a")
     for name, path in libs.items():
         api._lib = None
         api.LIB_PATH = path
