@@ -90,10 +90,17 @@ def load_library():
         raise ImportError(f"{LIB_PATH} is missing: run `python -m axiomr_b200.build` (nvcc, sm_100a). "
                           "There is no CPU fallback for the raster path.")
     lib = C.CDLL(LIB_PATH)
-    if hasattr(lib, "axr_simt_interpreter_marker") and os.environ.get("AXR_SIMT_TESTS_ONLY") != "1":
-        # tests/simt builds the kernels for a CPU-side SIMT interpreter (kernel unit tests without a GPU); it is not a device
+    if hasattr(lib, "axr_simt_interpreter_marker"):
+        # tests/simt compiles the kernels for a CPU-side SIMT interpreter (kernel unit tests without a GPU). It is not a device and
+        # this loader never accepts it; the test harness binds it itself (tests/simt/use_simt.py).
         raise ImportError(f"{LIB_PATH} is the test-only SIMT interpreter build, not the CUDA library. "
                           "There is no CPU fallback for the raster path.")
+    _lib = _bind(lib)
+    return _lib
+
+
+def _bind(lib):
+    """ctypes signatures of the C ABI (include/axr_b200.h)."""
     vp = C.c_void_p
     lib.axr_create.argtypes = [C.POINTER(_Config), C.POINTER(vp)]
     lib.axr_destroy.argtypes = [vp]
@@ -135,7 +142,6 @@ def load_library():
     lib.axr_measure_fp32_issue.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.axr_set_profiling.argtypes = [vp, C.c_int]
     lib.axr_get_kernel_times.argtypes = [vp, _f32p, C.POINTER(C.c_uint64)]
-    _lib = lib
     return lib
 
 

@@ -19,6 +19,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from axiomr_b200 import api, scenes as S  # noqa: E402
+import use_simt  # noqa: E402
+
+use_simt.install()  # this driver only ever runs against the interpreter build (AXR_B200_LIB)
 from oracle import pyoracle as po  # noqa: E402
 from fuzz import random_scene  # noqa: E402
 

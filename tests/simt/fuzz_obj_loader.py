@@ -92,6 +92,9 @@ def main():
     dev = None
     if os.environ.get("AXR_B200_LIB"):  # tangents / bitangents by the CUDA kernels (axr_generate_tangents) instead of obj.tangents
         from axiomr_b200 import api
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        import use_simt
+        use_simt.install()
         dev = api.Device(16, 16)
     t_end = time.time() + a.seconds
     n = nfaces = 0

@@ -4,8 +4,9 @@ The interpreter compiles the *unmodified* files of axiomr_b200/csrc with g++ (th
 warp collectives are rendezvous points; device allocations carry canaries) and this test then runs the GPU parity tests against
 that build in a subprocess: same scenes, same checks, same oracle. It pins kernel logic — indexing, bins, warp-level code,
 depth peeling, the C ABI's error paths — on every CPU run, and lets a kernel change be checked for bit-exactness before GPU time
-is spent on it. It says nothing about speed and it is not a product path: axiomr_b200.api refuses to load this build unless
-AXR_SIMT_TESTS_ONLY=1 (set here only), and nothing outside tests/ refers to it.
+is spent on it. It says nothing about speed and it is not a product path: axiomr_b200.api.load_library refuses this build,
+always; the harness binds it itself (tests/simt/use_simt.py, installed by tests/conftest.py when AXR_SIMT_TESTS_ONLY=1), and
+nothing outside tests/ refers to it.
 
 AXR_SIMT_FULL=1 also runs the slow cases (bin overflow + regrow, overlapped draws, the dense depth-peeling scenes): ~6 min.
 """
@@ -77,8 +78,7 @@ def test_product_loader_refuses_the_interpreter_build():
     finally:
         sys.path.pop(0)
     lib = simt_build.build()
-    env = {k: v for k, v in os.environ.items() if k != "AXR_SIMT_TESTS_ONLY"}
-    env["AXR_B200_LIB"] = lib
+    env = dict(os.environ, AXR_B200_LIB=lib, AXR_SIMT_TESTS_ONLY="1")  # no environment variable opens the product loader to it
     code = "from axiomr_b200 import api\ntry:\n    api.load_library()\nexcept ImportError as e:\n    print('REFUSED', e)\n"
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
     assert "REFUSED" in r.stdout and "no CPU fallback" in r.stdout, r.stdout + r.stderr
@@ -193,8 +193,11 @@ def test_ab_harness_dry_run(tmp_path):
         sys.path.pop(0)
     shutil.copy(simt_build.build(), tmp_path / "lib_simt.so")
     env = dict(os.environ, AXR_SIMT_TESTS_ONLY="1", AXR_AB_DIR=str(tmp_path), AXR_AB_OUT=str(tmp_path))
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ab.py"), "--workload", "c1", "--steps", "1", "--warmup", "0", "--e2e", "simt"],
-                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    # the tool goes through the product loader, which refuses the interpreter build: run it with the harness's loader installed
+    code = ("import sys, runpy; sys.path.insert(0, 'tests/simt'); import use_simt; use_simt.install(); "
+            "sys.argv = ['ab.py', '--workload', 'c1', '--steps', '1', '--warmup', '0', '--e2e', 'simt']; "
+            "runpy.run_path('tools/ab.py', run_name='__main__')")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
     rec = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
     assert rec["variant"] == "simt" and "error" not in rec, rec
