@@ -151,7 +151,9 @@ int axr_draw_mesh(axr_ctx* ctx, axr_mesh mesh, const float model[16]);
  * pass the depth test are stored by the kernel straight into the host arrays through a zero-copy mapping (pinned memory from
  * axr_host_alloc is mapped already, other memory is page-locked with cudaHostRegister on first use and remembered), so the
  * device -> host traffic is 8 bytes per updated pixel instead of the whole frame. Falls back to upload / draw / resolve when the
- * host memory cannot be mapped. The device-resident framebuffer of the context is left unspecified by this call. */
+ * host memory cannot be mapped. The device-resident framebuffer of the context is left unspecified by this call.
+ * Experiment knob, read once at axr_create: AXR_B200_HOST_DEPTH_ZEROCOPY=1 skips the depth upload and lets the merge test read the
+ * host depth of the visible pixels through the mapping (same results; timing to be established). */
 int axr_draw_mesh_host(axr_ctx* ctx, axr_mesh mesh, const float model[16], uint8_t* bgra, float* depth);
 int axr_sync(axr_ctx* ctx);
 int axr_get_stats(axr_ctx* ctx, axr_stats* out);
