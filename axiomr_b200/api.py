@@ -34,6 +34,7 @@ LIB_PATH = os.environ.get("AXR_B200_LIB") or os.path.join(HERE, "libaxr_b200.so"
 
 SHADER_FLAT, SHADER_PHONG, SHADER_PBR, SHADER_CUTOUT = 0, 1, 2, 3
 SAMPLER_NEAREST, SAMPLER_BILINEAR = 0, 1
+COLOR_EXACT, COLOR_FAST = 0, 1
 NO_TEXTURE = -1
 
 _f32p = C.POINTER(C.c_float)
@@ -74,7 +75,7 @@ ABI_SYMBOLS = [
     "axr_upload_texture", "axr_free_texture", "axr_set_material", "axr_set_uniforms", "axr_set_shader", "axr_set_sampler",
     "axr_clear", "axr_upload_framebuffer", "axr_resolve", "axr_draw_mesh", "axr_sync", "axr_get_stats", "axr_host_alloc",
     "axr_host_free", "axr_stream", "axr_framebuffer_device", "axr_set_output", "axr_framebuffer_ipc", "axr_open_ipc",
-    "axr_close_ipc", "axr_set_profiling", "axr_get_kernel_times", "axr_set_depth_read", "axr_alloc_shared", "axr_free_shared", "axr_set_overlap", "axr_upload_framebuffer_async", "axr_draw_mesh_host", "axr_generate_tangents", "axr_measure_fp32_issue",
+    "axr_close_ipc", "axr_set_profiling", "axr_get_kernel_times", "axr_set_depth_read", "axr_alloc_shared", "axr_free_shared", "axr_set_overlap", "axr_upload_framebuffer_async", "axr_draw_mesh_host", "axr_generate_tangents", "axr_measure_fp32_issue", "axr_set_color_math",
 ]
 STAGES = ["vertex_xform", "setup_raster", "scan_tiles", "bin_scatter", "tile_shade"]
 
@@ -116,6 +117,7 @@ def _bind(lib):
     lib.axr_set_uniforms.argtypes = [vp, _f32p, _f32p, _f32p]
     lib.axr_set_shader.argtypes = [vp, C.c_int, C.POINTER(_ShaderParams), C.c_size_t]
     lib.axr_set_sampler.argtypes = [vp, C.c_int]
+    lib.axr_set_color_math.argtypes = [vp, C.c_int]
     lib.axr_clear.argtypes = [vp, C.c_uint32, C.c_float]
     lib.axr_upload_framebuffer.argtypes = [vp, C.c_void_p, C.c_void_p]
     lib.axr_upload_framebuffer_async.argtypes = [vp, C.c_void_p, C.c_void_p]
@@ -239,6 +241,10 @@ class Device:
 
     def set_sampler(self, sampler: int):
         self._check(self.lib.axr_set_sampler(self.h, sampler))
+
+    def set_color_math(self, mode: int):
+        """COLOR_FAST (default; colour within 1 LSB of the reference) or COLOR_EXACT (the reference's rounding order)."""
+        self._check(self.lib.axr_set_color_math(self.h, mode))
 
     # --- framebuffer
     def clear(self, packed_argb: int = 0xFF000000, depth: float = float("inf")):

@@ -87,6 +87,8 @@ struct axr_ctx {
 		TriRecord* records = nullptr;
 		unsigned rec_cap = 0;
 		unsigned* n_records = nullptr;
+		unsigned* clip_tiles = nullptr;      // tiles with pixels owned by clipped faces (k_tile_shade -> k_shade_clipped)
+		unsigned* n_clip_tiles = nullptr;
 		DrawStatus* d_status = nullptr;
 		DrawStatus* h_status = nullptr;      // pinned + mapped: written by k_scan_tiles
 		DrawStatus* h_status_dev = nullptr;  // device-side alias of h_status
@@ -97,6 +99,7 @@ struct axr_ctx {
 	} slot[2];
 	unsigned draw_counter = 0;
 	cudaStream_t geom_stream = nullptr;
+	bool color_fast = true;  // axr_set_color_math: fused colour arithmetic in the shading stage (default) or the reference's individually rounded one
 	bool overlap = false;  // axr_set_overlap: geometry stages on geom_stream (else everything on the main stream)
 	PendingDraw pending;
 	axr_stats stats{};
@@ -244,23 +247,11 @@ cudaEvent_t prof_mark(axr_ctx* ctx, cudaStream_t s) {
 	return e;
 }
 
-#if AXR_PDL
-// Variant: launch with programmatic stream serialization (see AXR_PDL in axr_kernels.cuh)
-template <typename... KP, typename... A>
-cudaError_t launch_pdl(void (*kernel)(KP...), dim3 grid, dim3 block, cudaStream_t stream, A&&... args) {
-	cudaLaunchConfig_t cfg = {};
-	cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = stream;
-	cudaLaunchAttribute attr[1];
-	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-	attr[0].val.programmaticStreamSerializationAllowed = 1;
-	cfg.attrs = attr; cfg.numAttrs = 1;
-	return cudaLaunchKernelEx(&cfg, kernel, KP(args)...);
-}
-#endif
 
-// One launch over all tile rows of the band, or (axr_draw_mesh_host) one launch per uploaded row chunk, each behind its upload.
-template <typename Shader>
-int launch_tile(axr_ctx* ctx, const MeshView& mv, const Uniforms& u, const TileIn& in) {
+// One launch over all tile rows of the band, or (axr_draw_mesh_host) one launch per uploaded row chunk, each behind its upload;
+// then the small kernel for the pixels owned by clipped faces (k_shade_clipped: a fixed grid over a list that is usually empty).
+template <typename Shader, int SMP, bool FAST>
+int launch_tile_kernels(axr_ctx* ctx, const MeshView& mv, const Uniforms& u, const TileIn& in) {
 	const int chunks = ctx->host_chunks > 0 ? ctx->host_chunks : 1;
 	for (int b = 0; b < chunks; ++b) {
 		FrameParams fp = ctx->fp;
@@ -269,15 +260,16 @@ int launch_tile(axr_ctx* ctx, const MeshView& mv, const Uniforms& u, const TileI
 			cudaStreamWaitEvent(ctx->stream, ctx->up_done[b], 0);
 		}
 		dim3 grid(fp.ntx, fp.ty_hi - fp.ty_lo);
-#if AXR_PDL
-		if (u.sampler) launch_pdl(k_tile_shade<Shader, 1>, grid, dim3(TILE_THREADS), ctx->stream, mv, u, fp, in);
-		else launch_pdl(k_tile_shade<Shader, 0>, grid, dim3(TILE_THREADS), ctx->stream, mv, u, fp, in);
-#else
-		if (u.sampler) k_tile_shade<Shader, 1><<<grid, TILE_THREADS, 0, ctx->stream>>>(mv, u, fp, in);
-		else k_tile_shade<Shader, 0><<<grid, TILE_THREADS, 0, ctx->stream>>>(mv, u, fp, in);
-#endif
+		k_tile_shade<Shader, SMP, FAST><<<grid, TILE_THREADS, 0, ctx->stream>>>(mv, u, fp, in);
 	}
-	return chunks;
+	k_shade_clipped<Shader, SMP><<<CLIP_SHADE_CTAS, CLIP_SHADE_THREADS, 0, ctx->stream>>>(mv, u, ctx->fp, in);
+	return chunks + 1;
+}
+template <typename Shader>
+int launch_tile(axr_ctx* ctx, const MeshView& mv, const Uniforms& u, const TileIn& in) {
+	const bool fast = ctx->color_fast && Shader::HAS_FAST;
+	if (u.sampler) return fast ? launch_tile_kernels<Shader, 1, true>(ctx, mv, u, in) : launch_tile_kernels<Shader, 1, false>(ctx, mv, u, in);
+	return fast ? launch_tile_kernels<Shader, 0, true>(ctx, mv, u, in) : launch_tile_kernels<Shader, 0, false>(ctx, mv, u, in);
 }
 
 // One pass of the five kernels. peel: the pass belongs to a depth-peeled draw (draw_peeled below) — the raster sites reject
@@ -325,13 +317,8 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 	{
 		// at least sizeof(DrawStatus)/4 threads: the kernel also zeroes the draw's counters
 		const unsigned long long threads = m.n_verts > sizeof(DrawStatus) / 4 ? m.n_verts : sizeof(DrawStatus) / 4;
-#if AXR_PDL
-		launch_pdl(k_vertex_xform, dim3((unsigned)((threads + 255) / 256)), dim3(256), g, m.pos, m.n_verts, u.mvp, (float)ctx->fp.W, (float)ctx->fp.H,
-		           m.sv[si], sl.d_status, sl.n_records);
-#else
 		k_vertex_xform<<<(unsigned)((threads + 255) / 256), 256, 0, g>>>(m.pos, m.n_verts, u.mvp, (float)ctx->fp.W, (float)ctx->fp.H, m.sv[si],
-		                                                                sl.d_status, sl.n_records);
-#endif
+		                                                                sl.d_status, sl.n_records, sl.n_clip_tiles);
 		++launches;
 	}
 	prof_mark(ctx, g);
@@ -346,34 +333,19 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 	if (m.n_faces) {
 		const unsigned long long per_cta = (unsigned long long)SETUP_THREADS * SETUP_FPT;
 		const unsigned grid = (unsigned)((m.n_faces + per_cta - 1) / per_cta);
-#if AXR_PDL
-		if (peel) launch_pdl(k_setup_raster<true>, dim3(grid), dim3(SETUP_THREADS), g, mv, (const float4*)m.sv[si], u.mvp, ctx->fp, so);
-		else launch_pdl(k_setup_raster<false>, dim3(grid), dim3(SETUP_THREADS), g, mv, (const float4*)m.sv[si], u.mvp, ctx->fp, so);
-#else
 		if (peel) k_setup_raster<true><<<grid, SETUP_THREADS, 0, g>>>(mv, m.sv[si], u.mvp, ctx->fp, so);
 		else k_setup_raster<false><<<grid, SETUP_THREADS, 0, g>>>(mv, m.sv[si], u.mvp, ctx->fp, so);
-#endif
 		++launches;
 	}
 	prof_mark(ctx, g);
 	prof_mark(ctx, g);
-#if AXR_PDL
-	launch_pdl(k_scan_tiles, dim3(1), dim3(SCAN_THREADS), g, sl.tile_count, sl.bin_start, n_tiles(ctx), sl.ref_cap, (const unsigned*)sl.n_records,
-	           sl.rec_cap, sl.d_status, sl.h_status_dev);
-#else
 	k_scan_tiles<<<1, SCAN_THREADS, 0, g>>>(sl.tile_count, sl.bin_start, n_tiles(ctx), sl.ref_cap, sl.n_records, sl.rec_cap, sl.d_status,
 	                                       sl.h_status_dev);
-#endif
 	++launches;
 	prof_mark(ctx, g);
 	CU(cudaEventRecord(sl.status_event, g));  // the scan kernel has stored the status into mapped host memory
 	prof_mark(ctx, g);
-#if AXR_PDL
-	launch_pdl(k_bin_scatter, dim3(148 * 4), dim3(256), g, (const TriRecord*)sl.records, (const unsigned*)sl.n_records, ctx->fp,
-	           (const unsigned*)sl.bin_start, sl.tile_count, sl.items, (const DrawStatus*)sl.d_status);
-#else
 	k_bin_scatter<<<148 * 4, 256, 0, g>>>(sl.records, sl.n_records, ctx->fp, sl.bin_start, sl.tile_count, sl.items, sl.d_status);
-#endif
 	++launches;
 	prof_mark(ctx, g);
 	CU(cudaEventRecord(sl.geom_done, g));
@@ -388,6 +360,7 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 	in.row_major = ctx->host_chunks > 0 ? 1 : 0;
 	in.floor = peel ? ctx->peel_floor : nullptr;
 	in.again = peel ? ctx->peel_again : nullptr;
+	in.clip_tiles = sl.clip_tiles; in.n_clip_tiles = sl.n_clip_tiles;
 	switch (ctx->shader_kind) {
 	case AXR_SHADER_FLAT: launches += launch_tile<FlatShader>(ctx, mv, u, in); break;
 	case AXR_SHADER_PHONG: launches += launch_tile<PhongShader>(ctx, mv, u, in); break;
@@ -499,6 +472,7 @@ int axr_create(const axr_config* cfg, axr_ctx** out) {
 	c->fp.ty_hi = (y1 + GT - 1) / GT;
 	c->sampler = cfg->sampler ? 1 : 0;
 	if (const char* e = getenv("AXR_B200_HOST_DEPTH_ZEROCOPY")) c->host_depth_zero_copy = e[0] == '1';
+	if (const char* e = getenv("AXR_B200_COLOR_MATH")) c->color_fast = strcmp(e, "exact") != 0;
 	// identity uniforms until axr_set_uniforms
 	memset(c->view_proj, 0, sizeof c->view_proj);
 	memset(c->viewport, 0, sizeof c->viewport);
@@ -539,6 +513,9 @@ int axr_create(const axr_config* cfg, axr_ctx** out) {
 		CUC(cudaMalloc(&sl.tile_count, nt * 4));
 		CUC(cudaMalloc(&sl.bin_start, (nt + 1) * 4));
 		CUC(cudaMalloc(&sl.n_records, 4));
+		CUC(cudaMalloc(&sl.clip_tiles, nt * 4));
+		CUC(cudaMalloc(&sl.n_clip_tiles, 4));
+		CUC(cudaMemsetAsync(sl.n_clip_tiles, 0, 4, c->stream));
 		CUC(cudaMalloc(&sl.d_status, sizeof(DrawStatus)));
 		CUC(cudaHostAlloc(&sl.h_status, 64, cudaHostAllocMapped));
 		CUC(cudaHostGetDevicePointer(&sl.h_status_dev, sl.h_status, 0));
@@ -572,7 +549,7 @@ void axr_destroy(axr_ctx* ctx) {
 	cudaFree(ctx->peel_floor); cudaFree(ctx->peel_again);
 	for (auto& sl : ctx->slot) {
 		cudaFree(sl.vis); cudaFree(sl.tile_touched); cudaFree(sl.tile_count); cudaFree(sl.bin_start); cudaFree(sl.items);
-		cudaFree(sl.records); cudaFree(sl.n_records); cudaFree(sl.d_status);
+		cudaFree(sl.records); cudaFree(sl.n_records); cudaFree(sl.d_status); cudaFree(sl.clip_tiles); cudaFree(sl.n_clip_tiles);
 		if (sl.h_status) cudaFreeHost(sl.h_status);
 		if (sl.status_event) cudaEventDestroy(sl.status_event);
 		if (sl.geom_done) cudaEventDestroy(sl.geom_done);
@@ -769,6 +746,8 @@ int axr_set_material(axr_ctx* ctx, axr_mesh mh, uint32_t group, axr_tex diffuse,
 int axr_set_uniforms(axr_ctx* ctx, const float view_proj[16], const float viewport[16], const float cam_pos[3]) {
 	if (!ctx) return AXR_ERR_INVALID;
 	if (!view_proj || !cam_pos) return fail(ctx, AXR_ERR_INVALID, "axr_set_uniforms: null argument");
+	CU(cudaSetDevice(ctx->device));
+	if (int rc = check_pending(ctx)) return rc;  // a draw that has to be redone is redone with the state it was issued with
 	memcpy(ctx->view_proj, view_proj, sizeof ctx->view_proj);
 	if (viewport) memcpy(ctx->viewport, viewport, sizeof ctx->viewport);
 	memcpy(ctx->cam_pos, cam_pos, sizeof ctx->cam_pos);
@@ -780,6 +759,8 @@ int axr_set_shader(axr_ctx* ctx, int kind, const axr_shader_params* params, size
 	if (kind != AXR_SHADER_FLAT && kind != AXR_SHADER_PHONG && kind != AXR_SHADER_PBR && kind != AXR_SHADER_CUTOUT)
 		return fail(ctx, AXR_ERR_UNSUPPORTED, "axr_set_shader: no device functor for shader kind %d", kind);
 	if (!params || params_size != sizeof(axr_shader_params)) return fail(ctx, AXR_ERR_INVALID, "axr_set_shader: bad params");
+	CU(cudaSetDevice(ctx->device));
+	if (int rc = check_pending(ctx)) return rc;
 	ctx->shader_kind = kind;
 	ctx->shader_params = *params;
 	return AXR_OK;
@@ -788,6 +769,8 @@ int axr_set_shader(axr_ctx* ctx, int kind, const axr_shader_params* params, size
 int axr_set_sampler(axr_ctx* ctx, int sampler) {
 	if (!ctx) return AXR_ERR_INVALID;
 	if (sampler != AXR_SAMPLER_NEAREST && sampler != AXR_SAMPLER_BILINEAR) return fail(ctx, AXR_ERR_INVALID, "axr_set_sampler: %d", sampler);
+	CU(cudaSetDevice(ctx->device));
+	if (int rc = check_pending(ctx)) return rc;
 	ctx->sampler = sampler;
 	return AXR_OK;
 }
@@ -1025,6 +1008,15 @@ int axr_set_overlap(axr_ctx* ctx, int enabled) {
 	rc = sync_all(ctx);
 	if (rc) return rc;
 	ctx->overlap = enabled != 0;
+	return AXR_OK;
+}
+
+int axr_set_color_math(axr_ctx* ctx, int mode) {
+	if (!ctx) return AXR_ERR_INVALID;
+	if (mode != AXR_COLOR_EXACT && mode != AXR_COLOR_FAST) return fail(ctx, AXR_ERR_INVALID, "axr_set_color_math: %d", mode);
+	CU(cudaSetDevice(ctx->device));
+	if (int rc = check_pending(ctx)) return rc;
+	ctx->color_fast = mode == AXR_COLOR_FAST;
 	return AXR_OK;
 }
 

@@ -26,26 +26,6 @@
 
 namespace cg = cooperative_groups;
 
-// Variant (off by default, not yet run on a GPU): programmatic dependent launch of the five draw kernels (axr_api.cu launches them
-// with cudaLaunchAttributeProgrammaticStreamSerialization). Every kernel starts with griddepcontrol.wait — all memory operations of
-// the previous kernel on the stream are complete and visible from there on, so the data dependencies are those of plain stream order —
-// followed by griddepcontrol.launch_dependents, which lets the next kernel's CTAs be placed on SMs as this kernel's last wave drains:
-// what it hides is launch latency and the ramp between kernels (~15 us of gaps per C3 frame).
-#ifndef AXR_PDL
-#define AXR_PDL 0
-#endif
-#if AXR_PDL && defined(__CUDA_ARCH__)
-#define AXR_PDL_SYNC()                                              \
-	do {                                                            \
-		asm volatile("griddepcontrol.wait;" ::: "memory");          \
-		asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
-	} while (0)
-#else
-#define AXR_PDL_SYNC() \
-	do {               \
-	} while (0)
-#endif
-
 namespace axr {
 
 constexpr int GT = 32;            // GPU tile edge in pixels (a multiple of REF_TILE; keeps rows 128 B wide for the resolve)
@@ -159,11 +139,10 @@ __global__ void __launch_bounds__(256) k_fp32_peak(float* out, float a, float b,
 // It also zeroes the draw's device counters (k_setup_raster, the next kernel on the stream, is their first user), which
 // saves two memset nodes per draw.
 __global__ void __launch_bounds__(256) k_vertex_xform(const float4* __restrict__ pos, unsigned long long n, m4 mvp, float fW,
-                                                      float fH, float4* __restrict__ sv, DrawStatus* status, unsigned* n_records) {
-	AXR_PDL_SYNC();
+                                                      float fH, float4* __restrict__ sv, DrawStatus* status, unsigned* n_records, unsigned* n_clip_tiles) {
 	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < sizeof(DrawStatus) / 4) reinterpret_cast<unsigned*>(status)[i] = 0u;
-	if (i == 0) *n_records = 0u;
+	if (i == 0) { *n_records = 0u; *n_clip_tiles = 0u; }
 	if (i >= n) return;
 	float4 p = __ldg(pos + i);
 	v4 c = mul(mvp, V4(p.x, p.y, p.z, 1.0f));
@@ -235,7 +214,7 @@ __device__ __forceinline__ unsigned emit_triangle(const FrameParams& fp, const S
 		}
 		if (any) {
 			const int tx0 = s.X0 / GT, ty0 = s.Y0 / GT, tx1 = (s.X1 - 1) / GT, ty1 = (s.Y1 - 1) / GT;  // box <= 12x12 px: at most 2x2 tiles
-			if (DEFER_TOUCH && fp.ntx <= 256 && fp.nty <= 256)
+			if (DEFER_TOUCH && fp.ntx < 256 && fp.nty < 256)  // strictly: tile (255,255) alone would pack to NO_TOUCH
 				return (unsigned)tx0 | ((unsigned)ty0 << 8) | ((unsigned)tx1 << 16) | ((unsigned)ty1 << 24);
 			for (int ty = ty0; ty <= ty1; ++ty)
 				for (int tx = tx0; tx <= tx1; ++tx) touch_tile(fp, o, tx, ty);
@@ -297,12 +276,6 @@ constexpr int SETUP_THREADS = AXR_SETUP_THREADS;
 #ifndef AXR_TILE_MINB
 #define AXR_TILE_MINB 4
 #endif
-#ifndef AXR_TILE_SPLIT
-#define AXR_TILE_SPLIT 0
-#endif
-#ifndef AXR_SETUP_PREFETCH
-#define AXR_SETUP_PREFETCH 0
-#endif
 
 constexpr int SETUP_FPT = AXR_SETUP_FPT;  // faces per thread: index loads and 16 B screen-record gathers of all of them are issued back to back
 
@@ -310,18 +283,7 @@ template <bool PEEL>
 __global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(const __grid_constant__ MeshView mesh, const float4* __restrict__ sv,
                                                                 const __grid_constant__ m4 mvp, const __grid_constant__ FrameParams fp,
                                                                 const __grid_constant__ SetupOut o) {
-	AXR_PDL_SYNC();
 	const unsigned long long base = (unsigned long long)blockIdx.x * (SETUP_THREADS * SETUP_FPT) + threadIdx.x;
-#if AXR_SETUP_PREFETCH && defined(__CUDA_ARCH__)
-	// Variant (off by default, not yet timed): pull the index lines of the CTA AXR_SETUP_PREFETCH positions ahead into L2, so that its
-	// first-level loads are L2 hits instead of DRAM round trips (one 128 B line per thread, 12 B x SETUP_THREADS x SETUP_FPT per CTA).
-	{
-		const unsigned long long first = ((unsigned long long)blockIdx.x + AXR_SETUP_PREFETCH) * (SETUP_THREADS * SETUP_FPT) * 3ull;  // in u32
-		const unsigned long long line = first + (unsigned long long)threadIdx.x * 32ull;
-		if (threadIdx.x * 32u < SETUP_THREADS * SETUP_FPT * 3u && line < mesh.n_faces * 3ull)
-			asm volatile("prefetch.global.L2 [%0];" ::"l"(mesh.idx + line));
-	}
-#endif
 	unsigned vi[SETUP_FPT][3];
 	float4 s[SETUP_FPT][3];
 #pragma unroll
@@ -404,7 +366,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(unsigned* tile_coun
                                                              const unsigned* n_records, unsigned rec_cap, DrawStatus* status, DrawStatus* host_status) {
 	__shared__ unsigned s_warp[32];
 	__shared__ unsigned s_carry;
-	AXR_PDL_SYNC();
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	{  // fold the striped counters of k_setup_raster: 256 threads per counter, 16 stripes each, then shuffle + shared reduction
 		__shared__ unsigned long long s_fold[32];
@@ -477,7 +438,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(unsigned* tile_coun
 __global__ void __launch_bounds__(256) k_bin_scatter(const TriRecord* __restrict__ records, const unsigned* __restrict__ n_records,
                                                      FrameParams fp, const unsigned* __restrict__ bin_start, unsigned* cursor,
                                                      unsigned* __restrict__ items, const DrawStatus* status) {
-	AXR_PDL_SYNC();
 	if (status->overflow) return;
 	unsigned n = *n_records;
 	for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
@@ -512,61 +472,95 @@ struct TileIn {
 	unsigned long long* floor;      // depth peeling only (Shader::DISCARDS): per-pixel key of the last discarded winner
 	unsigned* again;                // depth peeling only: set when some winner was discarded in this pass
 	int row_major;                  // 1: a warp shades one 32 x 1 pixel row (128 B contiguous stores: output in host memory over PCIe)
+	unsigned* clip_tiles;           // tiles holding pixels owned by a clipped face: shaded by k_shade_clipped, not here
+	unsigned* n_clip_tiles;
 };
 
+// (uint8)(int)(clamp(c, 0, 1) * 255): reference src/tiled_pipeline.cpp:579-582. cvttss2si turns NaN into 0x80000000, whose low byte is 0.
+__device__ __forceinline__ unsigned to_u8(float c) {
+	float v = clampf(c, 0.0f, 1.0f) * 255.0f;  // in [0, 255], or NaN
+#ifdef __CUDA_ARCH__
+	v = (v == v) ? v : 0.0f;
+	return __float_as_uint(__fadd_rz(v, 8388608.0f)) & 0xffu;  // truncation without F2I (see floor_small)
+#else
+	return (unsigned)(unsigned char)cvtt(v);
+#endif
+}
 __device__ __forceinline__ unsigned pack_bgra(v4 c) {
-	// reference src/tiled_pipeline.cpp:579-582 (truncating float->u8 of clamp*255) + the R<->B swizzle of mergeTileResults :1171-1174
-	unsigned r = (unsigned)(unsigned char)cvtt(clampf(c.x, 0.0f, 1.0f) * 255.0f);
-	unsigned g = (unsigned)(unsigned char)cvtt(clampf(c.y, 0.0f, 1.0f) * 255.0f);
-	unsigned b = (unsigned)(unsigned char)cvtt(clampf(c.z, 0.0f, 1.0f) * 255.0f);
-	unsigned a = (unsigned)(unsigned char)cvtt(clampf(c.w, 0.0f, 1.0f) * 255.0f);
-	return b | (g << 8) | (r << 16) | (a << 24);
+	// + the R<->B swizzle of mergeTileResults :1171-1174
+	return to_u8(c.z) | (to_u8(c.y) << 8) | (to_u8(c.x) << 16) | (to_u8(c.w) << 24);
 }
 
+// Material group of a face: groups are ascending face ranges (reference src/mesh.cpp:336-346), group_first has n_groups + 1 entries
 __device__ __forceinline__ const Material& face_material(const MeshView& mesh, unsigned face) {
-	int g = 0;
+	int lo = 0;
 	if (mesh.n_groups > 1) {
-		while (g + 1 < mesh.n_groups && (unsigned long long)face >= mesh.group_first[g + 1]) ++g;
+		int hi = mesh.n_groups;
+		while (hi - lo > 1) {
+			const int mid = (lo + hi) >> 1;
+			if ((unsigned long long)face >= mesh.group_first[mid]) lo = mid; else hi = mid;
+		}
 	}
-	return mesh.materials[g];
+	return mesh.materials[lo];
 }
 
 // Accumulate one vertex's VertexOutput into the interpolated varyings: step k of ((v0*al) + (v1*be)) + v2*ga.
 template <typename Shader>
-__device__ __forceinline__ void accumulate_vertex(const Uniforms& u, int k, float w, v3 pos, v3 n, v3 t, v3 b, float uvx, float uvy, float* var) {
+__device__ __forceinline__ void accumulate_vertex(const Uniforms& u, int k, float w, const VIn& v, float* var) {
 	float o[Shader::NV];
-	Shader::vertex(u, pos, n, t, b, uvx, uvy, o);
+	Shader::vertex(u, v.pos, v.n, v.t, v.b, v.u, v.v, o);
 #pragma unroll
 	for (int i = 0; i < Shader::NV; ++i) var[i] = (k == 0) ? o[i] * w : var[i] + o[i] * w;
 }
 
-// Returns IShader::fragment's discard flag (reference src/tiled_pipeline.cpp:571-577: a discarded fragment leaves depth and colour).
-template <typename Shader, int SMP>
-__device__ __forceinline__ bool finish_pixel(const MeshView& mesh, const Uniforms& u, const TileIn& in, unsigned face, size_t gi, float z,
-                                             const float* var) {
+// IShader::vertex x3 + IShader::fragment for one pixel; returns fragment's discard flag (reference src/tiled_pipeline.cpp:571-577:
+// a discarded fragment leaves depth and colour). FAST: the functor's fused form (colour within 1 LSB instead of bit-equal).
+template <typename Shader, int SMP, bool FAST>
+__device__ __forceinline__ bool run_shader(const MeshView& mesh, const Uniforms& u, const TileIn& in, unsigned face, size_t gi, float z,
+                                           const float w[3], const VIn v[3]) {
 	v4 col;
-	if (Shader::template fragment<SMP>(u, face_material(mesh, face), var, col)) return true;
+	const Material& mat = face_material(mesh, face);
+	if constexpr (FAST && Shader::HAS_FAST) {
+		if (Shader::template shade_fast<SMP>(u, mat, w, v, col)) return true;
+	} else {
+		float var[Shader::NV];
+		accumulate_vertex<Shader>(u, 0, w[0], v[0], var);
+		accumulate_vertex<Shader>(u, 1, w[1], v[1], var);
+		accumulate_vertex<Shader>(u, 2, w[2], v[2], var);
+		if (Shader::template fragment<SMP>(u, mat, var, col)) return true;
+	}
 	in.depth[gi] = z;
 	in.color[gi] = pack_bgra(col);
 	return false;
 }
 
+__device__ __forceinline__ VIn load_vertex(const MeshView& mesh, unsigned i) {
+	const float4 p = __ldg(mesh.pos + i);
+	const float4* ap = reinterpret_cast<const float4*>(mesh.attr + i);
+	const float4 a0 = __ldg(ap), a1 = __ldg(ap + 1), a2 = __ldg(ap + 2);
+	VIn v;
+	v.pos = V3(p.x, p.y, p.z);
+	v.u = a0.x; v.v = a0.y;
+	v.n = V3(a0.z, a0.w, a1.x);
+	v.t = V3(a1.y, a1.z, a1.w);
+	v.b = V3(a2.x, a2.y, a2.z);
+	return v;
+}
+
 // Pixel whose visible triangle comes from a clipped face: re-derive sub-triangle (ordinal & 7) with full attributes
-// (reference src/pipeline.cpp:176-272). Rare; kept out of line so its stack frame does not burden the common path.
+// (reference src/pipeline.cpp:176-272). Rare; runs in its own kernel (k_shade_clipped) so that its 3.5 KB of clip buffers and
+// its call frame stay out of the tile kernel. Always the exact colour arithmetic.
 template <typename Shader, int SMP>
-__device__ __noinline__ bool shade_pixel_clipped(const MeshView& mesh, const Uniforms& u, const FrameParams& fp, const TileIn& in,
-                                                 unsigned ordinal, unsigned i0, unsigned i1, unsigned i2, int px, int py) {
+__device__ bool shade_pixel_clipped(const MeshView& mesh, const Uniforms& u, const FrameParams& fp, const TileIn& in, unsigned ordinal,
+                                    int px, int py) {
 	ClipFull a[MAX_CLIPPED_VERTS], b[MAX_CLIPPED_VERTS];
-	const unsigned vi[3] = {i0, i1, i2};
+	const unsigned* ip = mesh.idx + (size_t)(ordinal >> 3) * 3;
 	for (int k = 0; k < 3; ++k) {
-		float4 p = __ldg(mesh.pos + vi[k]);
-		const VAttr at = mesh.attr[vi[k]];
-		a[k].pos = V3(p.x, p.y, p.z);
-		a[k].clip = mul(u.mvp, V4(p.x, p.y, p.z, 1.0f));
-		a[k].uv[0] = at.uv[0]; a[k].uv[1] = at.uv[1];
-		a[k].n = V3(at.n[0], at.n[1], at.n[2]);
-		a[k].t = V3(at.t[0], at.t[1], at.t[2]);
-		a[k].b = V3(at.b[0], at.b[1], at.b[2]);
+		const VIn v = load_vertex(mesh, __ldg(ip + k));
+		a[k].pos = v.pos;
+		a[k].clip = mul(u.mvp, V4(v.pos.x, v.pos.y, v.pos.z, 1.0f));
+		a[k].uv[0] = v.u; a[k].uv[1] = v.v;
+		a[k].n = v.n; a[k].t = v.t; a[k].b = v.b;
 	}
 	ClipFull* out;
 	const int n = clip_triangle(a, b, &out);
@@ -577,85 +571,46 @@ __device__ __noinline__ bool shade_pixel_clipped(const MeshView& mesh, const Uni
 	for (int k = 0; k < 3; ++k) to_screen(c[k].clip, (float)fp.W, (float)fp.H, sx[k], sy[k], sz[k]);
 	Setup s;
 	if (!setup_triangle(sx[0], sy[0], sx[1], sy[1], sx[2], sy[2], sz[0], sz[1], sz[2], fp.W, fp.y_lo, fp.y_hi, s)) return false;
-	float c0, c1, c2, al, be, ga;
+	float c0, c1, c2, w[3];
 	coverage(s, px, py, c0, c1, c2);
-	const float z = interp_z(s, c0, c1, c2, al, be, ga);
+	const float z = interp_z(s, c0, c1, c2, w[0], w[1], w[2]);
 	const size_t gi = (size_t)py * fp.W + px;
 	if (!(z < (in.read_depth ? in.depth_read[gi] : INFINITY))) return false;
-	float var[Shader::NV];
-	const float w[3] = {al, be, ga};
-	for (int k = 0; k < 3; ++k) accumulate_vertex<Shader>(u, k, w[k], c[k].pos, c[k].n, c[k].t, c[k].b, c[k].uv[0], c[k].uv[1], var);
-	return finish_pixel<Shader, SMP>(mesh, u, in, ordinal >> 3, gi, z, var);
+	VIn v[3];
+	for (int k = 0; k < 3; ++k) { v[k].pos = c[k].pos; v[k].n = c[k].n; v[k].t = c[k].t; v[k].b = c[k].b; v[k].u = c[k].uv[0]; v[k].v = c[k].uv[1]; }
+	return run_shader<Shader, SMP, false>(mesh, u, in, ordinal >> 3, gi, z, w, v);
 }
 
 // One visible pixel: all gathers that depend only on the vertex indices are issued together (screen records, positions,
-// attributes, framebuffer depth), then setup -> barycentrics -> depth test -> IShader::vertex x3 -> IShader::fragment.
-// Returns true when the fragment was discarded by the shader (false also when it lost the depth test).
-template <typename Shader, int SMP>
-__device__ __forceinline__ bool shade_pixel(const MeshView& mesh, const Uniforms& u, const FrameParams& fp, const TileIn& in,
-                                            unsigned ordinal, unsigned i0, unsigned i1, unsigned i2, int px, int py) {
+// attributes, framebuffer depth), then edge setup -> barycentrics -> depth test -> shader.
+enum { PIX_DONE = 0, PIX_DISCARDED = 1, PIX_CLIPPED = 2 };
+template <typename Shader, int SMP, bool FAST>
+__device__ __forceinline__ int shade_pixel(const MeshView& mesh, const Uniforms& u, const FrameParams& fp, const TileIn& in, unsigned ordinal,
+                                           unsigned i0, unsigned i1, unsigned i2, int px, int py) {
 	const size_t gi = (size_t)py * fp.W + px;
 	const float4 s0 = __ldg(in.sv + i0), s1 = __ldg(in.sv + i1), s2 = __ldg(in.sv + i2);
-	const float4 p0 = __ldg(mesh.pos + i0), p1 = __ldg(mesh.pos + i1), p2 = __ldg(mesh.pos + i2);
-	const float4* ap0 = reinterpret_cast<const float4*>(mesh.attr + i0);
-	const float4* ap1 = reinterpret_cast<const float4*>(mesh.attr + i1);
-	const float4* ap2 = reinterpret_cast<const float4*>(mesh.attr + i2);
-	const float4 a00 = __ldg(ap0), a01 = __ldg(ap0 + 1), a02 = __ldg(ap0 + 2);
-	const float4 a10 = __ldg(ap1), a11 = __ldg(ap1 + 1), a12 = __ldg(ap1 + 2);
-	const float4 a20 = __ldg(ap2), a21 = __ldg(ap2 + 1), a22 = __ldg(ap2 + 2);
+	VIn v[3];
+	v[0] = load_vertex(mesh, i0); v[1] = load_vertex(mesh, i1); v[2] = load_vertex(mesh, i2);
 	const float fbz = in.read_depth ? in.depth_read[gi] : INFINITY;
-	if ((__float_as_uint(s0.w) | __float_as_uint(s1.w) | __float_as_uint(s2.w)) & 0x3fu) {
-		return shade_pixel_clipped<Shader, SMP>(mesh, u, fp, in, ordinal, i0, i1, i2, px, py);
-	}
+	if ((__float_as_uint(s0.w) | __float_as_uint(s1.w) | __float_as_uint(s2.w)) & 0x3fu) return PIX_CLIPPED;
+	// the key exists, so the setup kernel's setup_triangle() succeeded for these very inputs: only the edge part is redone
 	Setup s;
-	if (!setup_triangle(s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, fp.W, fp.y_lo, fp.y_hi, s)) return false;
-	float c0, c1, c2, al, be, ga;
+	s.fminx = cvtt(floorf(min3f(s0.x, s1.x, s2.x)));
+	setup_edges(s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, s);
+	float c0, c1, c2, w[3];
 	coverage(s, px, py, c0, c1, c2);
-	const float z = interp_z(s, c0, c1, c2, al, be, ga);
+	const float z = interp_z(s, c0, c1, c2, w[0], w[1], w[2]);
 	// mergeTileResults: strict tileZ < fbZ (reference src/tiled_pipeline.cpp:1148-1156)
-	if (!(z < fbz)) return false;
-	float var[Shader::NV];
-	accumulate_vertex<Shader>(u, 0, al, V3(p0.x, p0.y, p0.z), V3(a00.z, a00.w, a01.x), V3(a01.y, a01.z, a01.w), V3(a02.x, a02.y, a02.z), a00.x, a00.y, var);
-	accumulate_vertex<Shader>(u, 1, be, V3(p1.x, p1.y, p1.z), V3(a10.z, a10.w, a11.x), V3(a11.y, a11.z, a11.w), V3(a12.x, a12.y, a12.z), a10.x, a10.y, var);
-	accumulate_vertex<Shader>(u, 2, ga, V3(p2.x, p2.y, p2.z), V3(a20.z, a20.w, a21.x), V3(a21.y, a21.z, a21.w), V3(a22.x, a22.y, a22.z), a20.x, a20.y, var);
-	return finish_pixel<Shader, SMP>(mesh, u, in, ordinal >> 3, gi, z, var);
+	if (!(z < fbz)) return PIX_DONE;
+	return run_shader<Shader, SMP, FAST>(mesh, u, in, ordinal >> 3, gi, z, w, v) ? PIX_DISCARDED : PIX_DONE;
 }
 
-#if AXR_TILE_SPLIT
-// ---- variant (off by default, not yet timed on a B200): the shading phase in two steps ------------------------------------------
-// The plain path walks, per pixel, the dependent chain key -> indices -> vertex records -> (setup, depth test, vertex shaders)
-// -> texels -> (fragment) -> store, four pixels one after the other per thread: three global-memory latencies in series per pixel
-// at 32 resident warps per SM (the A/B series of round 1 showed the phase to be bound by that chain, not by issue slots or gather
-// wavefronts). Here every thread first RESOLVES all of its pixels — all index loads in flight together, then all screen-record
-// gathers and depth reads, then setup / coverage / z / depth test — and parks {indices, ordinal, barycentrics, z} in its own 32 B
-// shared-memory slots; the SHADE step then starts from those slots, so its chain is attributes -> texels only and it no longer
-// carries the screen records and the setup. Same arithmetic in the same order per pixel: bit-identical frames.
-struct __align__(16) PixRec { unsigned i0, i1, i2, ord; float al, be, ga, z; };
-constexpr unsigned REC_DEAD = 0xFFFFFFFFu;  // no ordinal reaches it (faces < 2^29, see axr_upload_mesh)
-
-template <typename Shader, int SMP>
-__device__ __forceinline__ bool shade_resolved(const MeshView& mesh, const Uniforms& u, const TileIn& in, const PixRec& r, size_t gi) {
-	const float4 p0 = __ldg(mesh.pos + r.i0), p1 = __ldg(mesh.pos + r.i1), p2 = __ldg(mesh.pos + r.i2);
-	const float4* ap0 = reinterpret_cast<const float4*>(mesh.attr + r.i0);
-	const float4* ap1 = reinterpret_cast<const float4*>(mesh.attr + r.i1);
-	const float4* ap2 = reinterpret_cast<const float4*>(mesh.attr + r.i2);
-	const float4 a00 = __ldg(ap0), a01 = __ldg(ap0 + 1), a02 = __ldg(ap0 + 2);
-	const float4 a10 = __ldg(ap1), a11 = __ldg(ap1 + 1), a12 = __ldg(ap1 + 2);
-	const float4 a20 = __ldg(ap2), a21 = __ldg(ap2 + 1), a22 = __ldg(ap2 + 2);
-	float var[Shader::NV];
-	accumulate_vertex<Shader>(u, 0, r.al, V3(p0.x, p0.y, p0.z), V3(a00.z, a00.w, a01.x), V3(a01.y, a01.z, a01.w), V3(a02.x, a02.y, a02.z), a00.x, a00.y, var);
-	accumulate_vertex<Shader>(u, 1, r.be, V3(p1.x, p1.y, p1.z), V3(a10.z, a10.w, a11.x), V3(a11.y, a11.z, a11.w), V3(a12.x, a12.y, a12.z), a10.x, a10.y, var);
-	accumulate_vertex<Shader>(u, 2, r.ga, V3(p2.x, p2.y, p2.z), V3(a20.z, a20.w, a21.x), V3(a21.y, a21.z, a21.w), V3(a22.x, a22.y, a22.z), a20.x, a20.y, var);
-	return finish_pixel<Shader, SMP>(mesh, u, in, r.ord >> 3, gi, r.z, var);
-}
-#endif  // AXR_TILE_SPLIT
-
-template <typename Shader, int SMP>
+template <typename Shader, int SMP, bool FAST>
 __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(const __grid_constant__ MeshView mesh, const __grid_constant__ Uniforms u, const __grid_constant__ FrameParams fp,
                                                                              const __grid_constant__ TileIn in) {
 	constexpr bool PEEL = Shader::DISCARDS;
 	__shared__ unsigned long long s_keys[GT_PIX];
-	AXR_PDL_SYNC();
+	__shared__ unsigned s_clipped;
 	if (in.status->overflow) return;  // the host grows the bins and re-issues the draw
 	const int tx = blockIdx.x, ty = fp.ty_lo + blockIdx.y;
 	const int tile = ty * fp.ntx + tx;
@@ -665,6 +620,7 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 	const unsigned b0 = nrec ? in.bin_start[tile] : 0u, b1 = nrec ? in.bin_start[tile + 1] : 0u;
 	if (!touched && b0 == b1) return;
 	const int tid = threadIdx.x;
+	if (tid == 0) s_clipped = 0u;
 	// 1. stage the tile's visibility keys in shared memory (and hand the global buffer back empty for the next draw)
 	for (int p = tid; p < GT_PIX; p += TILE_THREADS) {
 		int px = x0 + (p & (GT - 1)), py = y0 + (p / GT);
@@ -733,100 +689,9 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 		__syncthreads();
 	}
 	// 3. deferred shading of the visible triangle of each pixel + framebuffer resolve.
-	constexpr int PPT = GT_PIX / TILE_THREADS;
-#if AXR_TILE_SPLIT
-	{
-		// slot p is written and read by the one thread that owns pixel p: no barrier in between.
-		// AXR_TILE_SPLIT=3: 16 B slots {al, be, ga, z} (24 KB of shared memory per CTA with the keys instead of 40 KB, which leaves L1 more
-		// room); the shade step re-reads the three indices, which the resolve step has just pulled into L1.
-#if AXR_TILE_SPLIT == 3
-		__shared__ float4 s_rec[GT_PIX];
-#else
-		__shared__ PixRec s_rec[GT_PIX];
-#endif
-		const auto pixel_of = [&](int i) {
-			const int blk = i * (TILE_THREADS / 32) + (tid >> 5);
-			return in.row_major ? blk * GT + (tid & 31) : ((blk >> 2) * 4 + ((tid & 31) >> 3)) * GT + (blk & 3) * 8 + (tid & 7);
-		};
-		// 3a. resolve: index loads of all pixels first, then per pixel the gathers that depend on them
-		constexpr int RESOLVE_UNROLL = AXR_TILE_SPLIT == 1 ? PPT : 1;
-		unsigned long long k[PPT];
-		unsigned vi[PPT][3];
-#pragma unroll
-		for (int i = 0; i < PPT; ++i) {
-			k[i] = s_keys[pixel_of(i)];
-			if (k[i] != KEY_EMPTY) {
-				const unsigned* ip = mesh.idx + (size_t)((unsigned)(k[i] & 0xFFFFFFFFull) >> 3) * 3;
-				vi[i][0] = __ldg(ip); vi[i][1] = __ldg(ip + 1); vi[i][2] = __ldg(ip + 2);
-			}
-		}
-		// AXR_TILE_SPLIT=1: unrolled (the gathers of all four pixels may be in flight together); =2: one pixel at a time
-#pragma unroll RESOLVE_UNROLL
-		for (int i = 0; i < PPT; ++i) {
-			if (k[i] == KEY_EMPTY) continue;
-			const int p = pixel_of(i);
-			const int px = x0 + (p & (GT - 1)), py = y0 + (p / GT);
-			const size_t gi = (size_t)py * fp.W + px;
-			PixRec r;
-			r.i0 = vi[i][0]; r.i1 = vi[i][1]; r.i2 = vi[i][2];
-			r.ord = REC_DEAD;
-			r.al = r.be = r.ga = r.z = 0.0f;
-			const float4 s0 = __ldg(in.sv + r.i0), s1 = __ldg(in.sv + r.i1), s2 = __ldg(in.sv + r.i2);
-			const float fbz = in.read_depth ? in.depth_read[gi] : INFINITY;
-			if ((__float_as_uint(s0.w) | __float_as_uint(s1.w) | __float_as_uint(s2.w)) & 0x3fu) {
-				r.ord = (unsigned)(k[i] & 0xFFFFFFFFull);
-				r.z = __uint_as_float(0x7fc00000u);  // NaN marks "owned by a clipped face": shade_pixel_clipped redoes everything
-			} else {
-				Setup s;
-				if (setup_triangle(s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, fp.W, fp.y_lo, fp.y_hi, s)) {
-					float c0, c1, c2;
-					coverage(s, px, py, c0, c1, c2);
-					const float z = interp_z(s, c0, c1, c2, r.al, r.be, r.ga);
-					if (z < fbz) { r.ord = (unsigned)(k[i] & 0xFFFFFFFFull); r.z = z; }  // mergeTileResults: strict tileZ < fbZ
-				}
-			}
-#if AXR_TILE_SPLIT == 3
-			s_rec[p] = make_float4(r.al, r.be, r.ga, r.ord == REC_DEAD ? INFINITY : r.z);  // +inf: nothing to shade (no drawn z reaches it)
-#else
-			s_rec[p] = r;
-#endif
-		}
-		// 3b. shade
-#pragma unroll 1
-		for (int i = 0; i < PPT; ++i) {
-			if (k[i] == KEY_EMPTY) continue;
-			const int p = pixel_of(i);
-			const int px = x0 + (p & (GT - 1)), py = y0 + (p / GT);
-#if AXR_TILE_SPLIT == 3
-			const float4 q = s_rec[p];
-			PixRec r;
-			r.al = q.x; r.be = q.y; r.ga = q.z; r.z = q.w;
-			r.ord = (q.w == INFINITY) ? REC_DEAD : (unsigned)(k[i] & 0xFFFFFFFFull);
-			r.i0 = r.i1 = r.i2 = 0u;
-			if (r.ord != REC_DEAD) {
-				const unsigned* ip = mesh.idx + (size_t)(r.ord >> 3) * 3;
-				r.i0 = __ldg(ip); r.i1 = __ldg(ip + 1); r.i2 = __ldg(ip + 2);
-			}
-#else
-			const PixRec r = s_rec[p];
-#endif
-			bool discarded = false;
-			if (r.ord != REC_DEAD) {
-				if (r.z != r.z) discarded = shade_pixel_clipped<Shader, SMP>(mesh, u, fp, in, r.ord, r.i0, r.i1, r.i2, px, py);
-				else discarded = shade_resolved<Shader, SMP>(mesh, u, in, r, (size_t)py * fp.W + px);
-			}
-			if constexpr (PEEL) {
-				in.floor[(size_t)py * fp.W + px] = discarded ? k[i] : KEY_EMPTY;
-				if (discarded && *in.again == 0u) *in.again = 1u;
-			} else {
-				(void)discarded;
-			}
-		}
-		return;
-	}
-#endif
 	//    Not unrolled: one copy of the shading code keeps the kernel inside the instruction cache (unrolled x4 with prefetched
 	//    indices: +12 % time; prefetched indices selected inside a rolled loop: +2 %).
+	constexpr int PPT = GT_PIX / TILE_THREADS;
 #pragma unroll 1
 	for (int i = 0; i < PPT; ++i) {
 		// a warp = one compact 8x4 pixel block (neighbouring pixels share triangle vertices); the stores still fill whole 32 B
@@ -839,14 +704,47 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 		const unsigned* ip = mesh.idx + (size_t)(ord >> 3) * 3;
 		const unsigned i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
 		const int px = x0 + (p & (GT - 1)), py = y0 + (p / GT);
-		const bool discarded = shade_pixel<Shader, SMP>(mesh, u, fp, in, ord, i0, i1, i2, px, py);
+		const int res = shade_pixel<Shader, SMP, FAST>(mesh, u, fp, in, ord, i0, i1, i2, px, py);
+		if (res == PIX_CLIPPED) {
+			// owned by a clipped face: the key goes back to the global buffer and the tile onto the list k_shade_clipped works through
+			in.vis[(size_t)py * fp.W + px] = k;
+			if (atomicExch(&s_clipped, 1u) == 0u) in.clip_tiles[atomicAdd(in.n_clip_tiles, 1u)] = (unsigned)tile;
+			continue;
+		}
 		if constexpr (PEEL) {
 			// discarded: the next pass looks for this pixel's next key above k. Otherwise the pixel is finished (the winner
 			// was drawn, or it lost against the framebuffer and everything behind it would too): no key passes KEY_EMPTY.
-			in.floor[(size_t)py * fp.W + px] = discarded ? k : KEY_EMPTY;
-			if (discarded && *in.again == 0u) *in.again = 1u;
-		} else {
-			(void)discarded;
+			in.floor[(size_t)py * fp.W + px] = (res == PIX_DISCARDED) ? k : KEY_EMPTY;
+			if (res == PIX_DISCARDED && *in.again == 0u) *in.again = 1u;
+		}
+	}
+}
+
+// Second, small kernel of the shading stage: the pixels k_tile_shade left behind because their visible triangle is a sub-triangle
+// of a clipped face. A fixed grid walks the list of tiles that hold such pixels (empty for most frames: the CTAs then exit at once).
+constexpr int CLIP_SHADE_THREADS = 128, CLIP_SHADE_CTAS = 148 * 2;
+template <typename Shader, int SMP>
+__global__ void __launch_bounds__(CLIP_SHADE_THREADS) k_shade_clipped(const __grid_constant__ MeshView mesh, const __grid_constant__ Uniforms u,
+                                                                     const __grid_constant__ FrameParams fp, const __grid_constant__ TileIn in) {
+	constexpr bool PEEL = Shader::DISCARDS;
+	const unsigned n = *in.n_clip_tiles;
+	for (unsigned t = blockIdx.x; t < n; t += gridDim.x) {
+		const int tile = (int)in.clip_tiles[t];
+		const int x0 = (tile % fp.ntx) * GT, y0 = (tile / fp.ntx) * GT;
+		for (int p = threadIdx.x; p < GT_PIX; p += CLIP_SHADE_THREADS) {
+			const int px = x0 + (p & (GT - 1)), py = y0 + (p / GT);
+			if (px >= fp.W || py < fp.y_lo || py >= fp.y_hi) continue;
+			unsigned long long* g = in.vis + (size_t)py * fp.W + px;
+			const unsigned long long k = *g;
+			if (k == KEY_EMPTY) continue;
+			*g = KEY_EMPTY;
+			const bool discarded = shade_pixel_clipped<Shader, SMP>(mesh, u, fp, in, (unsigned)(k & 0xFFFFFFFFull), px, py);
+			if constexpr (PEEL) {
+				in.floor[(size_t)py * fp.W + px] = discarded ? k : KEY_EMPTY;
+				if (discarded && *in.again == 0u) *in.again = 1u;
+			} else {
+				(void)discarded;
+			}
 		}
 	}
 }

@@ -11,6 +11,7 @@
 #include <stdint.h>
 
 #define AXR_HD __host__ __device__ __forceinline__
+#define AXR_D __device__ __forceinline__
 
 namespace axr {
 
@@ -96,5 +97,93 @@ AXR_HD float clampf(float v, float lo, float hi) { return (v < lo) ? lo : ((hi <
 AXR_HD float maxf(float a, float b) { return (a < b) ? b : a; }                                    // std::max
 AXR_HD float min3f(float a, float b, float c) { float m = a; if (b < m) m = b; if (c < m) m = c; return m; }  // std::min({..})
 AXR_HD float max3f(float a, float b, float c) { float m = a; if (m < b) m = b; if (m < c) m = c; return m; }  // std::max({..})
+
+// ------------------------------------------------------------------ exact integer <-> float moves off the conversion pipe
+// I2F / F2I issue at an eighth of the FP32 rate on sm_100; for small non-negative integers the same results come from the
+// FADD pipe: 2^23 + n has n in its low mantissa bits. Bit-identical to the casts they replace (within the stated ranges).
+// byte k of a packed RGBA8 word -> float, exact (replaces I2F.U8)
+AXR_D float u8_to_f32(unsigned word, int k) {
+#ifdef __CUDA_ARCH__
+	return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650u + (unsigned)k)) - 8388608.0f;
+#else
+	return (float)((word >> (8 * k)) & 0xffu);
+#endif
+}
+// floor of 0 <= f < 2^22 as int and as float: (int)f and (float)(int)f without F2I / I2F (f + 2^23 rounded toward zero)
+AXR_D void floor_small(float f, int& i, float& fl) {
+#ifdef __CUDA_ARCH__
+	const float t = __fadd_rz(f, 8388608.0f);
+	i = (int)(__float_as_uint(t) & 0x7fffffu);
+	fl = t - 8388608.0f;
+#else
+	i = (int)f;
+	fl = (float)i;
+#endif
+}
+// non-negative int < 2^23 -> float, exact (replaces I2F)
+AXR_D float small_int_to_f32(int i) {
+#ifdef __CUDA_ARCH__
+	return __uint_as_float(0x4B000000u + (unsigned)i) - 8388608.0f;
+#else
+	return (float)i;
+#endif
+}
+
+// ------------------------------------------------------------------ fast colour math
+// The parity contract (BASELINE.json north_star) is exact coverage and depth, and 8-bit colour within 1 LSB. Everything that
+// feeds coverage, depth or the choice of a texel stays in the individually-rounded forms above; arithmetic that only feeds
+// the colour of a pixel may use these: fused multiply-adds and the SFU approximations (rel. error ~1e-7 .. 2^-22).
+namespace fm {
+AXR_D float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+AXR_D float rsq(float x) {
+#ifdef __CUDA_ARCH__
+	float r;
+	asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+#else
+	return 1.0f / sqrtf(x);
+#endif
+}
+AXR_D float rcp(float x) {
+#ifdef __CUDA_ARCH__
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+#else
+	return 1.0f / x;
+#endif
+}
+// x^y for x >= 0 (or NaN), small |y|: 2^(y log2 x). y == 0 is handled by the callers (powf(x, 0) == 1 for every x).
+AXR_D float pow_pos(float x, float y) {
+#ifdef __CUDA_ARCH__
+	float l, r;
+	asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+	asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * y));
+	return r;
+#else
+	return powf(x, y);
+#endif
+}
+AXR_D float dotf(v3 a, v3 b) { return fma(a.z, b.z, fma(a.y, b.y, a.x * b.x)); }
+AXR_D v3 scale(v3 a, float s) { return V3(a.x * s, a.y * s, a.z * s); }
+AXR_D v3 madd(v3 acc, v3 a, float s) { return V3(fma(a.x, s, acc.x), fma(a.y, s, acc.y), fma(a.z, s, acc.z)); }  // acc + a*s
+AXR_D v3 nrm(v3 a) { return scale(a, rsq(dotf(a, a))); }
+AXR_D v3 crs(v3 x, v3 y) { return V3(fma(x.y, y.z, -(y.y * x.z)), fma(x.z, y.x, -(y.z * x.x)), fma(x.x, y.y, -(y.x * x.y))); }
+// upper-left 3x3 of a column-major mat4 times a direction
+AXR_D v3 mul3(const m4& m, v3 v) {
+	return V3(fma(m.c[2].x, v.z, fma(m.c[1].x, v.y, m.c[0].x * v.x)), fma(m.c[2].y, v.z, fma(m.c[1].y, v.y, m.c[0].y * v.x)),
+	          fma(m.c[2].z, v.z, fma(m.c[1].z, v.y, m.c[0].z * v.x)));
+}
+AXR_D v3 mul3(const m3& m, v3 v) {
+	return V3(fma(m.c[2].x, v.z, fma(m.c[1].x, v.y, m.c[0].x * v.x)), fma(m.c[2].y, v.z, fma(m.c[1].y, v.y, m.c[0].y * v.x)),
+	          fma(m.c[2].z, v.z, fma(m.c[1].z, v.y, m.c[0].z * v.x)));
+}
+// model * (p, 1), xyz only
+AXR_D v3 affine(const m4& m, v3 p) {
+	return V3(fma(m.c[2].x, p.z, fma(m.c[1].x, p.y, fma(m.c[0].x, p.x, m.c[3].x))), fma(m.c[2].y, p.z, fma(m.c[1].y, p.y, fma(m.c[0].y, p.x, m.c[3].y))),
+	          fma(m.c[2].z, p.z, fma(m.c[1].z, p.y, fma(m.c[0].z, p.x, m.c[3].z))));
+}
+AXR_D float lerp(float a, float b, float t) { return fma(t, b - a, a); }
+}  // namespace fm
 
 }  // namespace axr

@@ -173,18 +173,8 @@ __device__ __forceinline__ bool is_backface(float x0, float y0, float x1, float 
 	return signedArea < 0;
 }
 
-// Returns false when the reference would draw nothing for this triangle (empty box or the degenerate-area return).
-__device__ __forceinline__ bool setup_triangle(float x0, float y0, float x1, float y1, float x2, float y2, float z0,
-                                               float z1, float z2, int W, int y_lo, int y_hi, Setup& s) {
-	float minx = min3f(x0, x1, x2), miny = min3f(y0, y1, y2);
-	float maxx = max3f(x0, x1, x2), maxy = max3f(y0, y1, y2);
-	// Union over the reference's 16x16 tiles of [max(tile.startX, floor(minX)), min(tile.endX, ceil(maxX))) (:436-440)
-	s.fminx = cvtt(floorf(minx));
-	s.X0 = max(0, s.fminx);
-	s.X1 = min(W, cvtt(ceilf(maxx)));
-	s.Y0 = max(y_lo, cvtt(floorf(miny)));
-	s.Y1 = min(y_hi, cvtt(ceilf(maxy)));
-	if (s.X0 >= s.X1 || s.Y0 >= s.Y1) return false;
+// Edge equations, area sign flip and 1/area (reference src/tiled_pipeline.cpp:450-486). Returns false on the degenerate-area return.
+__device__ __forceinline__ bool setup_edges(float x0, float y0, float x1, float y1, float x2, float y2, float z0, float z1, float z2, Setup& s) {
 	float e0_c = x1 * y2 - x2 * y1;
 	float e1_c = x2 * y0 - x0 * y2;
 	float e2_c = x0 * y1 - x1 * y0;
@@ -205,6 +195,21 @@ __device__ __forceinline__ bool setup_triangle(float x0, float y0, float x1, flo
 	s.inv_area = 1.0f / area;
 	s.z0 = z0; s.z1 = z1; s.z2 = z2;
 	return true;
+}
+
+// Returns false when the reference would draw nothing for this triangle (empty box or the degenerate-area return).
+__device__ __forceinline__ bool setup_triangle(float x0, float y0, float x1, float y1, float x2, float y2, float z0,
+                                               float z1, float z2, int W, int y_lo, int y_hi, Setup& s) {
+	float minx = min3f(x0, x1, x2), miny = min3f(y0, y1, y2);
+	float maxx = max3f(x0, x1, x2), maxy = max3f(y0, y1, y2);
+	// Union over the reference's 16x16 tiles of [max(tile.startX, floor(minX)), min(tile.endX, ceil(maxX))) (:436-440)
+	s.fminx = cvtt(floorf(minx));
+	s.X0 = max(0, s.fminx);
+	s.X1 = min(W, cvtt(ceilf(maxx)));
+	s.Y0 = max(y_lo, cvtt(floorf(miny)));
+	s.Y1 = min(y_hi, cvtt(ceilf(maxy)));
+	if (s.X0 >= s.X1 || s.Y0 >= s.Y1) return false;
+	return setup_edges(x0, y0, x1, y1, x2, y2, z0, z1, z2, s);
 }
 
 // Coverage of pixel (px,py), px in [X0,X1), as a closed form of the reference's AVX2 loop (:503-537):

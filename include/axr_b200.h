@@ -50,6 +50,14 @@ typedef enum axr_shader_kind { AXR_SHADER_FLAT = 0, AXR_SHADER_PHONG = 1, AXR_SH
  * (BASELINE.json config 3) with no reference counterpart; it is checked against oracle/axr_oracle.c only. */
 typedef enum axr_sampler { AXR_SAMPLER_NEAREST = 0, AXR_SAMPLER_BILINEAR = 1 } axr_sampler;
 
+/* Arithmetic of the shading stage. Coverage, depth and the choice of texels are bit-exact against the reference in both modes.
+ * EXACT: colour arithmetic individually rounded in the reference's order (colour bytes identical to the CPU reference up to its
+ * libm's powf). FAST (default): the same formulas with fused multiply-adds, the SFU reciprocal square root / log2 / exp2 and the
+ * vertex stage applied once per pixel by linearity — 8-bit colour within 1 LSB of the reference (the tolerance BASELINE.json
+ * states), about half the instructions per pixel. The environment variable AXR_B200_COLOR_MATH=exact|fast sets the default
+ * a context is created with. Shaders that discard (AXR_SHADER_CUTOUT) always run EXACT: their colour test decides coverage. */
+typedef enum axr_color_math { AXR_COLOR_EXACT = 0, AXR_COLOR_FAST = 1 } axr_color_math;
+
 /* Public shader parameters (FlatShader::lightDirection; PhongShader/PBRShader::lightDirection, lightColor). */
 typedef struct axr_shader_params {
 	float light_dir[3];
@@ -128,6 +136,7 @@ int axr_set_uniforms(axr_ctx* ctx, const float view_proj[16], const float viewpo
 /* replaces Pipeline::setShader(IShader*) (reference src/pipeline.cpp:22-24); params = the shader's public fields. */
 int axr_set_shader(axr_ctx* ctx, int kind, const axr_shader_params* params, size_t params_size);
 int axr_set_sampler(axr_ctx* ctx, int sampler);
+int axr_set_color_math(axr_ctx* ctx, int mode);  /* axr_color_math */
 
 /* ---- framebuffer: replaces Framebuffer::clearColor / clearDepth (reference src/framebuffer.cpp:26-42) and the raw
  *      getColorData()/getDepthData() accessors (reference include/framebuffer.hpp:45-48). Colour bytes are B,G,R,A;

@@ -175,6 +175,8 @@ template <typename T>
 static inline T atomicCAS(T* p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
 template <typename T>
 static inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
+template <typename T>
+static inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }
 
 // CUDA's global-namespace integer / float min and max
 #define SIMT_MINMAX(T)                                         \
