@@ -25,7 +25,8 @@ thread_local std::string g_create_error;
 struct DeviceMesh {
 	bool live = false;
 	float4* pos = nullptr;
-	VAttr* attr = nullptr;
+	float4* attr = nullptr;   // 48 B per vertex (three float4 planes, or records: AXR_ATTR_PLANES)
+	uint4* idx4 = nullptr;    // AXR_IDX_PAD only
 	unsigned* idx = nullptr;
 	float4* sv[2] = {nullptr, nullptr};  // per-draw screen-space vertex records (16 B each), one per draw slot
 	unsigned long long n_verts = 0, n_faces = 0;
@@ -38,8 +39,8 @@ struct DeviceMesh {
 
 struct DeviceTexture {
 	bool live = false;
-	uchar4* data = nullptr;
-	int w = 0, h = 0;
+	uchar4* data = nullptr;  // tiled order (axr_shaders.cuh: tex_offset_x / tex_offset_y)
+	int w = 0, h = 0, tiles_x = 0;
 };
 
 struct PendingDraw {
@@ -302,9 +303,11 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 	u.sampler = ctx->sampler;
 
 	MeshView mv;
-	mv.pos = m.pos; mv.attr = m.attr; mv.idx = m.idx;
+	mv.pos = m.pos; mv.attr = m.attr; mv.idx = m.idx; mv.idx4 = m.idx4;
+	mv.n_plane = m.n_verts ? m.n_verts : 1;
 	mv.n_verts = m.n_verts; mv.n_faces = m.n_faces;
 	mv.materials = m.d_materials;
+	mv.material0 = m.materials.empty() ? Material{} : m.materials[0];
 	mv.group_first = m.d_group_first;
 	mv.n_groups = (int)m.materials.size();
 
@@ -540,7 +543,7 @@ void axr_destroy(axr_ctx* ctx) {
 	cudaSetDevice(ctx->device);
 	if (ctx->geom_stream) cudaStreamSynchronize(ctx->geom_stream);
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-	for (auto& m : ctx->meshes) if (m.live) { cudaFree(m.pos); cudaFree(m.attr); cudaFree(m.idx); cudaFree(m.sv[0]); cudaFree(m.sv[1]); cudaFree(m.d_materials); cudaFree(m.d_group_first); }
+	for (auto& m : ctx->meshes) if (m.live) { cudaFree(m.pos); cudaFree(m.attr); cudaFree(m.idx); cudaFree(m.idx4); cudaFree(m.sv[0]); cudaFree(m.sv[1]); cudaFree(m.d_materials); cudaFree(m.d_group_first); }
 	for (auto& t : ctx->textures) if (t.live) cudaFree(t.data);
 	for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
 	for (void* p : ctx->shared_allocs) cudaFree(p);
@@ -596,12 +599,12 @@ int axr_upload_mesh(axr_ctx* ctx, const float* vertices, uint64_t n_verts, const
 	const size_t nv = n_verts ? n_verts : 1, nf = n_faces ? n_faces : 1;
 	float* raw = nullptr;
 	auto release = [&]() {  // a failed upload leaves nothing behind
-		cudaFree(m.pos); cudaFree(m.attr); cudaFree(m.sv[0]); cudaFree(m.sv[1]); cudaFree(m.idx); cudaFree(m.d_materials);
+		cudaFree(m.pos); cudaFree(m.attr); cudaFree(m.sv[0]); cudaFree(m.sv[1]); cudaFree(m.idx); cudaFree(m.idx4); cudaFree(m.d_materials);
 		cudaFree(m.d_group_first); cudaFree(raw);
 	};
 #define CUM(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { release(); return fail(ctx, AXR_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
 	CUM(cudaMalloc(&m.pos, nv * sizeof(float4)));
-	CUM(cudaMalloc(&m.attr, nv * sizeof(VAttr)));
+	CUM(cudaMalloc(&m.attr, nv * 3 * sizeof(float4)));
 	CUM(cudaMalloc(&m.sv[0], nv * sizeof(float4)));
 	CUM(cudaMalloc(&m.sv[1], nv * sizeof(float4)));
 	CUM(cudaMalloc(&m.idx, nf * 3 * sizeof(unsigned)));
@@ -610,9 +613,13 @@ int axr_upload_mesh(axr_ctx* ctx, const float* vertices, uint64_t n_verts, const
 	if (n_verts) {
 		CUM(cudaMalloc(&raw, n_verts * 14 * sizeof(float)));
 		CUM(cudaMemcpyAsync(raw, vertices, n_verts * 14 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-		k_split_vertices<<<(unsigned)((n_verts + 255) / 256), 256, 0, ctx->stream>>>(raw, n_verts, m.pos, m.attr);
+		k_split_vertices<<<(unsigned)((n_verts + 255) / 256), 256, 0, ctx->stream>>>(raw, n_verts, nv, m.pos, m.attr);
 	}
 	if (n_faces) CUM(cudaMemcpyAsync(m.idx, indices, n_faces * 3 * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+#if AXR_IDX_PAD
+	CUM(cudaMalloc(&m.idx4, nf * sizeof(uint4)));
+	if (n_faces) k_pad_indices<<<(unsigned)((n_faces + 255) / 256), 256, 0, ctx->stream>>>(m.idx, n_faces, m.idx4);
+#endif
 	CUM(cudaMemcpyAsync(m.d_group_first, m.group_first.data(), (ng + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
 	CUM(cudaStreamSynchronize(ctx->stream));
 #undef CUM
@@ -680,7 +687,7 @@ int axr_free_mesh(axr_ctx* ctx, axr_mesh mh) {
 	rc = sync_all(ctx);
 	if (rc) return rc;
 	DeviceMesh& m = ctx->meshes[mh];
-	cudaFree(m.pos); cudaFree(m.attr); cudaFree(m.idx); cudaFree(m.sv[0]); cudaFree(m.sv[1]); cudaFree(m.d_materials); cudaFree(m.d_group_first);
+	cudaFree(m.pos); cudaFree(m.attr); cudaFree(m.idx); cudaFree(m.idx4); cudaFree(m.sv[0]); cudaFree(m.sv[1]); cudaFree(m.d_materials); cudaFree(m.d_group_first);
 	m = DeviceMesh();
 	return AXR_OK;
 }
@@ -689,11 +696,20 @@ int axr_upload_texture(axr_ctx* ctx, const uint8_t* rgba, int w, int h, axr_tex*
 	if (!ctx) return AXR_ERR_INVALID;
 	if (!rgba || !out || w <= 0 || h <= 0) return fail(ctx, AXR_ERR_INVALID, "axr_upload_texture: bad argument");
 	CU(cudaSetDevice(ctx->device));
+	if ((unsigned long long)w * (unsigned long long)h >= (1ull << 31)) return fail(ctx, AXR_ERR_CAPACITY, "axr_upload_texture: %dx%d exceeds 2^31 texels", w, h);
 	DeviceTexture t;
 	t.w = w; t.h = h;
-	CU(cudaMalloc(&t.data, (size_t)w * h * 4));
-	CU(cudaMemcpyAsync(t.data, rgba, (size_t)w * h * 4, cudaMemcpyHostToDevice, ctx->stream));
-	CU(cudaStreamSynchronize(ctx->stream));
+	t.tiles_x = (w + 7) / 8;
+	const size_t padded = (size_t)t.tiles_x * 8 * (size_t)((h + 3) / 4 * 4);
+	uchar4* linear = nullptr;
+	CU(cudaMalloc(&t.data, padded * 4));
+	if (cudaMalloc(&linear, (size_t)w * h * 4) != cudaSuccess) { cudaFree(t.data); return fail(ctx, AXR_ERR_CUDA, "axr_upload_texture: out of device memory"); }
+	cudaMemsetAsync(t.data, 0, padded * 4, ctx->stream);
+	cudaMemcpyAsync(linear, rgba, (size_t)w * h * 4, cudaMemcpyHostToDevice, ctx->stream);
+	k_tile_texture<<<dim3((w + 31) / 32, (h + 7) / 8), dim3(32, 8), 0, ctx->stream>>>(linear, w, h, t.tiles_x, t.data);
+	const cudaError_t te = cudaStreamSynchronize(ctx->stream);
+	cudaFree(linear);
+	if (te != cudaSuccess) { cudaFree(t.data); return fail(ctx, AXR_ERR_CUDA, "axr_upload_texture: %s", cudaGetErrorString(te)); }
 	t.live = true;
 	size_t slot = ctx->textures.size();
 	for (size_t i = 0; i < ctx->textures.size(); ++i) if (!ctx->textures[i].live) { slot = i; break; }
@@ -716,7 +732,7 @@ int axr_free_texture(axr_ctx* ctx, axr_tex th) {
 		if (m.live)
 			for (auto& mat : m.materials)
 				for (auto& tr : mat.tex)
-					if (tr.data == gone) { tr = TexRef{nullptr, 0, 0}; m.materials_dirty = true; }
+					if (tr.data == gone) { tr = TexRef{nullptr, 0, 0, 0}; m.materials_dirty = true; }
 	return AXR_OK;
 }
 
@@ -729,10 +745,10 @@ int axr_set_material(axr_ctx* ctx, axr_mesh mh, uint32_t group, axr_tex diffuse,
 	const axr_tex th[5] = {diffuse, bump, metallic, roughness, ao};
 	Material mat{};
 	for (int i = 0; i < 5; ++i) {
-		if (th[i] == AXR_NO_TEXTURE) { mat.tex[i] = TexRef{nullptr, 0, 0}; continue; }
+		if (th[i] == AXR_NO_TEXTURE) { mat.tex[i] = TexRef{nullptr, 0, 0, 0}; continue; }
 		if (!valid_tex(ctx, th[i])) return fail(ctx, AXR_ERR_INVALID, "axr_set_material: bad texture handle %d", th[i]);
 		const DeviceTexture& t = ctx->textures[th[i]];
-		mat.tex[i] = TexRef{t.data, t.w, t.h};
+		mat.tex[i] = TexRef{t.data, t.w, t.h, t.tiles_x};
 	}
 	mat.specular_exponent = specular_exponent;
 	CU(cudaSetDevice(ctx->device));

@@ -72,10 +72,13 @@ struct FrameParams {
 
 struct MeshView {
 	const float4* pos;        // x,y,z,1
-	const VAttr* attr;
+	const float4* attr;       // AXR_ATTR_PLANES: three planes of n_plane float4 (uv + n.xy | n.z + t | b + pad); else 48 B VAttr records
+	unsigned long long n_plane;
+	const uint4* idx4;        // AXR_IDX_PAD: (i0, i1, i2, -) per face for the shading stage's single 16 B index gather
 	const unsigned* idx;      // 3 per face
 	unsigned long long n_verts, n_faces;
 	const Material* materials;
+	Material material0;                     // copy of materials[0]: single-group meshes read it from the kernel parameters (constant bank)
 	const unsigned long long* group_first;  // n_groups + 1 entries (ascending), only read when n_groups > 1
 	int n_groups;
 };
@@ -97,19 +100,38 @@ __global__ void k_clear(unsigned* color, float* depth, unsigned packed, float z,
 	size_t stride = (size_t)gridDim.x * blockDim.x;
 	for (; i < n; i += stride) { color[first + i] = packed; depth[first + i] = z; }
 }
-// AoS AR::Vertex (56 B) -> position float4 + 48 B attribute record (done once at mesh upload)
-__global__ void k_split_vertices(const float* __restrict__ raw, unsigned long long n, float4* __restrict__ pos, VAttr* __restrict__ attr) {
+// Layout knobs of the shading stage's gathers (A/B: tools/build_variants.py). A warp-wide 16 B gather is served a quarter-warp at a
+// time, one L1 wavefront per distinct 128 B line; neighbouring pixels reference neighbouring vertices, so float4 PLANES (8 vertices
+// per line) need about half the wavefronts of 48 B records (2.7 vertices per line).
+#ifndef AXR_ATTR_PLANES
+#define AXR_ATTR_PLANES 1
+#endif
+#ifndef AXR_IDX_PAD
+#define AXR_IDX_PAD 0
+#endif
+// AoS AR::Vertex (56 B) -> position float4 + attributes (done once at mesh upload)
+__global__ void k_split_vertices(const float* __restrict__ raw, unsigned long long n, unsigned long long n_plane, float4* __restrict__ pos,
+                                 float4* __restrict__ attr) {
 	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const float* v = raw + i * 14;
 	pos[i] = make_float4(v[0], v[1], v[2], 1.0f);
-	VAttr a;
-	a.uv[0] = v[3]; a.uv[1] = v[4];
-	a.n[0] = v[5]; a.n[1] = v[6]; a.n[2] = v[7];
-	a.t[0] = v[8]; a.t[1] = v[9]; a.t[2] = v[10];
-	a.b[0] = v[11]; a.b[1] = v[12]; a.b[2] = v[13];
-	a.pad = 0.f;
-	attr[i] = a;
+	const float4 a0 = make_float4(v[3], v[4], v[5], v[6]), a1 = make_float4(v[7], v[8], v[9], v[10]), a2 = make_float4(v[11], v[12], v[13], 0.0f);
+#if AXR_ATTR_PLANES
+	attr[i] = a0; attr[n_plane + i] = a1; attr[2 * n_plane + i] = a2;
+#else
+	attr[3 * i] = a0; attr[3 * i + 1] = a1; attr[3 * i + 2] = a2;
+#endif
+}
+// linear RGBA8 rows -> the tiled order the samplers read (axr_upload_texture); the padding texels are never addressed
+__global__ void k_tile_texture(const uchar4* __restrict__ linear, int w, int h, int tiles_x, uchar4* __restrict__ tiled) {
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x < w && y < h) tiled[tex_offset_y(y, w, tiles_x) + tex_offset_x(x)] = linear[(size_t)y * w + x];
+}
+// 12 B index triples -> padded 16 B quads (AXR_IDX_PAD)
+__global__ void k_pad_indices(const unsigned* __restrict__ idx, unsigned long long n_faces, uint4* __restrict__ idx4) {
+	unsigned long long f = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (f < n_faces) idx4[f] = make_uint4(idx[3 * f], idx[3 * f + 1], idx[3 * f + 2], 0u);
 }
 
 // ------------------------------------------------------------------------------------------------ FP32 issue micro-benchmark
@@ -275,6 +297,15 @@ constexpr int SETUP_THREADS = AXR_SETUP_THREADS;
 #endif
 #ifndef AXR_TILE_MINB
 #define AXR_TILE_MINB 4
+#endif
+#ifndef AXR_QUAD_LANES
+#define AXR_QUAD_LANES 1  // C3: 158 -> 154 us
+#endif
+#ifndef AXR_TILE_IDX_STASH
+#define AXR_TILE_IDX_STASH 0
+#endif
+#ifndef AXR_TILE_RECOMPUTE_SV
+#define AXR_TILE_RECOMPUTE_SV 0
 #endif
 
 constexpr int SETUP_FPT = AXR_SETUP_FPT;  // faces per thread: index loads and 16 B screen-record gathers of all of them are issued back to back
@@ -493,8 +524,9 @@ __device__ __forceinline__ unsigned pack_bgra(v4 c) {
 
 // Material group of a face: groups are ascending face ranges (reference src/mesh.cpp:336-346), group_first has n_groups + 1 entries
 __device__ __forceinline__ const Material& face_material(const MeshView& mesh, unsigned face) {
+	if (mesh.n_groups <= 1) return mesh.material0;
 	int lo = 0;
-	if (mesh.n_groups > 1) {
+	{
 		int hi = mesh.n_groups;
 		while (hi - lo > 1) {
 			const int mid = (lo + hi) >> 1;
@@ -536,8 +568,12 @@ __device__ __forceinline__ bool run_shader(const MeshView& mesh, const Uniforms&
 
 __device__ __forceinline__ VIn load_vertex(const MeshView& mesh, unsigned i) {
 	const float4 p = __ldg(mesh.pos + i);
-	const float4* ap = reinterpret_cast<const float4*>(mesh.attr + i);
+#if AXR_ATTR_PLANES
+	const float4 a0 = __ldg(mesh.attr + i), a1 = __ldg(mesh.attr + mesh.n_plane + i), a2 = __ldg(mesh.attr + 2 * mesh.n_plane + i);
+#else
+	const float4* ap = mesh.attr + 3ull * i;
 	const float4 a0 = __ldg(ap), a1 = __ldg(ap + 1), a2 = __ldg(ap + 2);
+#endif
 	VIn v;
 	v.pos = V3(p.x, p.y, p.z);
 	v.u = a0.x; v.v = a0.y;
@@ -588,10 +624,24 @@ template <typename Shader, int SMP, bool FAST>
 __device__ __forceinline__ int shade_pixel(const MeshView& mesh, const Uniforms& u, const FrameParams& fp, const TileIn& in, unsigned ordinal,
                                            unsigned i0, unsigned i1, unsigned i2, int px, int py) {
 	const size_t gi = (size_t)py * fp.W + px;
+#if !AXR_TILE_RECOMPUTE_SV
 	const float4 s0 = __ldg(in.sv + i0), s1 = __ldg(in.sv + i1), s2 = __ldg(in.sv + i2);
+#endif
 	VIn v[3];
 	v[0] = load_vertex(mesh, i0); v[1] = load_vertex(mesh, i1); v[2] = load_vertex(mesh, i2);
 	const float fbz = in.read_depth ? in.depth_read[gi] : INFINITY;
+#if AXR_TILE_RECOMPUTE_SV
+	// variant: the vertex stage's 16 B screen records are recomputed from the positions (same arithmetic, same bits) instead of
+	// gathered: three gathers fewer for ~150 instructions more
+	float4 s0, s1, s2;
+	{
+		const float fW = (float)fp.W, fH = (float)fp.H;
+		const v4 c0 = mul(u.mvp, V4(v[0].pos.x, v[0].pos.y, v[0].pos.z, 1.0f)), c1 = mul(u.mvp, V4(v[1].pos.x, v[1].pos.y, v[1].pos.z, 1.0f)),
+		         c2 = mul(u.mvp, V4(v[2].pos.x, v[2].pos.y, v[2].pos.z, 1.0f));
+		to_screen(c0, fW, fH, s0.x, s0.y, s0.z); to_screen(c1, fW, fH, s1.x, s1.y, s1.z); to_screen(c2, fW, fH, s2.x, s2.y, s2.z);
+		s0.w = __uint_as_float(clip_code(c0)); s1.w = __uint_as_float(clip_code(c1)); s2.w = __uint_as_float(clip_code(c2));
+	}
+#endif
 	if ((__float_as_uint(s0.w) | __float_as_uint(s1.w) | __float_as_uint(s2.w)) & 0x3fu) return PIX_CLIPPED;
 	// the key exists, so the setup kernel's setup_triangle() succeeded for these very inputs: only the edge part is redone
 	Setup s;
@@ -692,17 +742,49 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 	//    Not unrolled: one copy of the shading code keeps the kernel inside the instruction cache (unrolled x4 with prefetched
 	//    indices: +12 % time; prefetched indices selected inside a rolled loop: +2 %).
 	constexpr int PPT = GT_PIX / TILE_THREADS;
+#if AXR_TILE_IDX_STASH
+	// The vertex indices of all of a thread's pixels are fetched up front, together (one global round trip instead of one per pixel),
+	// and parked in shared memory: slot p is written and read by the thread that owns pixel p, so no barrier is needed.
+	__shared__ unsigned s_idx[3][GT_PIX];
+#pragma unroll
+	for (int i = 0; i < PPT; ++i) {
+		const int blk = i * (TILE_THREADS / 32) + (tid >> 5);
+#if AXR_QUAD_LANES
+		const int lane = tid & 31, lx = ((lane >> 3) & 1) * 4 + (lane & 3), ly = (lane >> 4) * 2 + ((lane >> 2) & 1);
+		const int p = in.row_major ? blk * GT + lane : ((blk >> 2) * 4 + ly) * GT + (blk & 3) * 8 + lx;
+#else
+		const int p = in.row_major ? blk * GT + (tid & 31) : ((blk >> 2) * 4 + ((tid & 31) >> 3)) * GT + (blk & 3) * 8 + (tid & 7);
+#endif
+		const unsigned long long k = s_keys[p];
+		if (k == KEY_EMPTY) continue;
+		const unsigned* ip = mesh.idx + (size_t)((unsigned)(k & 0xFFFFFFFFull) >> 3) * 3;
+		s_idx[0][p] = __ldg(ip); s_idx[1][p] = __ldg(ip + 1); s_idx[2][p] = __ldg(ip + 2);
+	}
+#endif
 #pragma unroll 1
 	for (int i = 0; i < PPT; ++i) {
 		// a warp = one compact 8x4 pixel block (neighbouring pixels share triangle vertices); the stores still fill whole 32 B
 		// sectors (8 px x 4 B per row). Measured equal to 32x1 rows on C3.
 		const int blk = i * (TILE_THREADS / 32) + (tid >> 5);
+#if AXR_QUAD_LANES
+		// quarter-warps (the unit a 16 B gather is served in) as 4x2 pixel blocks instead of 8x1 rows
+		const int lane = tid & 31, lx = ((lane >> 3) & 1) * 4 + (lane & 3), ly = (lane >> 4) * 2 + ((lane >> 2) & 1);
+		const int p = in.row_major ? blk * GT + lane : ((blk >> 2) * 4 + ly) * GT + (blk & 3) * 8 + lx;
+#else
 		const int p = in.row_major ? blk * GT + (tid & 31) : ((blk >> 2) * 4 + ((tid & 31) >> 3)) * GT + (blk & 3) * 8 + (tid & 7);
+#endif
 		const unsigned long long k = s_keys[p];
 		if (k == KEY_EMPTY) continue;
 		const unsigned ord = (unsigned)(k & 0xFFFFFFFFull);
+#if AXR_TILE_IDX_STASH
+		const unsigned i0 = s_idx[0][p], i1 = s_idx[1][p], i2 = s_idx[2][p];
+#elif AXR_IDX_PAD
+		const uint4 iq = __ldg(mesh.idx4 + (ord >> 3));
+		const unsigned i0 = iq.x, i1 = iq.y, i2 = iq.z;
+#else
 		const unsigned* ip = mesh.idx + (size_t)(ord >> 3) * 3;
 		const unsigned i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
+#endif
 		const int px = x0 + (p & (GT - 1)), py = y0 + (p / GT);
 		const int res = shade_pixel<Shader, SMP, FAST>(mesh, u, fp, in, ord, i0, i1, i2, px, py);
 		if (res == PIX_CLIPPED) {

@@ -9,7 +9,28 @@
 
 namespace axr {
 
-struct TexRef { const uchar4* data; int w, h; };
+// Texels live in HBM in a tiled order (AXR_TEX_TILED, default): a 128 B line holds an 8 x 4 texel block, each of its four 32 B
+// sectors a 4 x 2 block, so the taps of a bilinear lookup and the lookups of neighbouring pixels fall into few lines / sectors
+// (linear rows: ~15 distinct lines per warp-wide tap gather on the 4K scene; tiled: about half). tiles_x = ceil(w / 8).
+#ifndef AXR_TEX_TILED
+#define AXR_TEX_TILED 1
+#endif
+struct TexRef { const uchar4* data; int w, h; int tiles_x; };
+// element offset of texel (x, y); y counts texture rows (row 0 = image top)
+__host__ __device__ __forceinline__ unsigned tex_offset_x(int x) {
+#if AXR_TEX_TILED
+	return (((unsigned)x >> 3) << 5) | ((unsigned)x & 3u) | (((unsigned)x & 4u) << 1);
+#else
+	return (unsigned)x;
+#endif
+}
+__host__ __device__ __forceinline__ unsigned tex_offset_y(int y, int w, int tiles_x) {
+#if AXR_TEX_TILED
+	return ((unsigned)y >> 2) * ((unsigned)tiles_x << 5) + ((((unsigned)y & 1u) << 2) | (((unsigned)y & 2u) << 3));
+#else
+	return (unsigned)y * (unsigned)w;
+#endif
+}
 
 // Material of one group (reference include/mesh.hpp:20-34): diffuse, bump, metallic, roughness, ao + Ns
 struct Material {
@@ -41,7 +62,7 @@ constexpr int VARY_CUTOUT = 5;  // CutoutShader: [0..1] uv, [2..4] normal
 
 // ------------------------------------------------------------------ Texture::sample (reference include/texture.hpp:12-34)
 __device__ __forceinline__ unsigned texel_word(const TexRef& t, int x, int y) {
-	return __ldg(reinterpret_cast<const unsigned*>(t.data) + ((size_t)y * (size_t)t.w + (size_t)x));
+	return __ldg(reinterpret_cast<const unsigned*>(t.data) + (tex_offset_y(y, t.w, t.tiles_x) + tex_offset_x(x)));
 }
 __device__ __forceinline__ v4 unpack_texel(unsigned p) {
 	const float inv255 = 1.0f / 255.0f;
@@ -103,14 +124,14 @@ __device__ __forceinline__ TexLookup make_lookup(const TexRef& t, float u, float
 	TexLookup l;
 	if (SMP) {
 		const BilinearTaps b = bilinear_taps(t, u, v);
-		const unsigned w = (unsigned)t.w;
-		l.i00 = (unsigned)b.r0 * w + (unsigned)b.x0; l.i10 = (unsigned)b.r0 * w + (unsigned)b.x1;
-		l.i01 = (unsigned)b.r1 * w + (unsigned)b.x0; l.i11 = (unsigned)b.r1 * w + (unsigned)b.x1;
+		const unsigned ox0 = tex_offset_x(b.x0), ox1 = tex_offset_x(b.x1);
+		const unsigned oy0 = tex_offset_y(b.r0, t.w, t.tiles_x), oy1 = tex_offset_y(b.r1, t.w, t.tiles_x);
+		l.i00 = oy0 + ox0; l.i10 = oy0 + ox1; l.i01 = oy1 + ox0; l.i11 = oy1 + ox1;
 		l.tx = b.tx; l.ty = b.ty;
 	} else {
 		int x, y;
 		nearest_xy(t, u, v, x, y);
-		l.i00 = l.i10 = l.i01 = l.i11 = (unsigned)y * (unsigned)t.w + (unsigned)x;
+		l.i00 = l.i10 = l.i01 = l.i11 = tex_offset_y(y, t.w, t.tiles_x) + tex_offset_x(x);
 		l.tx = l.ty = 0.0f;
 	}
 	return l;
