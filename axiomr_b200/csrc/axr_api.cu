@@ -35,6 +35,8 @@ struct DeviceMesh {
 	Material* d_materials = nullptr;
 	unsigned long long* d_group_first = nullptr;
 	bool materials_dirty = true;
+	bool no_bins = false;  // the last draw of this mesh binned nothing: the next one is issued without the two bin kernels (and
+	                       // re-issued with them should a triangle need them after all, OVF_NEED_BINS)
 };
 
 struct DeviceTexture {
@@ -50,6 +52,7 @@ struct PendingDraw {
 	float model[16];
 	int redo_depth = 0;
 	bool peel = false;
+	bool bins = true;  // issued with the bin kernels
 };
 
 }  // namespace
@@ -221,8 +224,14 @@ int check_pending(axr_ctx* ctx) {
 	ctx->stats.small_triangles = st.small_triangles;
 	ctx->stats.binned_triangles = st.binned_triangles;
 	ctx->stats.bin_refs = st.bin_refs;
-	if (!st.overflow) return AXR_OK;
-	if (p.redo_depth >= 2) return fail(ctx, AXR_ERR_CAPACITY, "bin capacity still exceeded after regrowing (records %llu refs %llu)",
+	DeviceMesh& pm = ctx->meshes[p.mesh];
+	if (!st.overflow) {
+		// learn whether this mesh needs the bin kernels at all (BASELINE configs 2-4: every triangle is rasterised by its setup thread)
+		if (!p.peel) pm.no_bins = st.binned_triangles == 0;
+		return AXR_OK;
+	}
+	if (st.overflow & OVF_NEED_BINS) pm.no_bins = false;
+	if (p.redo_depth >= 3) return fail(ctx, AXR_ERR_CAPACITY, "bin capacity still exceeded after regrowing (records %llu refs %llu)",
 	                                   (unsigned long long)st.binned_triangles, (unsigned long long)st.bin_refs);
 	CU(cudaStreamSynchronize(ctx->geom_stream));
 	CU(cudaStreamSynchronize(ctx->stream));
@@ -333,23 +342,32 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 	so.small_dim = tput ? SMALL_DIM_TPUT : SMALL_DIM_LAT;
 	so.small_area = tput ? SMALL_AREA_TPUT : SMALL_AREA_LAT;
 	so.floor = peel ? ctx->peel_floor : nullptr;
-	if (m.n_faces) {
-		const unsigned long long per_cta = (unsigned long long)SETUP_THREADS * SETUP_FPT;
-		const unsigned grid = (unsigned)((m.n_faces + per_cta - 1) / per_cta);
-		if (peel) k_setup_raster<true><<<grid, SETUP_THREADS, 0, g>>>(mv, m.sv[si], u.mvp, ctx->fp, so);
-		else k_setup_raster<false><<<grid, SETUP_THREADS, 0, g>>>(mv, m.sv[si], u.mvp, ctx->fp, so);
+	const bool bins = peel || !m.no_bins;
+	so.bins_enabled = bins ? 1 : 0;
+	{
+		const unsigned grid = (unsigned)((m.n_faces + SETUP_THREADS - 1) / SETUP_THREADS);
+		if (grid) {
+			if (peel) k_setup_raster<true><<<grid, SETUP_THREADS, 0, g>>>(mv, m.sv[si], u.mvp, ctx->fp, so);
+			else k_setup_raster<false><<<grid, SETUP_THREADS, 0, g>>>(mv, m.sv[si], u.mvp, ctx->fp, so);
+			++launches;
+		}
+		k_fold_status<<<1, FOLD_THREADS, 0, g>>>(sl.d_status, sl.h_status_dev, so.bins_enabled);
 		++launches;
 	}
 	prof_mark(ctx, g);
 	prof_mark(ctx, g);
-	k_scan_tiles<<<1, SCAN_THREADS, 0, g>>>(sl.tile_count, sl.bin_start, n_tiles(ctx), sl.ref_cap, sl.n_records, sl.rec_cap, sl.d_status,
-	                                       sl.h_status_dev);
-	++launches;
+	if (bins) {
+		k_scan_tiles<<<1, SCAN_THREADS, 0, g>>>(sl.tile_count, sl.bin_start, n_tiles(ctx), sl.ref_cap, sl.n_records, sl.rec_cap, sl.d_status,
+		                                       sl.h_status_dev);
+		++launches;
+	}
 	prof_mark(ctx, g);
-	CU(cudaEventRecord(sl.status_event, g));  // the scan kernel has stored the status into mapped host memory
+	CU(cudaEventRecord(sl.status_event, g));  // the status has been stored into mapped host memory (by the setup kernel's last CTA / the scan)
 	prof_mark(ctx, g);
-	k_bin_scatter<<<148 * 4, 256, 0, g>>>(sl.records, sl.n_records, ctx->fp, sl.bin_start, sl.tile_count, sl.items, sl.d_status);
-	++launches;
+	if (bins) {
+		k_bin_scatter<<<148 * 4, 256, 0, g>>>(sl.records, sl.n_records, ctx->fp, sl.bin_start, sl.tile_count, sl.items, sl.d_status);
+		++launches;
+	}
 	prof_mark(ctx, g);
 	CU(cudaEventRecord(sl.geom_done, g));
 	// ---- tile raster + shading + resolve on the main stream (the one clears, uploads and resolves are ordered on)
@@ -384,6 +402,7 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 	memcpy(ctx->pending.model, model, sizeof(float) * 16);
 	ctx->pending.redo_depth = 0;
 	ctx->pending.peel = peel;
+	ctx->pending.bins = bins;
 	return AXR_OK;
 }
 

@@ -56,12 +56,12 @@ struct __align__(8) TriRecord {
 struct DrawStatus {
 	unsigned long long clipped_faces, triangles, small_triangles, binned_triangles;  // binned_triangles = records wanted
 	unsigned long long bin_refs;                                                      // refs wanted
-	unsigned overflow;                                                                // 1: records, 2: refs
+	unsigned overflow;                                                                // OVF_* bits
 	unsigned pad;
-	// per-CTA partial counters are spread over STAT_STRIPES slots (no single hot address); k_scan_tiles folds them
-	unsigned stripes[4][4096];
+	// per-warp partial counters are spread over STAT_STRIPES slots (no single hot address); k_fold_status folds them
+	unsigned stripes[4][512];
 };
-constexpr int STAT_STRIPES = 4096;
+constexpr int STAT_STRIPES = 512;
 
 struct FrameParams {
 	int W, H;
@@ -186,8 +186,11 @@ struct SetupOut {
 	unsigned* n_records;         // device counter (also the number wanted when it overflows)
 	DrawStatus* status;
 	int small_dim, small_area;   // direct-raster limits of this draw
+	int bins_enabled;            // 0: the draw was issued without the bin kernels (no triangle of this mesh needed them last time);
+	                             //    a triangle that does need them is counted, k_fold_status raises OVF_NEED_BINS and the host re-issues the draw with bins
 	const unsigned long long* floor;  // depth peeling only (PEEL): per pixel, keys <= floor have been dealt with
 };
+constexpr unsigned OVF_RECORDS = 1u, OVF_REFS = 2u, OVF_NEED_BINS = 4u;
 
 struct EmitCounters { unsigned tris, small, binned; };
 
@@ -199,8 +202,70 @@ __device__ __forceinline__ void touch_tile(const FrameParams& fp, const SetupOut
 	if (*tf == 0u) *tf = 1u;
 }
 
+#ifndef AXR_SETUP_LOOP
+#define AXR_SETUP_LOOP 0  // 0: closed-form coverage() per pixel (C3: 170 us); 1: row terms hoisted (spills at 32 registers, row updates diverge: 209 us)
+#endif
+
+// Exact coverage + visibility keys of a triangle whose pixel box is small (at most 12 x 12, 64 px), by the thread that set it up.
+// Returns true when a key was written.
+template <bool PEEL>
+__device__ __forceinline__ bool raster_small(const FrameParams& fp, const SetupOut& o, const Setup& s, unsigned ordinal) {
+	bool any = false;
+	auto hit = [&](int px, int py, float c0, float c1, float c2) {
+		float al, be, ga;
+		const float z = interp_z(s, c0, c1, c2, al, be, ga);
+		if (!z_draws(z)) return;
+		const unsigned long long key = make_key(z, ordinal);
+		unsigned long long* slot = o.vis + ((unsigned)py * (unsigned)fp.W + (unsigned)px);
+		if constexpr (PEEL) {
+			if (!(key > o.floor[(unsigned)py * (unsigned)fp.W + (unsigned)px])) return;
+		}
+		atomicMin(slot, key);  // result unused -> RED.MIN.64, fire and forget
+		any = true;
+	};
+	const int bw = s.X1 - s.X0, bh = s.Y1 - s.Y0;
+	int px = s.X0, py = s.Y0;
+#if AXR_SETUP_LOOP == 0
+	// One counter over the whole pixel box with the closed-form coverage() per pixel
+	for (int i = bw * bh; i > 0; --i) {
+		float c0, c1, c2;
+		if (coverage(s, px, py, c0, c1, c2)) hit(px, py, c0, c1, c2);
+		if (++px == s.X1) { px = s.X0; ++py; }
+	}
+#else
+	// The same arithmetic with the terms that are constant along a row kept in registers. The box is at most 12 px wide, so it lies
+	// in at most two of the reference's 16-px tiles: in the first one the reference's row starts at startX = max(tile.startX,
+	// floor(minX)) == X0 (X0 = max(0, floor(minX)) is inside that tile), in the second one at its left edge B. coverage() in
+	// axr_raster.cuh is the specification; every + and * below is the one it performs for the same pixel.
+	const int B = (s.X0 & ~(REF_TILE - 1)) + REF_TILE;
+	const float sxA = small_int_to_f32(s.X0) + 0.5f, sxB = small_int_to_f32(B) + 0.5f;
+	float rA0, rA1, rA2, rB0, rB1, rB2;
+	auto row = [&]() {
+		const float pyc = small_int_to_f32(py) + 0.5f;
+		const float p0 = s.b0 * pyc, p1 = s.b1 * pyc, p2 = s.b2 * pyc;
+		rA0 = s.a0 * sxA + p0 + s.c0; rA1 = s.a1 * sxA + p1 + s.c1; rA2 = s.a2 * sxA + p2 + s.c2;
+		rB0 = s.a0 * sxB + p0 + s.c0; rB1 = s.a1 * sxB + p1 + s.c1; rB2 = s.a2 * sxB + p2 + s.c2;
+	};
+	row();
+	for (int i = bw * bh; i > 0; --i) {
+		const bool inB = px >= B;
+		int d = px - (inB ? B : s.X0);
+		float c0 = inB ? rB0 : rA0, c1 = inB ? rB1 : rA1, c2 = inB ? rB2 : rA2;
+		if (d >= 8) {
+			c0 = c0 + s.a0 * 8.0f; c1 = c1 + s.a1 * 8.0f; c2 = c2 + s.a2 * 8.0f;
+			d -= 8;
+		}
+		const float fi = small_int_to_f32(d);
+		c0 = c0 + s.a0 * fi; c1 = c1 + s.a1 * fi; c2 = c2 + s.a2 * fi;
+		if (c0 >= 0.f && c1 >= 0.f && c2 >= 0.f) hit(px, py, c0, c1, c2);
+		if (++px == s.X1) { px = s.X0; ++py; row(); }
+	}
+#endif
+	return any;
+}
+
 // DEFER_TOUCH: the caller flags the tiles later (warp-aggregated); the return value is the tile rect of the pixel box packed as
-// tx0 | ty0<<8 | tx1<<16 | ty1<<24 in units of GPU tiles (frames up to 8192 px), or NO_TOUCH when there is nothing to flag.
+// tx0 | ty0<<8 | tx1<<16 | ty1<<24 in units of GPU tiles (frames up to 8160 px), or NO_TOUCH when there is nothing to flag.
 constexpr unsigned NO_TOUCH = 0xFFFFFFFFu;
 template <bool PEEL, bool DEFER_TOUCH>
 __device__ __forceinline__ unsigned emit_triangle(const FrameParams& fp, const SetupOut& o, float x0, float y0, float x1, float y1,
@@ -211,30 +276,7 @@ __device__ __forceinline__ unsigned emit_triangle(const FrameParams& fp, const S
 	const int bw = s.X1 - s.X0, bh = s.Y1 - s.Y0;
 	if (bw <= o.small_dim && bh <= o.small_dim && bw * bh <= o.small_area) {
 		cnt.small++;
-		bool any = false;
-		auto hit = [&](int px, int py, float c0, float c1, float c2) {
-			float al, be, ga;
-			const float z = interp_z(s, c0, c1, c2, al, be, ga);
-			if (!z_draws(z)) return;
-			const unsigned long long key = make_key(z, ordinal);
-			if constexpr (PEEL) {
-				if (!(key > o.floor[(size_t)py * fp.W + px])) return;
-			}
-			atomicMin(o.vis + (size_t)py * fp.W + px, key);  // result unused -> RED.MIN.64, fire and forget
-			any = true;
-		};
-		// One counter over the whole pixel box (<= 64 px) with the closed-form coverage() per pixel, instead of rows x 16-px
-		// segments x pixels with hoisted row terms: the hoisted form keeps ~8 more values live, which at this kernel's register
-		// budget meant spills inside the loop (68 B), and its nested trip counts diverge between lanes. C3: 198 -> 175 us.
-		{
-			int px = s.X0, py = s.Y0;
-			for (int i = bw * bh; i > 0; --i) {
-				float c0, c1, c2;
-				if (coverage(s, px, py, c0, c1, c2)) hit(px, py, c0, c1, c2);
-				if (++px == s.X1) { px = s.X0; ++py; }
-			}
-		}
-		if (any) {
+		if (raster_small<PEEL>(fp, o, s, ordinal)) {
 			const int tx0 = s.X0 / GT, ty0 = s.Y0 / GT, tx1 = (s.X1 - 1) / GT, ty1 = (s.Y1 - 1) / GT;  // box <= 12x12 px: at most 2x2 tiles
 			if (DEFER_TOUCH && fp.ntx < 256 && fp.nty < 256)  // strictly: tile (255,255) alone would pack to NO_TOUCH
 				return (unsigned)tx0 | ((unsigned)ty0 << 8) | ((unsigned)tx1 << 16) | ((unsigned)ty1 << 24);
@@ -244,6 +286,7 @@ __device__ __forceinline__ unsigned emit_triangle(const FrameParams& fp, const S
 		return NO_TOUCH;
 	}
 	cnt.binned++;
+	if (!o.bins_enabled) return NO_TOUCH;  // counted: k_fold_status raises OVF_NEED_BINS and the draw is re-issued with the bin kernels
 	// warp-aggregated append of the setup record
 	cg::coalesced_group g = cg::coalesced_threads();
 	unsigned base = 0;
@@ -289,11 +332,8 @@ __device__ __noinline__ unsigned setup_clipped_face(const FrameParams& fp, const
 #define AXR_SETUP_THREADS 128
 #endif
 constexpr int SETUP_THREADS = AXR_SETUP_THREADS;
-#ifndef AXR_SETUP_FPT
-#define AXR_SETUP_FPT 1
-#endif
 #ifndef AXR_SETUP_MINB
-#define AXR_SETUP_MINB 16  // 32 registers, 64 resident warps: the kernel is latency-bound (C3: 12 -> 175 us, 14 / 16 -> 169 us, 10 -> 186 us)
+#define AXR_SETUP_MINB 16  // 32 registers, 64 resident warps
 #endif
 #ifndef AXR_TILE_MINB
 #define AXR_TILE_MINB 4
@@ -308,119 +348,111 @@ constexpr int SETUP_THREADS = AXR_SETUP_THREADS;
 #define AXR_TILE_RECOMPUTE_SV 0
 #endif
 
-constexpr int SETUP_FPT = AXR_SETUP_FPT;  // faces per thread: index loads and 16 B screen-record gathers of all of them are issued back to back
+// The draw's counters go to the host through mapped pinned memory (plain stores over PCIe): a cudaMemcpyAsync between the
+// kernels would put a copy-engine operation, i.e. a bubble of ~10 us, into the middle of every draw.
+// No system fence: the host reads after synchronising on an event recorded behind the publishing kernel.
+__device__ __forceinline__ void publish_status(const DrawStatus* d, DrawStatus* h, int word) {
+	reinterpret_cast<volatile unsigned long long*>(h)[word] = reinterpret_cast<const volatile unsigned long long*>(d)[word];
+}
 
 template <bool PEEL>
 __global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(const __grid_constant__ MeshView mesh, const float4* __restrict__ sv,
                                                                 const __grid_constant__ m4 mvp, const __grid_constant__ FrameParams fp,
                                                                 const __grid_constant__ SetupOut o) {
-	const unsigned long long base = (unsigned long long)blockIdx.x * (SETUP_THREADS * SETUP_FPT) + threadIdx.x;
-	unsigned vi[SETUP_FPT][3];
-	float4 s[SETUP_FPT][3];
-#pragma unroll
-	for (int k = 0; k < SETUP_FPT; ++k) {
-		const unsigned long long f = base + (unsigned long long)k * SETUP_THREADS;
-		if (f < mesh.n_faces) {
-			vi[k][0] = __ldg(mesh.idx + f * 3); vi[k][1] = __ldg(mesh.idx + f * 3 + 1); vi[k][2] = __ldg(mesh.idx + f * 3 + 2);
-		}
-	}
-#pragma unroll
-	for (int k = 0; k < SETUP_FPT; ++k) {
-		const unsigned long long f = base + (unsigned long long)k * SETUP_THREADS;
-		if (f < mesh.n_faces) { s[k][0] = __ldg(sv + vi[k][0]); s[k][1] = __ldg(sv + vi[k][1]); s[k][2] = __ldg(sv + vi[k][2]); }
-	}
+	const unsigned f = blockIdx.x * SETUP_THREADS + threadIdx.x;  // faces < 2^29 (axr_upload_mesh): 32-bit index arithmetic throughout
+	const unsigned lane = threadIdx.x & 31u;
 	EmitCounters cnt = {0, 0, 0};
 	unsigned clipped = 0;
-	// One copy of the cull / setup / raster code, visited SETUP_FPT times (the loads above stay batched; the loop is NOT unrolled
-	// so that the register footprint, hence occupancy, is that of a single face).
-#pragma unroll 1
-	for (int k = 0; k < SETUP_FPT; ++k) {
-		const unsigned long long f = base + (unsigned long long)k * SETUP_THREADS;
-		float4 s0 = s[0][0], s1 = s[0][1], s2 = s[0][2];
-		unsigned i0 = vi[0][0], i1 = vi[0][1], i2 = vi[0][2];
-#pragma unroll
-		for (int j = 1; j < SETUP_FPT; ++j)
-			if (k == j) { s0 = s[j][0]; s1 = s[j][1]; s2 = s[j][2]; i0 = vi[j][0]; i1 = vi[j][1]; i2 = vi[j][2]; }
-		unsigned touched = NO_TOUCH;
-		if (f < mesh.n_faces) {
-			const unsigned k0 = __float_as_uint(s0.w), k1 = __float_as_uint(s1.w), k2 = __float_as_uint(s2.w);
-			if (((k0 | k1 | k2) & 0x3fu) == 0) {
-				// every vertex inside every plane: clipTriangle returns the triangle unchanged (reference src/pipeline.cpp:322-325)
-				if (!is_backface(s0.x, s0.y, s1.x, s1.y, s2.x, s2.y))
-					touched = emit_triangle<PEEL, true>(fp, o, s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, (unsigned)f * 8u, cnt);
-			} else if ((k0 & k1 & k2) >> 8) {
-				// all three vertices safely outside one plane: clipTriangle returns nothing (see clip_code_safe_out)
-			} else {
-				clipped++;
-				const unsigned c = setup_clipped_face<PEEL>(fp, o, mvp, __ldg(mesh.pos + i0), __ldg(mesh.pos + i1), __ldg(mesh.pos + i2), (unsigned)f);
-				cnt.tris += c & 255u; cnt.small += (c >> 8) & 255u; cnt.binned += c >> 16;
-			}
+	unsigned touched = NO_TOUCH;
+	if (f < (unsigned)mesh.n_faces) {
+		const unsigned* ip = mesh.idx + 3u * f;
+		const unsigned i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
+		const float4 s0 = __ldg(sv + i0), s1 = __ldg(sv + i1), s2 = __ldg(sv + i2);
+		const unsigned k0 = __float_as_uint(s0.w), k1 = __float_as_uint(s1.w), k2 = __float_as_uint(s2.w);
+		if (((k0 | k1 | k2) & 0x3fu) == 0) {
+			// every vertex inside every plane: clipTriangle returns the triangle unchanged (reference src/pipeline.cpp:322-325)
+			if (!is_backface(s0.x, s0.y, s1.x, s1.y, s2.x, s2.y))
+				touched = emit_triangle<PEEL, true>(fp, o, s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, f * 8u, cnt);
+		} else if ((k0 & k1 & k2) >> 8) {
+			// all three vertices safely outside one plane: clipTriangle returns nothing (see clip_code_safe_out)
+		} else {
+			clipped = 1;
+			const unsigned c = setup_clipped_face<PEEL>(fp, o, mvp, __ldg(mesh.pos + i0), __ldg(mesh.pos + i1), __ldg(mesh.pos + i2), f);
+			cnt.tris += c & 255u; cnt.small += (c >> 8) & 255u; cnt.binned += c >> 16;
 		}
-		// tile flags of the direct path, warp-aggregated: consecutive faces of a mesh land in the same one or two tiles, so one
-		// lane per distinct tile rect does the test-and-set (correct for any input; merely slower when faces are scattered)
-		__syncwarp();
-		const unsigned peers = __match_any_sync(0xffffffffu, touched);
-		if (touched != NO_TOUCH && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) {
-			const int tx0 = touched & 255, ty0 = (touched >> 8) & 255, tx1 = (touched >> 16) & 255, ty1 = touched >> 24;
+	}
+	__syncwarp();
+	// Tile flags of the direct path, warp-aggregated: the 32 consecutive faces of a warp land in the same one or two tiles, so lane 0
+	// flags the union of their tile rects (a superset costs an empty staging pass in the tile kernel, nothing else); scattered faces
+	// (union of more than 4 tiles) flag their own.
+	const bool has = touched != NO_TOUCH;
+	if (__ballot_sync(0xffffffffu, has)) {
+		const int tx0 = has ? (int)(touched & 255u) : 255, ty0 = has ? (int)((touched >> 8) & 255u) : 255;
+		const int tx1 = has ? (int)((touched >> 16) & 255u) : 0, ty1 = has ? (int)(touched >> 24) : 0;
+		const int ux0 = __reduce_min_sync(0xffffffffu, tx0), uy0 = __reduce_min_sync(0xffffffffu, ty0);
+		const int ux1 = __reduce_max_sync(0xffffffffu, tx1), uy1 = __reduce_max_sync(0xffffffffu, ty1);
+		if ((ux1 - ux0 + 1) * (uy1 - uy0 + 1) <= 4) {
+			if (lane == 0)
+				for (int ty = uy0; ty <= uy1; ++ty)
+					for (int tx = ux0; tx <= ux1; ++tx) touch_tile(fp, o, tx, ty);
+		} else if (has) {
 			for (int ty = ty0; ty <= ty1; ++ty)
 				for (int tx = tx0; tx <= tx1; ++tx) touch_tile(fp, o, tx, ty);
 		}
 	}
-	// counters: warp reduce, then one fire-and-forget reduction per non-zero counter per warp into one of 4096 stripes
-	// (no barrier, no fence, no hot address: warps retire independently); k_scan_tiles folds the stripes
-	__syncwarp();
-	const unsigned w0 = __reduce_add_sync(0xffffffffu, clipped), w1 = __reduce_add_sync(0xffffffffu, cnt.tris);
-	const unsigned w2 = __reduce_add_sync(0xffffffffu, cnt.small), w3 = __reduce_add_sync(0xffffffffu, cnt.binned);
-	if ((threadIdx.x & 31) == 0) {
-		const unsigned stripe = (blockIdx.x * (SETUP_THREADS / 32) + (threadIdx.x >> 5)) % STAT_STRIPES;
-		if (w0) atomicAdd(&o.status->stripes[0][stripe], w0);
-		if (w1) atomicAdd(&o.status->stripes[1][stripe], w1);
-		if (w2) atomicAdd(&o.status->stripes[2][stripe], w2);
-		if (w3) atomicAdd(&o.status->stripes[3][stripe], w3);
+	// Counters: warp reduce, then one fire-and-forget reduction per non-zero counter per warp into one of STAT_STRIPES stripes (no hot
+	// address). Warps whose faces were all culled have nothing to add.
+	if (__ballot_sync(0xffffffffu, (cnt.tris | clipped) != 0u)) {
+		const unsigned w0 = __reduce_add_sync(0xffffffffu, clipped), w1 = __reduce_add_sync(0xffffffffu, cnt.tris);
+		const unsigned w2 = __reduce_add_sync(0xffffffffu, cnt.small), w3 = __reduce_add_sync(0xffffffffu, cnt.binned);
+		if (lane == 0) {
+			const unsigned stripe = (blockIdx.x * (SETUP_THREADS / 32) + (threadIdx.x >> 5)) % STAT_STRIPES;
+			if (w0) atomicAdd(&o.status->stripes[0][stripe], w0);
+			if (w1) atomicAdd(&o.status->stripes[1][stripe], w1);
+			if (w2) atomicAdd(&o.status->stripes[2][stripe], w2);
+			if (w3) atomicAdd(&o.status->stripes[3][stripe], w3);
+		}
 	}
+}
+
+// Folds the striped counters of k_setup_raster and publishes the draw's status to the host (one small CTA behind the setup kernel;
+// a last-CTA-done ticket inside the setup kernel was measured: its barrier keeps every CTA resident until its slowest warp is done,
+// C3 171 -> 239 us).
+constexpr int FOLD_THREADS = 128;
+__global__ void __launch_bounds__(FOLD_THREADS) k_fold_status(DrawStatus* status, DrawStatus* host_status, int bins_enabled) {
+	__shared__ unsigned long long s_fold[4][FOLD_THREADS / 32];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+	for (int c = 0; c < 4; ++c) {
+		unsigned long long acc = 0;
+		for (int i = threadIdx.x; i < STAT_STRIPES; i += FOLD_THREADS) acc += status->stripes[c][i];
+		for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+		if (lane == 0) s_fold[c][warp] = acc;
+	}
+	__syncthreads();
+	if (threadIdx.x < 4) {
+		unsigned long long sum = 0;
+		for (int w = 0; w < FOLD_THREADS / 32; ++w) sum += s_fold[threadIdx.x][w];
+		(&status->clipped_faces)[threadIdx.x] = sum;
+		if (threadIdx.x == 3 && sum != 0 && !bins_enabled) status->overflow = OVF_NEED_BINS;
+	}
+	__syncthreads();
+	// bin_refs and (with bins) overflow are k_scan_tiles' to fill in; it publishes those words again
+	if (threadIdx.x < 6) publish_status(status, host_status, threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------ bins: scan + scatter
 // Block-wide exclusive prefix sum over the per-tile counts (one CTA of 1024 threads, 8 tiles per thread per round).
 // On exit: bin_start[0..n] holds offsets, tile_count[] is zeroed so k_bin_scatter can reuse it as the fill cursor.
-// With no binned records at all (every triangle was rasterised by its own setup thread) only the counters are folded.
+// Both bin kernels are only launched for draws issued with bins (SetupOut::bins_enabled); with no record at all they return at once.
 constexpr int SCAN_THREADS = 1024, SCAN_PER_THREAD = 8;
-// The draw's counters go to the host through mapped pinned memory (plain stores over PCIe): a cudaMemcpyAsync between the
-// kernels would put a copy-engine operation, i.e. a bubble of ~10 us, into the middle of every draw.
-__device__ __forceinline__ void publish_status(const DrawStatus* d, DrawStatus* h) {
-	volatile unsigned long long* hv = reinterpret_cast<volatile unsigned long long*>(h);
-	const volatile unsigned long long* dv = reinterpret_cast<const volatile unsigned long long*>(d);
-	for (int i = 0; i < 6; ++i) hv[i] = dv[i];  // clipped_faces, triangles, small, binned, bin_refs, {overflow, pad}
-	// no system fence: the host reads after synchronising on an event recorded behind this kernel
-}
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(unsigned* tile_count, unsigned* bin_start, int n, unsigned ref_cap,
                                                              const unsigned* n_records, unsigned rec_cap, DrawStatus* status, DrawStatus* host_status) {
 	__shared__ unsigned s_warp[32];
 	__shared__ unsigned s_carry;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	{  // fold the striped counters of k_setup_raster: 256 threads per counter, 16 stripes each, then shuffle + shared reduction
-		__shared__ unsigned long long s_fold[32];
-		const int c = tid >> 8, t = tid & 255;
-		unsigned long long acc = 0;
-#pragma unroll
-		for (int i = 0; i < STAT_STRIPES / 256; ++i) acc += status->stripes[c][t + i * 256];
-		for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
-		if (lane == 0) s_fold[warp] = acc;
-		__syncthreads();
-		if (tid < 4) {
-			unsigned long long sum = 0;
-			for (int w = 0; w < 8; ++w) sum += s_fold[tid * 8 + w];
-			(&status->clipped_faces)[tid] = sum;
-		}
-	}
 	const unsigned nrec = *n_records;
-	if (nrec == 0) {  // k_tile_shade does not read bin_start in this case
-		__syncthreads();
-		// six threads, one 8-byte word each (a single thread's volatile copies are six dependent L2 round trips);
-		// bin_refs, overflow and pad are still the zeros k_vertex_xform wrote
-		if (tid < 6) reinterpret_cast<volatile unsigned long long*>(host_status)[tid] = reinterpret_cast<const volatile unsigned long long*>(status)[tid];
-		return;
-	}
+	if (nrec == 0) return;  // k_tile_shade does not read bin_start in this case; the status was published by k_setup_raster
 	if (tid == 0) s_carry = 0;
 	__syncthreads();
 	for (int base = 0; base < n; base += SCAN_THREADS * SCAN_PER_THREAD) {
@@ -458,11 +490,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(unsigned* tile_coun
 		bin_start[n] = total;
 		status->bin_refs = total;
 		unsigned ovf = 0;
-		if (nrec > rec_cap) ovf |= 1u;
-		if (total > ref_cap) ovf |= 2u;
+		if (nrec > rec_cap) ovf |= OVF_RECORDS;
+		if (total > ref_cap) ovf |= OVF_REFS;
 		status->overflow = ovf;
 		__threadfence();
-		publish_status(status, host_status);
+		publish_status(status, host_status, 4);  // bin_refs
+		publish_status(status, host_status, 5);  // overflow
 	}
 }
 

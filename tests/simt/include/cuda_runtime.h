@@ -168,6 +168,24 @@ static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
 		if ((part >> i) & 1u) r += (unsigned)out[i];
 	return r;
 }
+static inline int __reduce_min_sync(unsigned mask, int v) {
+	unsigned long long out[32];
+	const unsigned part = simt::warp_exchange(mask, simt::OP_REDUCE, simt::to_bits(v), out);
+	int r = v;
+	for (int i = 0; i < 32; ++i)
+		if ((part >> i) & 1u) r = std::min(r, simt::from_bits<int>(out[i]));
+	return r;
+}
+static inline int __reduce_max_sync(unsigned mask, int v) {
+	unsigned long long out[32];
+	const unsigned part = simt::warp_exchange(mask, simt::OP_REDUCE, simt::to_bits(v), out);
+	int r = v;
+	for (int i = 0; i < 32; ++i)
+		if ((part >> i) & 1u) r = std::max(r, simt::from_bits<int>(out[i]));
+	return r;
+}
+template <typename T>
+static inline T __ldcg(const T* p) { return *p; }
 // Fibers are cooperative (one OS thread), so a plain read-modify-write is atomic.
 template <typename T>
 static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }

@@ -434,7 +434,7 @@ def test_c_abi_error_codes_and_lifecycle(po):
         dev.clear()
         dev.draw_mesh(m2, np.eye(4))
         st = dev.stats()
-        assert st["faces"] == f.shape[0] and 3 <= st["kernel_launches"] <= 6
+        assert st["faces"] == f.shape[0] and 3 <= st["kernel_launches"] <= 7
         # two contexts on one device do not interfere
         dev2 = api.Device(96, 64)
         try:

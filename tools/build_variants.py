@@ -10,10 +10,11 @@ from axiomr_b200 import build as b  # noqa: E402
 # Compile-time knobs of axr_kernels.cuh (launch shapes). The defaults are the winners of the round-1 A/B runs
 # (profiles/r01_ab_*.jsonl); these variants bracket them.
 VARIANTS = {
-    "idx_stash": ["AXR_TILE_IDX_STASH=1"],
-    "idx_stash_128x8": ["AXR_TILE_IDX_STASH=1", "AXR_TILE_THREADS=128", "AXR_TILE_MINB=8"],
-    "tile_128x8": ["AXR_TILE_THREADS=128", "AXR_TILE_MINB=8"],
-    "row_lanes": ["AXR_QUAD_LANES=0"],
+    "setup_loop0": ["AXR_SETUP_LOOP=0"],
+    "setup_mb12": ["AXR_SETUP_MINB=12"],
+    "setup_mb10": ["AXR_SETUP_MINB=10"],
+    "setup_loop0_mb12": ["AXR_SETUP_LOOP=0", "AXR_SETUP_MINB=12"],
+    "setup_t256_mb6": ["AXR_SETUP_THREADS=256", "AXR_SETUP_MINB=6"],
 }
 
 def _one(name: str) -> str:
