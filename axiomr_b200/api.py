@@ -75,7 +75,7 @@ ABI_SYMBOLS = [
     "axr_upload_texture", "axr_free_texture", "axr_set_material", "axr_set_uniforms", "axr_set_shader", "axr_set_sampler",
     "axr_clear", "axr_upload_framebuffer", "axr_resolve", "axr_draw_mesh", "axr_sync", "axr_get_stats", "axr_host_alloc",
     "axr_host_free", "axr_stream", "axr_framebuffer_device", "axr_set_output", "axr_framebuffer_ipc", "axr_open_ipc",
-    "axr_close_ipc", "axr_set_profiling", "axr_get_kernel_times", "axr_set_depth_read", "axr_alloc_shared", "axr_free_shared", "axr_set_overlap", "axr_upload_framebuffer_async", "axr_draw_mesh_host", "axr_generate_tangents", "axr_measure_fp32_issue", "axr_set_color_math",
+    "axr_close_ipc", "axr_set_profiling", "axr_get_kernel_times", "axr_set_depth_read", "axr_alloc_shared", "axr_free_shared", "axr_set_overlap", "axr_upload_framebuffer_async", "axr_draw_mesh_host", "axr_generate_tangents", "axr_measure_fp32_issue", "axr_set_color_math", "axr_update_mesh_vertices", "axr_dirty_map_entries", "axr_set_dirty_map", "axr_clear_dirty_tiles",
 ]
 STAGES = ["vertex_xform", "setup_raster", "scan_tiles", "bin_scatter", "tile_shade"]
 
@@ -110,6 +110,7 @@ def _bind(lib):
     lib.axr_last_error.restype = C.c_char_p
     lib.axr_upload_mesh.argtypes = [vp, _f32p, C.c_uint64, _u32p, C.c_uint64, C.POINTER(_Group), C.c_uint32, C.POINTER(C.c_int32)]
     lib.axr_free_mesh.argtypes = [vp, C.c_int32]
+    lib.axr_update_mesh_vertices.argtypes = [vp, C.c_int32, _f32p, C.c_uint64]
     lib.axr_generate_tangents.argtypes = [vp, _f32p, C.c_uint64, _u32p, C.c_uint64, _f32p]
     lib.axr_upload_texture.argtypes = [vp, _u8p, C.c_int, C.c_int, C.POINTER(C.c_int32)]
     lib.axr_free_texture.argtypes = [vp, C.c_int32]
@@ -139,6 +140,9 @@ def _bind(lib):
     lib.axr_close_ipc.argtypes = [vp, vp]
     lib.axr_set_depth_read.argtypes = [vp, C.c_int]
     lib.axr_set_overlap.argtypes = [vp, C.c_int]
+    lib.axr_dirty_map_entries.argtypes = [vp]
+    lib.axr_set_dirty_map.argtypes = [vp, vp]
+    lib.axr_clear_dirty_tiles.argtypes = [vp, vp, vp, vp, C.c_int, C.c_uint32, C.c_float, vp]
     lib.axr_alloc_shared.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.c_void_p]
     lib.axr_free_shared.argtypes = [vp, vp]
     lib.axr_measure_fp32_issue.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -218,6 +222,11 @@ class Device:
         self._check(self.lib.axr_generate_tangents(self.h, v.ctypes.data_as(_f32p), v.shape[0], f.ctypes.data_as(_u32p), f.shape[0],
                                                    out.ctypes.data_as(_f32p)))
         return out
+
+    def update_mesh_vertices(self, mesh: int, vertices: np.ndarray):
+        """Re-send the vertices of an uploaded mesh (same count, same faces)."""
+        v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 14)
+        self._check(self.lib.axr_update_mesh_vertices(self.h, mesh, v.ctypes.data_as(_f32p), v.shape[0]))
 
     def free_mesh(self, mesh: int):
         self._check(self.lib.axr_free_mesh(self.h, mesh))
@@ -329,6 +338,17 @@ class Device:
         p = C.c_void_p()
         self._check(self.lib.axr_open_ipc(self.h, C.create_string_buffer(handle, 64), C.byref(p)))
         return int(p.value)
+
+    def dirty_map_entries(self) -> int:
+        return int(self.lib.axr_dirty_map_entries(self.h))
+
+    def set_dirty_map(self, dirty_dev: int | None):
+        """Every draw flags the 32x32 tiles it may store into in this u32 map (device pointer, may be peer memory); None = off."""
+        self._check(self.lib.axr_set_dirty_map(self.h, dirty_dev))
+
+    def clear_dirty_tiles(self, color_dev: int, depth_dev: int, dirty_dev: int, count: int = 1, packed_argb: int = 0xFF000000,
+                          depth: float = float("inf"), stream: int | None = None):
+        self._check(self.lib.axr_clear_dirty_tiles(self.h, color_dev, depth_dev, dirty_dev, count, packed_argb, depth, stream))
 
     def set_overlap(self, enabled: bool):
         self._check(self.lib.axr_set_overlap(self.h, 1 if enabled else 0))
@@ -539,6 +559,12 @@ class Mesh:
         self._f = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1, 3)
         self._materials = materials if materials is not None else {"default": Material("default")}
         self._groups = groups if groups is not None else [MaterialGroup(next(iter(self._materials)), 0, self._f.shape[0])]
+        self._version = 0
+
+    def invalidate(self):
+        """Tell the pipelines that hold a device copy of this mesh that its arrays were edited in place (the reference reads the
+        host Mesh on every drawMesh; here it is uploaded once and cached): the next drawMesh re-sends it."""
+        self._version += 1
 
     def getVertices(self):
         return self._v
@@ -636,9 +662,32 @@ class TiledPipeline(Pipeline):
             self.last_h2d_bytes += t.data.nbytes
         return self._tex_cache[k][0]
 
+    host_path_description = (
+        "TiledPipeline.drawMesh(model, mesh) on a pinned host Framebuffer (axr_draw_mesh_host): nothing is uploaded — the merge test "
+        "reads the host depth of the visible pixels through a zero-copy mapping (128 B row reads over PCIe, counted in h2d_bytes) and "
+        "the pixels that pass are stored by the tile kernel straight into the host arrays (8 B per updated pixel, 128 B row stores), "
+        "complete on return; host-side clearColor/clearDepth before the call are the caller's and untimed, as in the CPU arm; "
+        "mesh/textures cached on the device after the first call (Mesh.invalidate() re-sends an edited mesh)")
+
+    def invalidate(self, mesh: Mesh):
+        """The adapter's counterpart of Mesh.invalidate(): forget the device copy of `mesh` (it is re-uploaded by the next drawMesh)."""
+        ent = self._mesh_cache.pop(id(mesh), None)
+        if ent is not None and self.device is not None:
+            self.device.free_mesh(ent[0])
+
     def _mesh(self, mesh: Mesh) -> int:
-        """The reference reads the host Mesh on every call; here it is uploaded on first use and cached by identity."""
+        """The reference reads the host Mesh on every call; here it is uploaded on first use and cached by identity + version:
+        a mesh whose vertices were edited in place (Mesh.invalidate()) with unchanged counts is re-sent into the same device
+        buffers, any other change re-uploads it."""
         k = id(mesh)
+        ent = self._mesh_cache.get(k)
+        if ent is not None and ent[2] != getattr(mesh, "_version", 0):
+            if ent[3] == (mesh.getVertices().shape[0], mesh.getFaces().shape[0]) and np.array_equal(ent[4], mesh.getFaces()):
+                self.device.update_mesh_vertices(ent[0], mesh.getVertices())
+                self.last_h2d_bytes += mesh.getVertices().nbytes
+                self._mesh_cache[k] = (ent[0], mesh, mesh._version, ent[3], ent[4])
+            else:
+                self.invalidate(mesh)
         if k not in self._mesh_cache:
             groups = [(g.startIndex, g.faceCount) for g in mesh.getMaterialGroups()]
             h = self.device.upload_mesh(mesh.getVertices(), mesh.getFaces(), groups)
@@ -648,7 +697,8 @@ class TiledPipeline(Pipeline):
                 self.device.set_material(h, gi, self._texture(m.diffuseTexture), self._texture(m.bumpTexture),
                                          self._texture(m.metallicTexture), self._texture(m.roughnessTexture),
                                          self._texture(m.aoTexture), float(m.specularExponent))
-            self._mesh_cache[k] = (h, mesh)
+            self._mesh_cache[k] = (h, mesh, getattr(mesh, "_version", 0), (mesh.getVertices().shape[0], mesh.getFaces().shape[0]),
+                                   mesh.getFaces().copy())
         return self._mesh_cache[k][0]
 
     def drawMesh(self, modelMatrix, mesh: Mesh):
@@ -663,18 +713,21 @@ class TiledPipeline(Pipeline):
         dev.set_uniforms(cam.getViewProjectionMatrix(), cam.getPosition(), cam.getViewportMatrix())
         sh = self.m_Shader
         dev.set_shader(sh.kind, sh.lightDirection, getattr(sh, "lightColor", (1.0, 1.0, 1.0)))
-        # host depth goes up (4 B/px), the pixels that pass the depth test come back through zero-copy stores (8 B each)
+        # nothing is uploaded: the host depth of the visible pixels is read through the zero-copy mapping (4 B each), the pixels
+        # that pass the depth test are stored the same way (8 B each)
         dev.draw_mesh_host(h, modelMatrix, fb.getColorData(), fb.getDepthData())
-        self.last_h2d_bytes += fb.getDepthData().nbytes + 16 * 4 * 3 + 12
+        self.last_h2d_bytes += 16 * 4 * 3 + 12  # uniforms; plus 4 B per visible pixel read through the mapping (the caller knows how many)
         self.last_d2h_bytes = None  # 8 bytes per updated pixel; the caller knows how many pixels changed
 
 
-def render_scene(scene, device: int = 0, color=None, depth=None, band=None, dev: Device | None = None):
+def render_scene(scene, device: int = 0, color=None, depth=None, band=None, dev: Device | None = None, color_math: int | None = None):
     """Draw a scenes.Scene once on a cleared (or given) framebuffer through the C ABI. Returns (BGRA, depth, stats)."""
     own = dev is None
     if own:
         dev = Device(scene.width, scene.height, device, scene.sampler, band)
     try:
+        if color_math is not None:
+            dev.set_color_math(color_math)
         mesh = dev.load_scene(scene)
         if color is None:
             dev.clear(0xFF000000, float("inf"))

@@ -103,6 +103,7 @@ struct axr_ctx {
 	} slot[2];
 	unsigned draw_counter = 0;
 	cudaStream_t geom_stream = nullptr;
+	unsigned* dirty_map = nullptr;  // axr_set_dirty_map
 	bool color_fast = true;  // axr_set_color_math: fused colour arithmetic in the shading stage (default) or the reference's individually rounded one
 	bool overlap = false;  // axr_set_overlap: geometry stages on geom_stream (else everything on the main stream)
 	PendingDraw pending;
@@ -129,9 +130,10 @@ struct axr_ctx {
 	cudaEvent_t up_done[MAX_HOST_CHUNKS] = {};
 	cudaEvent_t depth_free = nullptr;  // main stream: the previous user of the device depth copy is done
 	int host_chunks = 0;               // > 0 only while axr_draw_mesh_host issues its draw
-	// Experiment knob (environment variable AXR_B200_HOST_DEPTH_ZEROCOPY=1 at axr_create; not yet timed): no depth upload at all,
-	// the merge test reads the host depth of the visible pixels through the zero-copy mapping (128 B row reads over PCIe)
-	bool host_depth_zero_copy = false;
+	// axr_draw_mesh_host: no depth upload at all, the merge test reads the host depth of the visible pixels through the zero-copy
+	// mapping (128 B row reads over PCIe; C3: 0.976 -> 0.874 ms per call). AXR_B200_HOST_DEPTH_ZEROCOPY=0 at axr_create restores the
+	// chunked upload of the whole depth plane.
+	bool host_depth_zero_copy = true;
 	int chunk_ty[MAX_HOST_CHUNKS + 1] = {};  // GPU tile rows [chunk_ty[b], chunk_ty[b+1]) of chunk b
 
 	// depth peeling (draws with a shader that may discard): per-pixel floor keys + the "another pass" flag; allocated on first use
@@ -382,6 +384,7 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 	in.floor = peel ? ctx->peel_floor : nullptr;
 	in.again = peel ? ctx->peel_again : nullptr;
 	in.clip_tiles = sl.clip_tiles; in.n_clip_tiles = sl.n_clip_tiles;
+	in.dirty = ctx->dirty_map;
 	switch (ctx->shader_kind) {
 	case AXR_SHADER_FLAT: launches += launch_tile<FlatShader>(ctx, mv, u, in); break;
 	case AXR_SHADER_PHONG: launches += launch_tile<PhongShader>(ctx, mv, u, in); break;
@@ -694,6 +697,27 @@ int axr_generate_tangents(axr_ctx* ctx, const float* v8, uint64_t n_verts, const
 	CUT(cudaStreamSynchronize(s));
 #undef CUT
 	cleanup();
+	return AXR_OK;
+}
+
+int axr_update_mesh_vertices(axr_ctx* ctx, axr_mesh mh, const float* vertices, uint64_t n_verts) {
+	if (!ctx) return AXR_ERR_INVALID;
+	if (!valid_mesh(ctx, mh) || !vertices) return fail(ctx, AXR_ERR_INVALID, "axr_update_mesh_vertices: bad mesh handle %d or null pointer", mh);
+	DeviceMesh& m = ctx->meshes[mh];
+	if (n_verts != m.n_verts) return fail(ctx, AXR_ERR_INVALID, "axr_update_mesh_vertices: %llu vertices, the mesh has %llu", (unsigned long long)n_verts, m.n_verts);
+	if (n_verts == 0) return AXR_OK;
+	CU(cudaSetDevice(ctx->device));
+	int rc = check_pending(ctx);
+	if (rc) return rc;
+	rc = sync_all(ctx);  // no draw in flight may still read the old vertices
+	if (rc) return rc;
+	float* raw = nullptr;
+	CU(cudaMalloc(&raw, n_verts * 14 * sizeof(float)));
+	cudaMemcpyAsync(raw, vertices, n_verts * 14 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+	k_split_vertices<<<(unsigned)((n_verts + 255) / 256), 256, 0, ctx->stream>>>(raw, n_verts, n_verts, m.pos, m.attr);
+	const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+	cudaFree(raw);
+	if (e != cudaSuccess) return fail(ctx, AXR_ERR_CUDA, "axr_update_mesh_vertices: %s", cudaGetErrorString(e));
 	return AXR_OK;
 }
 
@@ -1032,6 +1056,26 @@ int axr_set_output(axr_ctx* ctx, void* bgra_dev, void* depth_dev) {
 	if ((bgra_dev == nullptr) != (depth_dev == nullptr)) return fail(ctx, AXR_ERR_INVALID, "axr_set_output: pass both pointers or neither");
 	ctx->out_color = bgra_dev ? (unsigned*)bgra_dev : ctx->color;
 	ctx->out_depth = depth_dev ? (float*)depth_dev : ctx->depth;
+	return AXR_OK;
+}
+
+int axr_dirty_map_entries(const axr_ctx* ctx) { return ctx ? ctx->fp.ntx * ctx->fp.nty : 0; }
+
+int axr_set_dirty_map(axr_ctx* ctx, void* dirty_dev) {
+	if (!ctx) return AXR_ERR_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	if (int rc = check_pending(ctx)) return rc;
+	ctx->dirty_map = (unsigned*)dirty_dev;
+	return AXR_OK;
+}
+
+int axr_clear_dirty_tiles(axr_ctx* ctx, void* bgra_dev, void* depth_dev, void* dirty_dev, int count, uint32_t packed_argb, float depth, void* stream) {
+	if (!ctx) return AXR_ERR_INVALID;
+	if (!bgra_dev || !depth_dev || !dirty_dev || count <= 0 || count > 65535) return fail(ctx, AXR_ERR_INVALID, "axr_clear_dirty_tiles: bad argument");
+	CU(cudaSetDevice(ctx->device));
+	k_clear_dirty_tiles<<<dim3(ctx->fp.ntx, ctx->fp.nty, count), 256, 0, stream ? (cudaStream_t)stream : ctx->stream>>>(
+		(unsigned*)bgra_dev, (float*)depth_dev, (unsigned*)dirty_dev, ctx->fp.W, ctx->fp.H, ctx->fp.ntx, GT, packed_argb, depth);
+	CU(cudaGetLastError());
 	return AXR_OK;
 }
 

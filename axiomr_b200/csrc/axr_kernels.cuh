@@ -109,6 +109,25 @@ __global__ void k_clear(unsigned* color, float* depth, unsigned packed, float z,
 #ifndef AXR_IDX_PAD
 #define AXR_IDX_PAD 0
 #endif
+// Framebuffer clear restricted to the tiles a draw stored into (dirty map written by k_tile_shade): `count` targets of W*H pixels
+// laid out back to back (colour planes, depth planes, dirty maps each contiguous); the flags are reset. One CTA per tile and target.
+__global__ void __launch_bounds__(256) k_clear_dirty_tiles(unsigned* color, float* depth, unsigned* dirty, int W, int H, int ntx, int tile_px,
+                                                           unsigned packed, float z) {
+	const size_t npx = (size_t)W * H;
+	const int tile = blockIdx.y * ntx + blockIdx.x;
+	unsigned* flag = dirty + (size_t)blockIdx.z * ((size_t)gridDim.x * gridDim.y) + tile;
+	if (*flag == 0u) return;
+	__syncthreads();
+	if (threadIdx.x == 0) *flag = 0u;
+	const int x0 = blockIdx.x * tile_px, y0 = blockIdx.y * tile_px;
+	for (int p = threadIdx.x; p < tile_px * tile_px; p += blockDim.x) {
+		const int px = x0 + p % tile_px, py = y0 + p / tile_px;
+		if (px < W && py < H) {
+			const size_t gi = (size_t)blockIdx.z * npx + (size_t)py * W + px;
+			color[gi] = packed; depth[gi] = z;
+		}
+	}
+}
 // AoS AR::Vertex (56 B) -> position float4 + attributes (done once at mesh upload)
 __global__ void k_split_vertices(const float* __restrict__ raw, unsigned long long n, unsigned long long n_plane, float4* __restrict__ pos,
                                  float4* __restrict__ attr) {
@@ -537,6 +556,7 @@ struct TileIn {
 	unsigned* again;                // depth peeling only: set when some winner was discarded in this pass
 	int row_major;                  // 1: a warp shades one 32 x 1 pixel row (128 B contiguous stores: output in host memory over PCIe)
 	unsigned* clip_tiles;           // tiles holding pixels owned by a clipped face: shaded by k_shade_clipped, not here
+	unsigned* dirty;                // optional (axr_set_dirty_map): per GPU tile, set to 1 when this draw may store into the tile
 	unsigned* n_clip_tiles;
 };
 
@@ -655,14 +675,13 @@ __device__ bool shade_pixel_clipped(const MeshView& mesh, const Uniforms& u, con
 enum { PIX_DONE = 0, PIX_DISCARDED = 1, PIX_CLIPPED = 2 };
 template <typename Shader, int SMP, bool FAST>
 __device__ __forceinline__ int shade_pixel(const MeshView& mesh, const Uniforms& u, const FrameParams& fp, const TileIn& in, unsigned ordinal,
-                                           unsigned i0, unsigned i1, unsigned i2, int px, int py) {
+                                           unsigned i0, unsigned i1, unsigned i2, int px, int py, float fbz) {
 	const size_t gi = (size_t)py * fp.W + px;
 #if !AXR_TILE_RECOMPUTE_SV
 	const float4 s0 = __ldg(in.sv + i0), s1 = __ldg(in.sv + i1), s2 = __ldg(in.sv + i2);
 #endif
 	VIn v[3];
 	v[0] = load_vertex(mesh, i0); v[1] = load_vertex(mesh, i1); v[2] = load_vertex(mesh, i2);
-	const float fbz = in.read_depth ? in.depth_read[gi] : INFINITY;
 #if AXR_TILE_RECOMPUTE_SV
 	// variant: the vertex stage's 16 B screen records are recomputed from the positions (same arithmetic, same bits) instead of
 	// gathered: three gathers fewer for ~150 instructions more
@@ -716,7 +735,10 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 		s_keys[p] = k;
 	}
 	__syncthreads();
-	if (tid == 0) { in.tile_touched[tile] = 0u; in.tile_cursor[tile] = 0u; }
+	if (tid == 0) {
+		in.tile_touched[tile] = 0u; in.tile_cursor[tile] = 0u;
+		if (in.dirty) in.dirty[tile] = 1u;
+	}
 	// 2. binned triangles. Each warp takes 32 references at a time: every lane loads and sets up ITS record (32 independent
 	//    gathers in flight), then the warp walks the set-up records one by one (setup broadcast by shuffles) and evaluates
 	//    8x4 pixel blocks per step with shared-memory atomicMin.
@@ -809,6 +831,10 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 		const unsigned long long k = s_keys[p];
 		if (k == KEY_EMPTY) continue;
 		const unsigned ord = (unsigned)(k & 0xFFFFFFFFull);
+		const int px = x0 + (p & (GT - 1)), py = y0 + (p / GT);
+		// the framebuffer depth for the merge test does not depend on the triangle: issued first, so that a read that crosses PCIe
+		// (host framebuffer, axr_draw_mesh_host) or NVLink has the index -> vertex gathers to hide behind
+		const float fbz = in.read_depth ? in.depth_read[(size_t)py * fp.W + px] : INFINITY;
 #if AXR_TILE_IDX_STASH
 		const unsigned i0 = s_idx[0][p], i1 = s_idx[1][p], i2 = s_idx[2][p];
 #elif AXR_IDX_PAD
@@ -818,8 +844,7 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 		const unsigned* ip = mesh.idx + (size_t)(ord >> 3) * 3;
 		const unsigned i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
 #endif
-		const int px = x0 + (p & (GT - 1)), py = y0 + (p / GT);
-		const int res = shade_pixel<Shader, SMP, FAST>(mesh, u, fp, in, ord, i0, i1, i2, px, py);
+		const int res = shade_pixel<Shader, SMP, FAST>(mesh, u, fp, in, ord, i0, i1, i2, px, py, fbz);
 		if (res == PIX_CLIPPED) {
 			// owned by a clipped face: the key goes back to the global buffer and the tile onto the list k_shade_clipped works through
 			in.vis[(size_t)py * fp.W + px] = k;

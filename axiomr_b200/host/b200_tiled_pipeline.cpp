@@ -95,6 +95,13 @@ int B200TiledPipeline::meshHandle(const Mesh& mesh) {
 	return h;
 }
 
+void B200TiledPipeline::invalidate(const Mesh& mesh) {
+	auto it = m_Meshes.find(&mesh);
+	if (it == m_Meshes.end()) return;
+	if (m_Ctx) axr_free_mesh(m_Ctx, it->second);
+	m_Meshes.erase(it);
+}
+
 void B200TiledPipeline::drawMesh(const glm::mat4& modelMatrix, const Mesh& mesh) {
 	if (!m_Shader || !m_Camera || !m_Framebuffer) return;  // reference src/tiled_pipeline.cpp:146
 	ensureContext();
@@ -130,10 +137,12 @@ void B200TiledPipeline::drawMesh(const glm::mat4& modelMatrix, const Mesh& mesh)
 
 	const int h = meshHandle(mesh);
 	const size_t npx = (size_t)m_Framebuffer->getWidth() * m_Framebuffer->getHeight();
-	// host depth up (4 B/px), passing pixels back through zero-copy stores (8 B each); complete on return
+	// nothing is uploaded: host depth of the visible pixels read through the zero-copy mapping (4 B each), passing pixels stored
+	// the same way (8 B each); complete on return
 	rc = axr_draw_mesh_host(m_Ctx, h, &modelMatrix[0][0], m_Framebuffer->getColorData(), m_Framebuffer->getDepthData());
 	if (rc != AXR_OK) fail("axr_draw_mesh_host", rc);
-	m_LastH2D += npx * 4 + 16 * 4 * 3 + 12;
+	(void)npx;
+	m_LastH2D += 16 * 4 * 3 + 12;
 	m_LastD2H += 0;  // 8 bytes per updated pixel, written by the kernel
 }
 

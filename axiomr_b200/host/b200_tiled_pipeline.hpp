@@ -31,6 +31,10 @@ public:
 	B200TiledPipeline(const B200TiledPipeline&) = delete;
 	B200TiledPipeline& operator=(const B200TiledPipeline&) = delete;
 	void drawMesh(const glm::mat4& modelMatrix, const Mesh& mesh) override;
+	// The reference reads the host Mesh on every drawMesh; this adapter uploads it on first use and keeps the device copy, keyed by
+	// the Mesh's address. After editing a Mesh in place (or destroying it and building another at the same address), call
+	// invalidate(): the device copy is dropped and the next drawMesh uploads the current contents.
+	void invalidate(const Mesh& mesh);
 
 	// bytes moved host<->device by the last drawMesh (framebuffer round trip + first-use mesh / texture uploads)
 	size_t lastH2DBytes() const { return m_LastH2D; }

@@ -6,8 +6,8 @@ Rendering shards without any data-path collective in two ways:
             replicated mesh and rasterises / shades only its rows (strong scaling, Amdahl-limited by the geometry stages).
 The single exchange step is the composite to GPU 0 — a gather of disjoint regions, no reduction:
   * NCCL grouped send/recv straight out of / into the framebuffer allocations (`Compositor`, mode "nccl"), or
-  * fused: the resolve stores of every rank go directly into GPU 0's framebuffer through a CUDA-IPC peer mapping
-    (`Compositor`, mode "peer"; bands only), so the transfer rides NVLink while the tile kernel is still shading.
+  * fused: the resolve stores of every rank go directly into targets in GPU 0's memory through a CUDA-IPC peer mapping
+    (`Compositor`, mode "peer"), so the transfer rides NVLink while the tile kernel is still shading.
 """
 from __future__ import annotations
 
@@ -91,13 +91,15 @@ def framebuffer_tensors(dev):
 class Compositor:
     """Gathers every rank's finished region to GPU 0 after each frame (the path's one exchange step).
 
-    transport "peer" (default) — composite fused into the tile kernel over NVLink peer memory (CUDA IPC):
-      bands : every rank maps GPU 0's framebuffer; its clear and resolve stores go straight into its own rows there. Rows are
-              disjoint, so there is no per-frame synchronisation at all.
-      views : GPU 0 owns two sets of per-view slots (colour + depth). Rank r > 0 points its output at slot (set i%2, r): its tile
-              kernel stores the covered pixels of frame i directly into GPU 0's memory (no depth read-back: the slot is freshly
-              cleared, axr_set_depth_read(0)). GPU 0 clears the *other* set for frame i+1 before its own draw; one tiny NCCL all-reduce per frame on the render streams orders "all stores of frame i are done"
-              before "the set is cleared again". Only covered pixels cross NVLink (≈ 25 MB instead of 66 MB per 4K view).
+    transport "peer" (default) — composite fused into the tile kernel over NVLink peer memory (CUDA IPC). GPU 0 owns two sets of
+      targets (colour + depth + a dirty-tile map each); frame i uses set i % 2:
+        views : one target per rank r > 0 (GPU 0 renders its own view into its own framebuffer);
+        bands : one full-frame target every rank, GPU 0 included, renders its rows into.
+      A rank's tile kernel stores the covered pixels of the frame straight into the target (no depth read over NVLink: the target
+      is freshly cleared, axr_set_depth_read(0)) and flags the 32x32 tiles it touches in the target's dirty map. While frame i
+      renders, GPU 0 clears the tiles flagged in the OTHER set (axr_clear_dirty_tiles on a side stream: a fraction of the frame
+      instead of all of it), and one 4-byte NCCL all-reduce per frame on the render streams orders "all stores of frame i are
+      done" before "the set is cleared again". Only covered pixels cross NVLink.
     transport "nccl" — the baseline: grouped send/recv of whole regions after each frame (bands: in place; views:
       double-buffered, on a second stream, overlapping the next frame).
     """
@@ -113,7 +115,11 @@ class Compositor:
         self.step = 0
         dv = self.color.device
         self.H, self.W = dev.height, dev.width
-        if mode == "views" and self.transport == "nccl":
+        if mode == "bands":
+            self.bands = band_rows(dev.height, world)
+        if self.transport == "peer":
+            self._setup_peer()
+        elif mode == "views":
             self.comm = torch.cuda.Stream(device=dv)
             self.done = [None, None]   # comm-stream events: buffer b has been sent / slot set b has been filled
             shape = (self.H, self.W)
@@ -123,38 +129,28 @@ class Compositor:
             else:
                 self.bufs = [(torch.empty(shape, dtype=torch.int32, device=dv), torch.empty(shape, dtype=torch.float32, device=dv))
                              for _ in range(2)]
-        elif mode == "views":
-            self._setup_peer_views()
-        else:
-            self.bands = band_rows(dev.height, world)
-            if self.transport == "peer":
-                self._setup_peer_bands()
 
-    # ------------------------------------------------------------------ bands
-    def _setup_peer_bands(self):
-        dist = self.dist
-        handles = [None]
-        if self.rank == 0:
-            handles = [self.dev.framebuffer_ipc()]
-        dist.broadcast_object_list(handles, src=0)
-        if self.rank != 0:
-            ch, dh = handles[0]
-            self._peer = (self.dev.open_ipc(ch), self.dev.open_ipc(dh))
-            self.dev.set_output(*self._peer)
-        dist.barrier()
+    # ------------------------------------------------------------------ targets on GPU 0 (peer transport)
+    @property
+    def n_targets(self) -> int:
+        return self.world - 1 if self.mode == "views" else 1
 
-    # ------------------------------------------------------------------ views over peer memory
-    def _slot_offsets(self, b: int, r: int):
-        """Byte offsets of (colour, depth) of slot (set b, rank r) inside the shared allocation.
-        Per set: [colour of ranks 1..N-1, contiguous][depth of ranks 1..N-1, contiguous] so a set is cleared by two flat fills."""
-        npx = self.H * self.W
-        base = b * (self.world - 1) * npx * 8
-        return base + (r - 1) * npx * 4, base + (self.world - 1) * npx * 4 + (r - 1) * npx * 4
+    def _offsets(self, b: int, t: int):
+        """Byte offsets of (colour, depth, dirty map) of target t of set b inside the shared allocation.
+        Per set: [colour planes][depth planes][dirty maps], each group contiguous (what axr_clear_dirty_tiles walks)."""
+        npx, nt, n = self.H * self.W, self.n_tiles, self.n_targets
+        set_bytes = n * (npx * 8 + nt * 4)
+        base = b * set_bytes
+        return base + t * npx * 4, base + n * npx * 4 + t * npx * 4, base + n * npx * 8 + t * nt * 4
 
-    def _setup_peer_views(self):
+    def _target_index(self) -> int:
+        return self.rank - 1 if self.mode == "views" else 0
+
+    def _setup_peer(self):
         torch, dist = self.torch, self.dist
         npx = self.H * self.W
-        total = 2 * (self.world - 1) * npx * 8
+        self.n_tiles = self.dev.dirty_map_entries()
+        total = 2 * self.n_targets * (npx * 8 + self.n_tiles * 4)
         handles = [None]
         if self.rank == 0:
             self._shared_ptr, h = self.dev.alloc_shared(total)
@@ -164,75 +160,71 @@ class Compositor:
         self.token = torch.zeros(1, dtype=torch.int32, device=dv)
         if self.rank == 0:
             self.slots = []
+            n = self.n_targets
             for b in range(2):
-                co, do = self._slot_offsets(b, 1)
-                shape = ((self.world - 1), self.H, self.W)
-                self.slots.append((torch.as_tensor(_DevArray(self._shared_ptr + co, shape, "<i4"), device=dv),
-                                   torch.as_tensor(_DevArray(self._shared_ptr + do, shape, "<f4"), device=dv)))
-            # cleared templates: a set is re-cleared with device-to-device copies (copy engines, no SM time) on a side stream
-            # while GPU 0 renders its own view
+                co, do, mo = self._offsets(b, 0)
+                c = torch.as_tensor(_DevArray(self._shared_ptr + co, (n, self.H, self.W), "<i4"), device=dv)
+                d = torch.as_tensor(_DevArray(self._shared_ptr + do, (n, self.H, self.W), "<f4"), device=dv)
+                m = torch.as_tensor(_DevArray(self._shared_ptr + mo, (n, self.n_tiles), "<i4"), device=dv)
+                c.fill_(-16777216)   # 0xFF000000
+                d.fill_(float("inf"))
+                m.zero_()
+                self.slots.append((c, d, m))
             self.side = torch.cuda.Stream(device=dv)
-            self.tmpl_c = torch.full((self.H, self.W), -16777216, dtype=torch.int32, device=dv)   # 0xFF000000
-            self.tmpl_d = torch.full((self.H, self.W), float("inf"), dtype=torch.float32, device=dv)
-            for b in range(2):
-                self._clear_set(b)
             torch.cuda.synchronize()
         else:
             self._shared_ptr = self.dev.open_ipc(handles[0])
-            self.dev.set_depth_read(False)
+        if self.rank != 0 or self.mode == "bands":
+            self.dev.set_depth_read(False)   # the target is freshly cleared and receives exactly this draw
         dist.barrier()
-
-    def _clear_set(self, b: int):
-        for r in range(self.world - 1):
-            self.slots[b][0][r].copy_(self.tmpl_c, non_blocking=True)
-            self.slots[b][1][r].copy_(self.tmpl_d, non_blocking=True)
 
     # ------------------------------------------------------------------ per frame
     @property
     def clears_own_target(self) -> bool:
-        """views over peer memory: the slot a rank renders into was cleared by GPU 0 already; the rank must not clear it."""
-        return not (self.mode == "views" and self.transport == "peer" and self.rank != 0)
+        """peer transport: the target a rank renders into was cleared by GPU 0 already; only GPU 0's own view (views mode) is the
+        rank's to clear."""
+        if self.transport != "peer":
+            return True
+        return self.mode == "views" and self.rank == 0
 
     def begin_step(self):
         """Call before the frame's clear: selects the output buffer of this frame."""
         b = self.step % 2
-        if self.mode != "views":
-            return
         if self.transport == "nccl":
-            if self.rank != 0:
+            if self.mode == "views" and self.rank != 0:
                 if self.done[b] is not None:
                     self.stream.wait_event(self.done[b])      # the send of the frame rendered two steps ago has finished
                 c, d = self.bufs[b]
                 self.dev.set_output(c.data_ptr(), d.data_ptr())
             return
-        if self.rank != 0:
-            co, do = self._slot_offsets(b, self.rank)
+        if self.rank != 0 or self.mode == "bands":
+            co, do, mo = self._offsets(b, self._target_index())
             self.dev.set_output(self._shared_ptr + co, self._shared_ptr + do)
-        else:
-            # Clear the other set for the next frame while this one renders: device-to-device copies of a cleared template on a
-            # side stream, ordered after the previous frame's all-reduce. (Fill KERNELS on a side stream were measured slower than
-            # no overlap at all — they fight the vertex / setup kernels for SM slots: N = 8, +220 us on GPU 0.)
+            self.dev.set_dirty_map(self._shared_ptr + mo)
+        if self.rank == 0:
+            # Clear the other set's dirty tiles for the next frame while this one renders, on a side stream, ordered after the
+            # previous frame's all-reduce.
             ready = self.torch.cuda.Event()
             ready.record(self.stream)
-            with self.torch.cuda.stream(self.side):
-                self.side.wait_event(ready)
-                self._clear_set((b + 1) % 2)
+            nb = (b + 1) % 2
+            co, do, mo = self._offsets(nb, 0)
+            self.side.wait_event(ready)
+            self.dev.clear_dirty_tiles(self._shared_ptr + co, self._shared_ptr + do, self._shared_ptr + mo, self.n_targets,
+                                       stream=self.side.cuda_stream)
 
     def composite(self):
         torch, dist = self.torch, self.dist
         b = self.step % 2
         self.step += 1
-        if self.mode == "bands":
-            if self.transport == "peer":
-                return  # the tile kernel already stored this rank's band into GPU 0's framebuffer over NVLink
-            with torch.cuda.stream(self.stream):
-                gather_bands(self.color, self.depth, self.bands, self.rank, dist)
-            return
         if self.transport == "peer":
             with torch.cuda.stream(self.stream):
                 if self.rank == 0:
                     self.stream.wait_stream(self.side)    # the next frame's set is clear
                 dist.all_reduce(self.token)                # every rank's stores of this frame precede anything after it
+            return
+        if self.mode == "bands":
+            with torch.cuda.stream(self.stream):
+                gather_bands(self.color, self.depth, self.bands, self.rank, dist)
             return
         ready = torch.cuda.Event()
         ready.record(self.stream)                         # this frame is rendered
@@ -248,11 +240,26 @@ class Compositor:
 
     def finish(self):
         """Make the render stream wait for every outstanding transfer (call before the closing synchronisation)."""
-        if self.mode == "views" and self.transport == "nccl":
-            self.stream.wait_stream(self.comm)
-        elif self.mode == "views" and self.rank == 0:
+        if self.transport == "nccl":
+            if self.mode == "views":
+                self.stream.wait_stream(self.comm)
+        elif self.rank == 0:
             self.stream.wait_stream(self.side)
 
+    def last_set(self) -> int:
+        """Index of the set the most recent frame went to."""
+        return (self.step - 1) % 2
+
     def view_slot(self, b: int, r: int):
-        """(colour int32 HxW, depth f32 HxW) of rank r's frame in slot set b, on GPU 0."""
+        """(colour int32 HxW, depth f32 HxW) of rank r's frame in slot set b, on GPU 0 (views)."""
         return self.slots[b][0][r - 1], self.slots[b][1][r - 1]
+
+    def frame(self, b: int):
+        """(colour int32 HxW, depth f32 HxW) of the composited frame of set b, on GPU 0 (bands, peer transport)."""
+        return self.slots[b][0][0], self.slots[b][1][0]
+
+    def release(self):
+        """Detach the context from the shared targets (before closing it)."""
+        if self.transport == "peer":
+            self.dev.set_output(None, None)
+            self.dev.set_dirty_map(None)

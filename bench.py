@@ -234,6 +234,116 @@ def _emit(line: dict):
         sys.stdout.flush()
 
 
+def _time_steps(torch, stream, barrier, step, n):
+    """n steps between two CUDA events on the context stream, barrier + synchronize on both sides. Returns ms per step."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(n):
+        step(i)
+    e1.record(stream)
+    barrier()
+    return e0.elapsed_time(e1) / n
+
+
+def _max_over_ranks(torch, dist, x: float) -> float:
+    if not dist:
+        return x
+    t = torch.tensor([x], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _parity_counts(torch, c_a, d_a, c_b, d_b):
+    """Bit comparison of two framebuffers on the device: (coverage mismatches, depth words that differ, max colour byte difference)."""
+    cov = int((torch.isfinite(d_a) != torch.isfinite(d_b)).sum().item())
+    dbits = int((d_a.contiguous().view(torch.int32) != d_b.contiguous().view(torch.int32)).sum().item())
+    ba = c_a.contiguous().view(torch.uint8).to(torch.int16)
+    bb = c_b.contiguous().view(torch.uint8).to(torch.int16)
+    cmax = int((ba - bb).abs().max().item()) if ba.numel() else 0
+    return cov, dbits, cmax
+
+
+def _run_multi(torch, dist, api, multi, sc, rank, world, local, mode, transport, steps, warmup, views_total=None, check=True):
+    """One multi-GPU (or, at world == 1, single-GPU) figure: K timed frames of `sc` sharded by `mode`, then — on GPU 0, outside the
+    timed region — a bit comparison of what landed there with GPU 0's own single-GPU render of the same view / frame.
+    views_total: every rank renders its share of that many camera views per step (BASELINE config 5's 64 views) instead of one."""
+    W, H = sc.width, sc.height
+    band = multi.band_rows(H, world)[rank] if (world > 1 and mode == "bands") else None
+    dev = api.Device(W, H, device=local, sampler=sc.sampler, band=band)
+    mesh = dev.load_scene(sc)
+    dev.set_overlap(True)
+    stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local))
+    comp = multi.Compositor(dev, rank, world, mode, band, stream, transport=transport) if world > 1 else None
+    n_cams = max(world, 8) if views_total is None else views_total
+    my_views = [rank] if views_total is None else multi.views_for_rank(rank, world, views_total)
+    if mode == "bands":
+        my_views = [0]
+    cams = {v: S.view_matrix_for(v, n_cams, W, H) for v in my_views} if mode == "views" else {0: (sc.view_proj, sc.cam_pos)}
+
+    def frame(v):
+        if len(cams) > 1 or mode == "views":
+            dev.set_uniforms(*cams[v])
+        if comp:
+            comp.begin_step()
+        if not comp or comp.clears_own_target:
+            dev.clear(0xFF000000, float("inf"))
+        dev.draw_mesh(mesh, sc.model)
+        if comp:
+            comp.composite()
+
+    def step(_i):
+        for v in my_views:
+            frame(v)
+
+    def barrier():
+        if comp:
+            comp.finish()
+        dev.sync()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(warmup):
+        step(i)
+    ms = _max_over_ranks(torch, dist, _time_steps(torch, stream, barrier, step, steps))
+    parity = None
+    if check and comp and transport == "peer":
+        # GPU 0 re-renders, on its own, what the other ranks stored into its memory during the last frame, and compares bit for bit
+        cov = dbits = cmax = 0
+        if rank == 0:
+            b = comp.last_set()
+            ref = api.Device(W, H, device=local, sampler=sc.sampler)
+            rmesh = ref.load_scene(sc)
+            rc, rd = multi.framebuffer_tensors(ref)
+            targets = ([(r, comp.view_slot(b, r)) for r in range(1, world)] if mode == "views" else [(0, comp.frame(b))])
+            for r, (tc, td) in targets:
+                if mode == "views":
+                    last_view = multi.views_for_rank(r, world, views_total)[-1] if views_total else r
+                    ref.set_uniforms(*S.view_matrix_for(last_view, n_cams, W, H))
+                ref.clear(0xFF000000, float("inf"))
+                ref.draw_mesh(rmesh, sc.model)
+                ref.sync()
+                torch.cuda.synchronize()
+                a, b_, c_ = _parity_counts(torch, tc, td, rc, rd)
+                cov += a; dbits += b_; cmax = max(cmax, c_)
+            ref.close()
+        parity = {"coverage_mismatch": cov, "depth_bit_mismatch": dbits, "color_max_diff": cmax,
+                  "compared": (f"{world - 1} view slot(s)" if mode == "views" else "the composited frame") +
+                              " on GPU 0 against GPU 0's own single-GPU render, last frame, outside the timed region"}
+    if dist:
+        dist.barrier()
+    if comp:
+        comp.release()
+    dev.close()
+    frames = len(my_views) if mode == "views" else 1
+    total_frames = (views_total if views_total else world) if mode == "views" else 1
+    return {"ms_per_step": ms, "frames_per_step": total_frames, "frames_per_rank": frames,
+            "value": sc.n_faces * total_frames / (ms * 1e-3) / 1e6, "unit": "Mtri/s", "frames_per_s": total_frames / (ms * 1e-3),
+            "composite_parity": parity}
+
+
 def main():
     _quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -246,6 +356,7 @@ def main():
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"], help="composite to GPU 0: fused peer stores or NCCL gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the BASELINE config 5 figures (8K bands, 64 views) and the sustained pass")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -279,7 +390,7 @@ def main():
     stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local))
     comp = multi.Compositor(dev, rank, world, args.mode, band, stream, transport=args.transport) if world > 1 else None
 
-    def step():
+    def step(_i=0):
         if comp:
             comp.begin_step()
         if not comp or comp.clears_own_target:
@@ -297,57 +408,80 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    # ---- primary timed region: K steps with consecutive frames overlapped (axr_set_overlap(1): the geometry stages of frame i+1
+    #      run on a second stream beside the tile kernel of frame i — the mode the library is meant to be driven in)
+    dev.set_overlap(True)
     for _ in range(args.warmup):
         step()
     barrier()
     stats = dev.stats()
-    launches_per_step = int(stats["kernel_launches"]) + 1 + (comp.launches_per_step if comp else 0)
-
+    launches_per_step = int(stats["kernel_launches"]) + (1 if (not comp or comp.clears_own_target) else 0) + (comp.launches_per_step if comp else 0)
     clocks = ClockSampler(local)
     clocks.start()
-    dev.set_profiling(True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
+    ms_step = _max_over_ranks(torch, dist, _time_steps(torch, stream, barrier, step, args.steps))
+
+    # ---- the same K steps serially (overlap off: every kernel of a frame on one stream, in launch order) with a CUDA event pair
+    #      around every kernel: per-kernel durations for the roofline (measured live, on the stream the kernels are launched on)
+    dev.set_overlap(False)
+    for _ in range(2):
         step()
-    if comp:
-        comp.finish()
-    e1.record(stream)
-    barrier()
-    ms_total = e0.elapsed_time(e1)
+    dev.set_profiling(True)
+    ms_serial = _max_over_ranks(torch, dist, _time_steps(torch, stream, barrier, step, args.steps))
     ktimes, kdraws = dev.kernel_times()
     dev.set_profiling(False)
-    clk = clocks.stop()
-    ms_step = ms_total / args.steps
-    if dist:
-        t = torch.tensor([ms_step], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step = float(t.item())
 
-    # ---- the same K steps once more with consecutive draws overlapped (axr_set_overlap): extra figure, single GPU only
-    ms_overlap = None
-    if world == 1:
-        dev.set_overlap(True)
-        for _ in range(args.warmup):
+    # ---- sustained pass: the primary loop again for >= 0.6 s, so that the clock / power samples below describe load, not idle
+    dev.set_overlap(True)
+    sustained = None
+    if not args.no_extras:
+        n_sus = int(min(20000, max(args.steps, 0.6e3 / max(ms_step, 1e-3))))
+        for _ in range(2):
             step()
-        barrier()
-        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        o0.record(stream)
-        for _ in range(args.steps):
-            step()
-        o1.record(stream)
-        barrier()
-        ms_overlap = o0.elapsed_time(o1) / args.steps
-        dev.set_overlap(False)
+        ms_sus = _max_over_ranks(torch, dist, _time_steps(torch, stream, barrier, step, n_sus))
+        sustained = {"steps": n_sus, "ms_per_step": ms_sus, "note": "same loop as the timed region, run long enough for nvidia-smi to sample it"}
+    clk = clocks.stop()
+
+    # ---- multi-GPU: what landed on GPU 0 during the last frame, bit-compared with GPU 0's own render (outside the timed region)
+    composite_parity = None
+    if comp and args.transport == "peer":
+        cov = dbits = cmax = 0
+        if rank == 0:
+            b = comp.last_set()
+            ref = api.Device(W, H, device=local, sampler=sc.sampler)
+            rmesh = ref.load_scene(sc)
+            rc, rd = multi.framebuffer_tensors(ref)
+            targets = ([(r, comp.view_slot(b, r)) for r in range(1, world)] if args.mode == "views" else [(0, comp.frame(b))])
+            for r, (tc, td) in targets:
+                if args.mode == "views":
+                    ref.set_uniforms(*S.view_matrix_for(r, max(world, 8), W, H))
+                ref.clear(0xFF000000, float("inf"))
+                ref.draw_mesh(rmesh, sc.model)
+                ref.sync()
+                torch.cuda.synchronize()
+                a_, b_, c_ = _parity_counts(torch, tc, td, rc, rd)
+                cov += a_; dbits += b_; cmax = max(cmax, c_)
+            ref.close()
+        composite_parity = {"coverage_mismatch": cov, "depth_bit_mismatch": dbits, "color_max_diff": cmax,
+                            "compared": (f"{world - 1} view slot(s)" if args.mode == "views" else "the composited frame") +
+                                        " on GPU 0 against GPU 0's own single-GPU render of the same view, last frame, outside the timed region"}
+        if dist:
+            dist.barrier()
 
     # ---- FP32 issue micro-benchmark: the measured issue rate turns the kernels' instruction counts into a floor
     fp32_rate, ffma_rate = dev.measure_fp32_issue()
 
     # covered pixels (for the texture term of the algorithmic bytes) — outside the timed region
-    _, depth = dev.resolve()
-    y0, y1 = dev.band
-    covered = int(np.isfinite(depth[y0:y1]).sum())
+    if comp and args.transport == "peer" and args.mode == "bands":
+        covered = 0
+        if rank == 0:
+            covered = int(torch.isfinite(comp.frame(comp.last_set())[1]).sum().item())
+    else:
+        if comp and args.transport == "peer" and rank != 0:
+            covered = 0   # this rank's pixels live in GPU 0's slot; rank 0's own view is counted below
+        else:
+            _, depth = dev.resolve()
+            y0, y1 = dev.band
+            covered = int(np.isfinite(depth[y0:y1]).sum())
 
     units = T * (world if (world > 1 and args.mode == "views") else 1)  # faces processed per step by the whole job
     value = units / (ms_step * 1e-3) / 1e6
@@ -375,31 +509,37 @@ def main():
             "higher_is_better": True, "scaling": "weak" if args.mode == "views" else "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_label(args.workload, sc),
-                       "step": "axr_clear + axr_draw_mesh (5 kernels) on one stream, all inputs resident in HBM",
+                       "step": "axr_clear + axr_draw_mesh, all inputs resident in HBM; consecutive frames overlapped (axr_set_overlap(1): vertex + "
+                               "setup kernels of frame i+1 on a second stream beside the tile kernel of frame i). `serial` holds the same K steps "
+                               "with everything on one stream, which is what kernel_ms / roofline time",
                        "l2": "working set (mesh %.0f MB + textures + 8 B/px keys + framebuffer) exceeds the 126 MB L2; no explicit flush"
                              % ((sc.vertices.nbytes + sc.indices.nbytes) / 1e6),
+                       "color_math": "fast (fused multiply-adds + SFU approximations in the colour arithmetic only; coverage, depth and texel "
+                                     "selection exact; 8-bit colour within 1 LSB of the reference, the tolerance BASELINE.json states)",
                        "parallelism": ("1 GPU" if world == 1 else f"{args.mode} x{world}: " +
                                        (("one camera view of the replicated scene per GPU; the tile kernel of every rank stores its covered pixels "
                                          "(colour + depth) straight into a per-view slot in GPU 0's memory through a CUDA-IPC peer mapping over "
-                                         "NVLink; GPU 0 clears the slots; one 4-byte NCCL all-reduce per frame orders frames"
+                                         "NVLink and flags the tiles it touched; GPU 0 re-clears only those tiles; one 4-byte NCCL all-reduce per "
+                                         "frame orders frames"
                                          if args.transport == "peer" else
                                          "one camera view of the replicated scene per GPU; every finished frame (colour + depth, 8 B/px) is gathered to "
                                          "GPU 0 with NCCL send/recv on a second stream while the next frame renders (double-buffered)")
                                         if args.mode == "views" else
-                                        "16-px-aligned screen bands of one frame, replicated geometry stages; every rank's clear + resolve "
-                                        "stores go straight into GPU 0's framebuffer through a CUDA-IPC peer mapping over NVLink")),
+                                        "16-px-aligned screen bands of one frame, replicated geometry stages; every rank's covered pixels go straight "
+                                        "into a frame in GPU 0's memory (CUDA-IPC peer mapping over NVLink), GPU 0 re-clears the touched tiles")),
                        "parity_mode": "nearest sampling == reference; bilinear is an extension checked against oracle/axr_oracle.c"},
             "gpu_launches": launches_per_step * args.steps,
+            "serial": {"ms_per_step": ms_serial, "value": units / (ms_serial * 1e-3) / 1e6, "unit": "Mtri/s",
+                       "note": "same K steps with axr_set_overlap(0) and an event pair around every kernel"},
+            "sustained": sustained,
             "kernel_ms": kavg, "draw_ms": draw_ms, "draw_stats": stats, "covered_pixels": covered,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": traffic, "algorithmic_bytes": per_stage[dom], "kernel_ms": dom_ms, "peak_source": peak_src},
-            "roofline_frame": {"bound": "hbm", "algorithmic_bytes": b_alg, "achieved": b_alg / (draw_ms * 1e-3) / 1e9,
-                               "peak": peak, "unit": "GB/s", "frac": b_alg / (draw_ms * 1e-3) / 1e9 / peak,
-                               "note": "BASELINE.md §4 figure of record: B_alg / sum of the five draw kernels' event times "
-                                       "(clear excluded); with the clear kernel: frac = %.4f" % (b_alg / (ms_step * 1e-3) / 1e9 / peak)},
-            "overlapped_draws": (None if ms_overlap is None else
-                                 {"ms_per_step": ms_overlap, "value": units / (ms_overlap * 1e-3) / 1e6, "unit": "Mtri/s",
-                                  "note": "same K steps with axr_set_overlap(1): geometry of frame i+1 beside the tile kernel of frame i"}),
+            "roofline_frame": {"bound": "hbm", "algorithmic_bytes": b_alg, "achieved": b_alg / (ms_step * 1e-3) / 1e9,
+                               "peak": peak, "unit": "GB/s", "frac": b_alg / (ms_step * 1e-3) / 1e9 / peak,
+                               "note": "BASELINE.md §4 figure of record: B_alg / ms_per_step of the timed region (clear included, frames "
+                                       "overlapped); serial, draw kernels only: frac = %.4f" % (b_alg / (draw_ms * 1e-3) / 1e9 / peak if draw_ms else 0.0)},
+            "composite_parity": composite_parity,
             "clocks": clk,
         }
         # per-kernel binding bound = max(T_hbm, T_fp32_issue): instruction counts are ncu's for this workload (profiles/traffic.json)
@@ -409,22 +549,38 @@ def main():
         except Exception:
             counters = {}
         issue = {"measured_fmul_fadd_Gwinst_per_s": fp32_rate / 1e9, "measured_ffma_Gwinst_per_s": ffma_rate / 1e9,
-                 "nominal_Gwinst_per_s": 148 * 4 * 1.965, "unit_note": "one warp-instruction = 32 lanes; the path runs FMUL+FADD (no FMA contraction)"}
+                 "nominal_Gwinst_per_s": 148 * 4 * 1.965, "unit_note": "one warp-instruction = 32 lanes"}
         per_kernel = {}
         for k, c in counters.items():
             t_issue = c["warp_inst"] / fp32_rate * 1e3
             t_hbm = per_stage.get(k, 0) / (peak * 1e9) * 1e3
             per_kernel[k] = {"warp_inst": c["warp_inst"], "t_issue_ms": t_issue, "t_hbm_ms": t_hbm, "binding": "fp32_issue" if t_issue > t_hbm else "hbm",
                              "measured_ms": kavg.get(k), "frac_of_binding": (max(t_issue, t_hbm) / kavg[k]) if kavg.get(k) else None}
-            if c.get("note"):
-                per_kernel[k]["note"] = c["note"]
         issue["per_kernel"] = per_kernel
         if per_kernel:
-            t_bind = sum(max(v["t_issue_ms"], v["t_hbm_ms"]) for v in per_kernel.values())
-            issue["frame"] = {"sum_binding_ms": t_bind, "draw_ms": draw_ms, "frac_of_binding": t_bind / draw_ms if draw_ms else None,
-                              "note": "issue-slot utilisation of the instruction stream the kernels execute (ncu counts), not an algorithmic "
-                                      "minimum: the HBM figure of record is roofline_frame"}
+            issue["note"] = ("issue-slot utilisation of the instruction stream the kernels execute (ncu counts), not an algorithmic "
+                             "minimum and not a roofline fraction: the figure of record is roofline_frame")
         line["fp32_issue"] = issue
+
+    if comp:
+        comp.release()
+
+    # ---- BASELINE config 5 as written (extra figures, same process group): the C3 scene at 8K split into screen bands, and 64 camera
+    #      views (64 / N per GPU) composited to GPU 0 — each with its own composite parity check
+    extras = {}
+    if not args.no_extras and args.workload == "c3":
+        dev.close()
+        dev = None
+        k5 = max(3, args.steps // 4)
+        sc8k = build_workload("c5")
+        extras["bands_c5"] = _run_multi(torch, dist, api, multi, sc8k, rank, world, local, "bands", "peer", k5, 3)
+        extras["bands_c5"]["workload"] = workload_label("c5", sc8k)
+        del sc8k
+        extras["views64"] = _run_multi(torch, dist, api, multi, sc, rank, world, local, "views", "peer", max(1, k5 // 2), 1, views_total=64)
+        extras["views64"]["workload"] = "64 camera views (yaw = i*2pi/64) of " + workload_label(args.workload, sc)
+        if rank == 0:
+            line["bands_c5"] = extras["bands_c5"]
+            line["views64"] = extras["views64"]
 
     # ---- e2e: the reference-facing call (TiledPipeline.drawMesh on a HOST framebuffer) with H2D/D2H inside the timed region
     if not args.no_e2e:
@@ -440,7 +596,9 @@ def main():
         tex = [api.Texture(t) if t is not None else None for t in sc.textures]
         mat = api.Material("m0", tex[0], tex[2], tex[1], tex[3], tex[4], sc.specular_exponent)
         hmesh = api.Mesh(sc.vertices, sc.indices, {"m0": mat})
-        dev.close()  # free HBM held by the device-resident arm
+        if dev is not None:
+            dev.close()  # free HBM held by the device-resident arm
+            dev = None
         n_e2e = max(3, min(args.steps, 10))
 
         def e2e_step():
@@ -457,23 +615,18 @@ def main():
             e2e_step()  # first call uploads and caches the mesh (the reference reads its host Mesh on every call)
         torch.cuda.synchronize()
         e2e_ms = sum(e2e_step() for _ in range(n_e2e)) * 1e3 / n_e2e
-        if dist:
-            t = torch.tensor([e2e_ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms = float(t.item())
+        e2e_ms = _max_over_ranks(torch, dist, e2e_ms)
+        covered_e2e = int(np.isfinite(fb.getDepthData()).sum())
         if rank == 0:
             line["e2e"] = {"value": units / (e2e_ms * 1e-3) / 1e6, "unit": "Mtri/s", "ms_per_step": e2e_ms, "steps": n_e2e,
-                           "h2d_bytes_per_step": int(pipe.last_h2d_bytes), "d2h_bytes_per_step": int(covered) * 8,
-                           "call": "TiledPipeline.drawMesh(model, mesh) on a pinned host Framebuffer (axr_draw_mesh_host): H2D of the host "
-                                   "depth (4 B/px, the kernel never reads colour), draw, the pixels that pass the depth test stored by the tile "
-                                   "kernel straight into the host arrays (zero-copy, 8 B per updated pixel, 128 B row stores; upload and tile kernel "
-                                   "pipelined in up to 4 row chunks), complete on return; host-side "
-                                   "clearColor/clearDepth before the call are the caller's and untimed, as in the CPU arm; mesh/textures cached "
-                                   "on the device after the first call",
+                           "h2d_bytes_per_step": int(pipe.last_h2d_bytes) + int(covered_e2e) * 4, "d2h_bytes_per_step": int(covered_e2e) * 8,
+                           "call": pipe.host_path_description,
                            "mesh_upload_bytes_first_call": int(sc.vertices.nbytes + sc.indices.nbytes)}
         pipe.device.close()
     elif rank == 0:
         line["e2e"] = None
+    if dev is not None:
+        dev.close()
 
     # ---- CPU baseline (rank 0, N = 1 only): the reference's own thread-pool path on this box's host cores
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

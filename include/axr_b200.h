@@ -114,6 +114,9 @@ int axr_abi_version(void);
 int axr_upload_mesh(axr_ctx* ctx, const float* vertices, uint64_t n_verts, const uint32_t* indices,
                     uint64_t n_faces, const axr_group* groups, uint32_t n_groups, axr_mesh* out);
 int axr_free_mesh(axr_ctx* ctx, axr_mesh mesh);
+/* The reference reads its host Mesh on every drawMesh; here a mesh is uploaded once. A caller that edits vertices in place (same
+ * vertex count, same faces: animation, morphing) re-sends them with this call instead of freeing and re-uploading. */
+int axr_update_mesh_vertices(axr_ctx* ctx, axr_mesh mesh, const float* vertices, uint64_t n_verts);
 /* rgba: w*h*4 bytes, row 0 = image top — what stbi_load(..., STBI_rgb_alpha) returns. */
 int axr_upload_texture(axr_ctx* ctx, const uint8_t* rgba, int w, int h, axr_tex* out);
 int axr_free_texture(axr_ctx* ctx, axr_tex tex);
@@ -156,13 +159,13 @@ int axr_resolve(axr_ctx* ctx, uint8_t* bgra_out, float* depth_out);
  *      reference's strict depth test; never clears. Asynchronous on the context stream. */
 int axr_draw_mesh(axr_ctx* ctx, axr_mesh mesh, const float model[16]);
 /* drawMesh with the reference's exact calling convention: composite onto a HOST framebuffer (Framebuffer::getColorData() /
- * getDepthData()), complete on return. Only the host depth is uploaded (the tile kernel never reads colour); the pixels that
- * pass the depth test are stored by the kernel straight into the host arrays through a zero-copy mapping (pinned memory from
- * axr_host_alloc is mapped already, other memory is page-locked with cudaHostRegister on first use and remembered), so the
- * device -> host traffic is 8 bytes per updated pixel instead of the whole frame. Falls back to upload / draw / resolve when the
- * host memory cannot be mapped. The device-resident framebuffer of the context is left unspecified by this call.
- * Experiment knob, read once at axr_create: AXR_B200_HOST_DEPTH_ZEROCOPY=1 skips the depth upload and lets the merge test read the
- * host depth of the visible pixels through the mapping (same results; timing to be established). */
+ * getDepthData()), complete on return. Nothing is uploaded: the host arrays are mapped into the device's address space (pinned
+ * memory from axr_host_alloc is mapped already, other memory is page-locked with cudaHostRegister on first use and remembered); the
+ * merge test reads the host depth of the visible pixels through the mapping (128 B row reads over PCIe) and the pixels that pass
+ * are stored by the tile kernel straight into the host arrays, 8 bytes per updated pixel. Falls back to upload / draw / resolve
+ * when the host memory cannot be mapped. The device-resident framebuffer of the context is left unspecified by this call.
+ * AXR_B200_HOST_DEPTH_ZEROCOPY=0 (read once at axr_create) uploads the whole host depth plane in row chunks instead of reading it
+ * through the mapping (measured slower on C3: 0.98 against 0.87 ms per call). */
 int axr_draw_mesh_host(axr_ctx* ctx, axr_mesh mesh, const float model[16], uint8_t* bgra, float* depth);
 int axr_sync(axr_ctx* ctx);
 int axr_get_stats(axr_ctx* ctx, axr_stats* out);
@@ -191,6 +194,15 @@ int axr_framebuffer_device(axr_ctx* ctx, void** bgra_dev, void** depth_dev);  /*
 /* Redirect this context's band output into another allocation laid out as a full frame (e.g. GPU 0's framebuffer
  * mapped through CUDA IPC / peer access): the resolve stores then go straight over NVLink. NULL restores the own buffers. */
 int axr_set_output(axr_ctx* ctx, void* bgra_dev, void* depth_dev);
+/* Dirty-tile tracking for composite targets that are re-cleared every frame (multi-GPU views / bands: GPU 0 owns the targets, the
+ * other GPUs store into them over NVLink). With a dirty map set, every draw flags the 32x32-pixel tiles it may store into
+ * (axr_dirty_map_entries() 32-bit flags, row-major tiles, ceil(W/32) per row; the map may live on another GPU);
+ * axr_clear_dirty_tiles then clears only the flagged tiles of `count` targets laid out back to back (colour planes of W*H words, depth
+ * planes of W*H floats, maps of axr_dirty_map_entries() flags, each group contiguous) and resets the flags — the clear of a sparsely
+ * covered frame touches a fraction of it. stream: cudaStream_t to launch on, NULL = the context stream. */
+int axr_dirty_map_entries(const axr_ctx* ctx);
+int axr_set_dirty_map(axr_ctx* ctx, void* dirty_dev);
+int axr_clear_dirty_tiles(axr_ctx* ctx, void* bgra_dev, void* depth_dev, void* dirty_dev, int count, uint32_t packed_argb, float depth, void* stream);
 /* Overlap consecutive draws: with overlap on, the geometry stages (vertex, setup, bins) of draw i+1 are enqueued on a second,
  * higher-priority stream and run beside the tile / shading kernel of draw i (two sets of per-draw buffers alternate). Results
  * are identical; throughput of back-to-back draws rises by a few percent (C3: 0.464 -> 0.433 ms per frame). Default: off, which

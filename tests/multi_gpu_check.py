@@ -32,9 +32,10 @@ for transport in ("peer", "nccl"):
     mesh = dev.load_scene(base)
     stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local))
     comp = multi.Compositor(dev, rank, world, "bands", band, stream, transport=transport)
-    for _ in range(3):   # several frames: exercises clear + redraw into the shared framebuffer
+    for _ in range(5):   # several frames: exercises the (dirty-tile) clears + redraw into the shared targets, both sets
         comp.begin_step()
-        dev.clear()
+        if comp.clears_own_target:
+            dev.clear()
         dev.draw_mesh(mesh, base.model)
         comp.composite()
     comp.finish()
@@ -42,16 +43,15 @@ for transport in ("peer", "nccl"):
     torch.cuda.synchronize()
     dist.barrier()
     if rank == 0:
-        color, depth = multi.framebuffer_tensors(dev)
-        c = color.cpu().numpy().view(np.uint8).reshape(H, W, 4)
-        d = depth.cpu().numpy()
+        color, depth = comp.frame(comp.last_set()) if transport == "peer" else multi.framebuffer_tensors(dev)
+        c = color.contiguous().cpu().numpy().view(np.uint8).reshape(H, W, 4)
+        d = depth.contiguous().cpu().numpy()
         c0, d0 = full_frame(base)
         same = np.array_equal(c, c0) and np.array_equal(d.view(np.uint32), d0.view(np.uint32))
         print(f"bands/{transport}: composite == single-GPU frame: {same}", flush=True)
         ok &= same
     dist.barrier()
-    if transport == "peer" and rank != 0:
-        dev.set_output(None, None)
+    comp.release()
     dev.close()
 # ---- views
 for transport in ("peer", "nccl"):
@@ -76,8 +76,8 @@ for transport in ("peer", "nccl"):
             other = S.Scene("t", W, H, v, f, S.SHADER_PHONG, model=base.model, textures=base.textures)
             other.view_proj, other.cam_pos = S.view_matrix_for(r, 8, W, H)
             c0, d0 = full_frame(other)
-            # peer: the last frame (step 4) went to set 0 and set 1 has been cleared for the next one; nccl: both sets hold frames
-            for b in ((0,) if transport == "peer" else (0, 1)):
+            # peer: the last frame went to set last_set() and the other set has been cleared for the next one; nccl: both sets hold frames
+            for b in ((comp.last_set(),) if transport == "peer" else (0, 1)):
                 cs, ds = (comp.view_slot(b, r) if transport == "peer" else (comp.slots[b][0][r - 1], comp.slots[b][1][r - 1]))
                 c = cs.contiguous().cpu().numpy().view(np.uint8).reshape(H, W, 4)
                 d = ds.contiguous().cpu().numpy()
@@ -85,6 +85,7 @@ for transport in ("peer", "nccl"):
                 print(f"views/{transport}: slot set {b} view {r} == single-GPU render: {same}", flush=True)
                 ok &= same
     dist.barrier()
+    comp.release()
     dev.close()
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.broadcast(flag, 0)
