@@ -93,6 +93,9 @@ struct axr_ctx {
 		unsigned* n_records = nullptr;
 		unsigned* clip_tiles = nullptr;      // tiles with pixels owned by clipped faces (k_tile_shade -> k_shade_clipped)
 		unsigned* n_clip_tiles = nullptr;
+		unsigned* clip_faces = nullptr;      // faces that need the clipper (k_setup_raster -> k_setup_clipped); one entry per face of the largest mesh drawn
+		unsigned long long clip_cap = 0;
+		unsigned* n_clip_faces = nullptr;
 		DrawStatus* d_status = nullptr;
 		DrawStatus* h_status = nullptr;      // pinned + mapped: written by k_scan_tiles
 		DrawStatus* h_status_dev = nullptr;  // device-side alias of h_status
@@ -325,6 +328,14 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 	// ---- geometry stages on geom_stream. The slot was last used two draws ago: wait until that draw's tile kernel has
 	//      consumed it (it resets the keys, flags and cursors it read).
 	cudaStream_t g = (ctx->overlap && !peel) ? ctx->geom_stream : ctx->stream;
+	if (sl.clip_cap < m.n_faces) {  // first draw of a mesh larger than any before it on this slot
+		CU(cudaStreamSynchronize(ctx->geom_stream));
+		CU(cudaStreamSynchronize(ctx->stream));
+		if (sl.clip_faces) CU(cudaFree(sl.clip_faces));
+		sl.clip_faces = nullptr; sl.clip_cap = 0;
+		CU(cudaMalloc(&sl.clip_faces, (size_t)m.n_faces * 4));
+		sl.clip_cap = m.n_faces;
+	}
 	if (sl.used) CU(cudaStreamWaitEvent(g, sl.shade_done, 0));
 	uint64_t launches = 0;
 	prof_mark(ctx, g);
@@ -332,7 +343,7 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 		// at least sizeof(DrawStatus)/4 threads: the kernel also zeroes the draw's counters
 		const unsigned long long threads = m.n_verts > sizeof(DrawStatus) / 4 ? m.n_verts : sizeof(DrawStatus) / 4;
 		k_vertex_xform<<<(unsigned)((threads + 255) / 256), 256, 0, g>>>(m.pos, m.n_verts, u.mvp, (float)ctx->fp.W, (float)ctx->fp.H, m.sv[si],
-		                                                                sl.d_status, sl.n_records, sl.n_clip_tiles);
+		                                                                sl.d_status, sl.n_records, sl.n_clip_tiles, sl.n_clip_faces);
 		++launches;
 	}
 	prof_mark(ctx, g);
@@ -344,16 +355,20 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 	so.small_dim = tput ? SMALL_DIM_TPUT : SMALL_DIM_LAT;
 	so.small_area = tput ? SMALL_AREA_TPUT : SMALL_AREA_LAT;
 	so.floor = peel ? ctx->peel_floor : nullptr;
+	so.clip_faces = sl.clip_faces; so.n_clip_faces = sl.n_clip_faces;
+	so.n_chunks = 0; so.swz_rows = 0;
 	const bool bins = peel || !m.no_bins;
 	so.bins_enabled = bins ? 1 : 0;
 	{
-		const unsigned grid = (unsigned)((m.n_faces + SETUP_THREADS - 1) / SETUP_THREADS);
+		const unsigned grid = m.n_faces ? setup_grid(m.n_faces, so.n_chunks, so.swz_rows) : 0u;
 		if (grid) {
-			if (peel) k_setup_raster<true><<<grid, SETUP_THREADS, 0, g>>>(mv, m.sv[si], u.mvp, ctx->fp, so);
-			else k_setup_raster<false><<<grid, SETUP_THREADS, 0, g>>>(mv, m.sv[si], u.mvp, ctx->fp, so);
+			if (peel) k_setup_raster<true><<<grid, SETUP_THREADS, 0, g>>>(mv, m.sv[si], ctx->fp, so);
+			else k_setup_raster<false><<<grid, SETUP_THREADS, 0, g>>>(mv, m.sv[si], ctx->fp, so);
 			++launches;
 		}
-		k_fold_status<<<1, FOLD_THREADS, 0, g>>>(sl.d_status, sl.h_status_dev, so.bins_enabled);
+		// the faces that need the clipper + (its last CTA) the fold of the draw's counters into the status the host reads
+		if (peel) k_setup_clipped<true><<<CLIPSETUP_CTAS, CLIPSETUP_THREADS, 0, g>>>(mv, u.mvp, ctx->fp, so, sl.h_status_dev);
+		else k_setup_clipped<false><<<CLIPSETUP_CTAS, CLIPSETUP_THREADS, 0, g>>>(mv, u.mvp, ctx->fp, so, sl.h_status_dev);
 		++launches;
 	}
 	prof_mark(ctx, g);
@@ -541,6 +556,8 @@ int axr_create(const axr_config* cfg, axr_ctx** out) {
 		CUC(cudaMalloc(&sl.clip_tiles, nt * 4));
 		CUC(cudaMalloc(&sl.n_clip_tiles, 4));
 		CUC(cudaMemsetAsync(sl.n_clip_tiles, 0, 4, c->stream));
+		CUC(cudaMalloc(&sl.n_clip_faces, 4));
+		CUC(cudaMemsetAsync(sl.n_clip_faces, 0, 4, c->stream));
 		CUC(cudaMalloc(&sl.d_status, sizeof(DrawStatus)));
 		CUC(cudaHostAlloc(&sl.h_status, 64, cudaHostAllocMapped));
 		CUC(cudaHostGetDevicePointer(&sl.h_status_dev, sl.h_status, 0));
@@ -575,6 +592,7 @@ void axr_destroy(axr_ctx* ctx) {
 	for (auto& sl : ctx->slot) {
 		cudaFree(sl.vis); cudaFree(sl.tile_touched); cudaFree(sl.tile_count); cudaFree(sl.bin_start); cudaFree(sl.items);
 		cudaFree(sl.records); cudaFree(sl.n_records); cudaFree(sl.d_status); cudaFree(sl.clip_tiles); cudaFree(sl.n_clip_tiles);
+		cudaFree(sl.clip_faces); cudaFree(sl.n_clip_faces);
 		if (sl.h_status) cudaFreeHost(sl.h_status);
 		if (sl.status_event) cudaEventDestroy(sl.status_event);
 		if (sl.geom_done) cudaEventDestroy(sl.geom_done);

@@ -58,7 +58,7 @@ struct DrawStatus {
 	unsigned long long bin_refs;                                                      // refs wanted
 	unsigned overflow;                                                                // OVF_* bits
 	unsigned pad;
-	// per-warp partial counters are spread over STAT_STRIPES slots (no single hot address); k_fold_status folds them
+	// per-warp partial counters are spread over STAT_STRIPES slots (no single hot address); the last CTA of k_setup_clipped folds them
 	unsigned stripes[4][512];
 };
 constexpr int STAT_STRIPES = 512;
@@ -180,10 +180,11 @@ __global__ void __launch_bounds__(256) k_fp32_peak(float* out, float a, float b,
 // It also zeroes the draw's device counters (k_setup_raster, the next kernel on the stream, is their first user), which
 // saves two memset nodes per draw.
 __global__ void __launch_bounds__(256) k_vertex_xform(const float4* __restrict__ pos, unsigned long long n, m4 mvp, float fW,
-                                                      float fH, float4* __restrict__ sv, DrawStatus* status, unsigned* n_records, unsigned* n_clip_tiles) {
+                                                      float fH, float4* __restrict__ sv, DrawStatus* status, unsigned* n_records, unsigned* n_clip_tiles,
+                                                      unsigned* n_clip_faces) {
 	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < sizeof(DrawStatus) / 4) reinterpret_cast<unsigned*>(status)[i] = 0u;
-	if (i == 0) { *n_records = 0u; *n_clip_tiles = 0u; }
+	if (i == 0) { *n_records = 0u; *n_clip_tiles = 0u; *n_clip_faces = 0u; }
 	if (i >= n) return;
 	float4 p = __ldg(pos + i);
 	v4 c = mul(mvp, V4(p.x, p.y, p.z, 1.0f));
@@ -206,8 +207,11 @@ struct SetupOut {
 	DrawStatus* status;
 	int small_dim, small_area;   // direct-raster limits of this draw
 	int bins_enabled;            // 0: the draw was issued without the bin kernels (no triangle of this mesh needed them last time);
-	                             //    a triangle that does need them is counted, k_fold_status raises OVF_NEED_BINS and the host re-issues the draw with bins
+	                             //    a triangle that does need them is counted, k_setup_clipped raises OVF_NEED_BINS and the host re-issues the draw with bins
 	const unsigned long long* floor;  // depth peeling only (PEEL): per pixel, keys <= floor have been dealt with
+	unsigned* clip_faces;        // faces that need the clipper: appended by k_setup_raster, worked through by k_setup_clipped
+	unsigned* n_clip_faces;      // (capacity: the face count of the mesh, so the list cannot overflow)
+	unsigned n_chunks, swz_rows; // CTA -> face chunk interleave of k_setup_raster (setup_grid())
 };
 constexpr unsigned OVF_RECORDS = 1u, OVF_REFS = 2u, OVF_NEED_BINS = 4u;
 
@@ -221,8 +225,11 @@ __device__ __forceinline__ void touch_tile(const FrameParams& fp, const SetupOut
 	if (*tf == 0u) *tf = 1u;
 }
 
+#ifndef AXR_SETUP_ABLATE
+#define AXR_SETUP_ABLATE 0  // measurement only (tools/build_variants.py): 1 = loads + cull, 2 = + triangle setup, 3 = + coverage loop without the reductions
+#endif
 #ifndef AXR_SETUP_LOOP
-#define AXR_SETUP_LOOP 0  // 0: closed-form coverage() per pixel (C3: 170 us); 1: row terms hoisted (spills at 32 registers, row updates diverge: 209 us)
+#define AXR_SETUP_LOOP 1  // 1: runs x rows x pixels with the run / row terms hoisted (C3: 177 us; 2: four pixels per step, branch-free: 195 us); 0: closed-form coverage() per pixel in one counted loop
 #endif
 
 // Exact coverage + visibility keys of a triangle whose pixel box is small (at most 12 x 12, 64 px), by the thread that set it up.
@@ -239,46 +246,70 @@ __device__ __forceinline__ bool raster_small(const FrameParams& fp, const SetupO
 		if constexpr (PEEL) {
 			if (!(key > o.floor[(unsigned)py * (unsigned)fp.W + (unsigned)px])) return;
 		}
+#if AXR_SETUP_ABLATE != 3
 		atomicMin(slot, key);  // result unused -> RED.MIN.64, fire and forget
+#endif
 		any = true;
 	};
-	const int bw = s.X1 - s.X0, bh = s.Y1 - s.Y0;
-	int px = s.X0, py = s.Y0;
 #if AXR_SETUP_LOOP == 0
 	// One counter over the whole pixel box with the closed-form coverage() per pixel
+	const int bw = s.X1 - s.X0, bh = s.Y1 - s.Y0;
+	int px = s.X0, py = s.Y0;
 	for (int i = bw * bh; i > 0; --i) {
 		float c0, c1, c2;
 		if (coverage(s, px, py, c0, c1, c2)) hit(px, py, c0, c1, c2);
 		if (++px == s.X1) { px = s.X0; ++py; }
 	}
 #else
-	// The same arithmetic with the terms that are constant along a row kept in registers. The box is at most 12 px wide, so it lies
-	// in at most two of the reference's 16-px tiles: in the first one the reference's row starts at startX = max(tile.startX,
-	// floor(minX)) == X0 (X0 = max(0, floor(minX)) is inside that tile), in the second one at its left edge B. coverage() in
-	// axr_raster.cuh is the specification; every + and * below is the one it performs for the same pixel.
-	const int B = (s.X0 & ~(REF_TILE - 1)) + REF_TILE;
-	const float sxA = small_int_to_f32(s.X0) + 0.5f, sxB = small_int_to_f32(B) + 0.5f;
-	float rA0, rA1, rA2, rB0, rB1, rB2;
-	auto row = [&]() {
-		const float pyc = small_int_to_f32(py) + 0.5f;
-		const float p0 = s.b0 * pyc, p1 = s.b1 * pyc, p2 = s.b2 * pyc;
-		rA0 = s.a0 * sxA + p0 + s.c0; rA1 = s.a1 * sxA + p1 + s.c1; rA2 = s.a2 * sxA + p2 + s.c2;
-		rB0 = s.a0 * sxB + p0 + s.c0; rB1 = s.a1 * sxB + p1 + s.c1; rB2 = s.a2 * sxB + p2 + s.c2;
-	};
-	row();
-	for (int i = bw * bh; i > 0; --i) {
-		const bool inB = px >= B;
-		int d = px - (inB ? B : s.X0);
-		float c0 = inB ? rB0 : rA0, c1 = inB ? rB1 : rA1, c2 = inB ? rB2 : rA2;
-		if (d >= 8) {
-			c0 = c0 + s.a0 * 8.0f; c1 = c1 + s.a1 * 8.0f; c2 = c2 + s.a2 * 8.0f;
-			d -= 8;
+	// coverage() (axr_raster.cuh) is the specification; this walks the same pixels with the terms that do not change hoisted, every
+	// + and * being the one coverage() performs for that pixel. A row of the box splits into at most three RUNS of pixels that share
+	// startX = max(px & ~15, fminx) and the `d >= 8` branch: a run ends at the next 16-px reference tile and, while d < 8, at
+	// startX + 8. Per run: a*sxc; per row of a run: ((a*sxc + b*pyc) + c) [+ a*8]; per pixel: + a*(float)i and the three compares.
+	int xs = s.X0;
+#pragma unroll 1
+	do {
+		const int startX = max(xs & ~(REF_TILE - 1), s.fminx);
+		const bool hi = xs - startX >= 8;  // the second group of eight of the reference's 16-px row
+		int xe = min(s.X1, (xs | (REF_TILE - 1)) + 1);
+		if (!hi) xe = min(xe, startX + 8);
+		const float sxc = small_int_to_f32(startX) + 0.5f;
+		const float p0 = s.a0 * sxc, p1 = s.a1 * sxc, p2 = s.a2 * sxc;
+		const int i0 = hi ? startX + 8 : startX;  // the pixel whose lane index i is 0
+#pragma unroll 1
+		for (int py = s.Y0; py < s.Y1; ++py) {
+			const float pyc = small_int_to_f32(py) + 0.5f;
+			float r0 = p0 + s.b0 * pyc + s.c0, r1 = p1 + s.b1 * pyc + s.c1, r2 = p2 + s.b2 * pyc + s.c2;
+			if (hi) { r0 = r0 + s.a0 * 8.0f; r1 = r1 + s.a1 * 8.0f; r2 = r2 + s.a2 * 8.0f; }
+#if AXR_SETUP_LOOP == 2
+			// four pixels at a time, branch-free: twelve independent chains instead of one pixel's dependent one (the loop is bound by
+			// the latency of its own chain, not by issue slots); the rare covered pixel recomputes its three values in hit4()
+#pragma unroll 1
+			for (int px0 = xs; px0 < xe; px0 += 4) {
+				unsigned m = 0;
+#pragma unroll
+				for (int k = 0; k < 4; ++k) {
+					const float fi = small_int_to_f32(px0 - i0 + k);
+					const float c0 = r0 + s.a0 * fi, c1 = r1 + s.a1 * fi, c2 = r2 + s.a2 * fi;
+					if (c0 >= 0.f && c1 >= 0.f && c2 >= 0.f && px0 + k < xe) m |= 1u << k;
+				}
+				while (m) {
+					const int px = px0 + (__ffs(m) - 1);
+					m &= m - 1;
+					const float fi = small_int_to_f32(px - i0);
+					hit(px, py, r0 + s.a0 * fi, r1 + s.a1 * fi, r2 + s.a2 * fi);
+				}
+			}
+#else
+#pragma unroll 1
+			for (int px = xs; px < xe; ++px) {
+				const float fi = small_int_to_f32(px - i0);
+				const float c0 = r0 + s.a0 * fi, c1 = r1 + s.a1 * fi, c2 = r2 + s.a2 * fi;
+				if (c0 >= 0.f && c1 >= 0.f && c2 >= 0.f) hit(px, py, c0, c1, c2);
+			}
+#endif
 		}
-		const float fi = small_int_to_f32(d);
-		c0 = c0 + s.a0 * fi; c1 = c1 + s.a1 * fi; c2 = c2 + s.a2 * fi;
-		if (c0 >= 0.f && c1 >= 0.f && c2 >= 0.f) hit(px, py, c0, c1, c2);
-		if (++px == s.X1) { px = s.X0; ++py; row(); }
-	}
+		xs = xe;
+	} while (xs < s.X1);
 #endif
 	return any;
 }
@@ -290,11 +321,18 @@ template <bool PEEL, bool DEFER_TOUCH>
 __device__ __forceinline__ unsigned emit_triangle(const FrameParams& fp, const SetupOut& o, float x0, float y0, float x1, float y1,
                                                   float x2, float y2, float z0, float z1, float z2, unsigned ordinal, EmitCounters& cnt) {
 	cnt.tris++;
+#if AXR_SETUP_ABLATE == 1
+	return NO_TOUCH;
+#endif
 	Setup s;
 	if (!setup_triangle(x0, y0, x1, y1, x2, y2, z0, z1, z2, fp.W, fp.y_lo, fp.y_hi, s)) return NO_TOUCH;
 	const int bw = s.X1 - s.X0, bh = s.Y1 - s.Y0;
 	if (bw <= o.small_dim && bh <= o.small_dim && bw * bh <= o.small_area) {
 		cnt.small++;
+#if AXR_SETUP_ABLATE == 2
+		if (s.inv_area == 123.0f) cnt.small++;
+		return NO_TOUCH;
+#endif
 		if (raster_small<PEEL>(fp, o, s, ordinal)) {
 			const int tx0 = s.X0 / GT, ty0 = s.Y0 / GT, tx1 = (s.X1 - 1) / GT, ty1 = (s.Y1 - 1) / GT;  // box <= 12x12 px: at most 2x2 tiles
 			if (DEFER_TOUCH && fp.ntx < 256 && fp.nty < 256)  // strictly: tile (255,255) alone would pack to NO_TOUCH
@@ -305,7 +343,7 @@ __device__ __forceinline__ unsigned emit_triangle(const FrameParams& fp, const S
 		return NO_TOUCH;
 	}
 	cnt.binned++;
-	if (!o.bins_enabled) return NO_TOUCH;  // counted: k_fold_status raises OVF_NEED_BINS and the draw is re-issued with the bin kernels
+	if (!o.bins_enabled) return NO_TOUCH;  // counted: k_setup_clipped raises OVF_NEED_BINS and the draw is re-issued with the bin kernels
 	// warp-aggregated append of the setup record
 	cg::coalesced_group g = cg::coalesced_threads();
 	unsigned base = 0;
@@ -352,7 +390,7 @@ __device__ __noinline__ unsigned setup_clipped_face(const FrameParams& fp, const
 #endif
 constexpr int SETUP_THREADS = AXR_SETUP_THREADS;
 #ifndef AXR_SETUP_MINB
-#define AXR_SETUP_MINB 16  // 32 registers, 64 resident warps
+#define AXR_SETUP_MINB 12  // 40 registers, 48 resident warps (16 x 32 registers spills in the coverage loop: C3 197 against 175 us)
 #endif
 #ifndef AXR_TILE_MINB
 #define AXR_TILE_MINB 4
@@ -374,40 +412,124 @@ __device__ __forceinline__ void publish_status(const DrawStatus* d, DrawStatus* 
 	reinterpret_cast<volatile unsigned long long*>(h)[word] = reinterpret_cast<const volatile unsigned long long*>(d)[word];
 }
 
+#ifndef AXR_SETUP_ROUNDS
+#define AXR_SETUP_ROUNDS 1  // faces per thread
+#endif
+constexpr int SETUP_ROUNDS = AXR_SETUP_ROUNDS;
+constexpr int SETUP_CHUNK = SETUP_THREADS * SETUP_ROUNDS;  // faces per CTA
+#ifndef AXR_SETUP_SWZ_K
+#define AXR_SETUP_SWZ_K 16
+#endif
+#ifndef AXR_SETUP_SWZ_GROUP
+#define AXR_SETUP_SWZ_GROUP 128
+#endif
+constexpr unsigned SETUP_SWZ_K = AXR_SETUP_SWZ_K, SETUP_SWZ_GROUP = AXR_SETUP_SWZ_GROUP;
+// grid of k_setup_raster for n_faces faces; fills the interleave parameters
+inline unsigned setup_grid(unsigned long long n_faces, unsigned& n_chunks, unsigned& swz_rows) {
+	n_chunks = (unsigned)((n_faces + SETUP_CHUNK - 1) / SETUP_CHUNK);
+	swz_rows = 0;
+	if (SETUP_SWZ_K <= 1) return n_chunks;
+	const unsigned groups = (n_chunks + SETUP_SWZ_GROUP - 1) / SETUP_SWZ_GROUP;
+	swz_rows = (groups + SETUP_SWZ_K - 1) / SETUP_SWZ_K;
+	return swz_rows * SETUP_SWZ_K * SETUP_SWZ_GROUP;
+}
+
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+#ifdef __CUDA_ARCH__
+	asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+	(void)p;
+#endif
+}
+
+// A CTA owns SETUP_CHUNK consecutive faces. With SETUP_ROUNDS > 1 it first brings the chunk's indices into shared memory with
+// 16-byte loads (all of them in flight at once), prefetches the screen records they name into L1, and then works through the faces
+// in rounds of one face per thread: the kernel's dependent index -> record latency is paid once per chunk instead of once per face
+// (with one face per thread the load phase is bound by latency x resident warps: loads + cull alone are 70 us of C3's setup kernel).
 template <bool PEEL>
 __global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(const __grid_constant__ MeshView mesh, const float4* __restrict__ sv,
-                                                                const __grid_constant__ m4 mvp, const __grid_constant__ FrameParams fp,
-                                                                const __grid_constant__ SetupOut o) {
-	const unsigned f = blockIdx.x * SETUP_THREADS + threadIdx.x;  // faces < 2^29 (axr_upload_mesh): 32-bit index arithmetic throughout
+                                                                const __grid_constant__ FrameParams fp, const __grid_constant__ SetupOut o) {
 	const unsigned lane = threadIdx.x & 31u;
+	const unsigned nf = (unsigned)mesh.n_faces;  // faces < 2^29 (axr_upload_mesh): 32-bit index arithmetic throughout
+	// CTA -> chunk: the hardware hands out CTAs in index order, so the ~1800 resident ones would all sit in one stretch of the index
+	// buffer, and meshes are laid out coherently: whole stretches are back-facing (their warps only wait for loads) or front-facing
+	// (their warps only compute), the two phases alternate GPU-wide and never overlap. Groups of SETUP_SWZ_GROUP consecutive chunks are
+	// therefore dealt out round-robin over SETUP_SWZ_K distant regions of the mesh.
+	unsigned chunk = blockIdx.x;
+	if (SETUP_SWZ_K > 1) {
+		const unsigned g = blockIdx.x / SETUP_SWZ_GROUP, j = blockIdx.x % SETUP_SWZ_GROUP;
+		chunk = ((g % SETUP_SWZ_K) * o.swz_rows + g / SETUP_SWZ_K) * SETUP_SWZ_GROUP + j;
+		if (chunk >= o.n_chunks) return;
+	}
+	const unsigned base = chunk * SETUP_CHUNK;
 	EmitCounters cnt = {0, 0, 0};
-	unsigned clipped = 0;
-	unsigned touched = NO_TOUCH;
-	if (f < (unsigned)mesh.n_faces) {
-		const unsigned* ip = mesh.idx + 3u * f;
-		const unsigned i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
-		const float4 s0 = __ldg(sv + i0), s1 = __ldg(sv + i1), s2 = __ldg(sv + i2);
-		const unsigned k0 = __float_as_uint(s0.w), k1 = __float_as_uint(s1.w), k2 = __float_as_uint(s2.w);
-		if (((k0 | k1 | k2) & 0x3fu) == 0) {
-			// every vertex inside every plane: clipTriangle returns the triangle unchanged (reference src/pipeline.cpp:322-325)
-			if (!is_backface(s0.x, s0.y, s1.x, s1.y, s2.x, s2.y))
-				touched = emit_triangle<PEEL, true>(fp, o, s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, f * 8u, cnt);
-		} else if ((k0 & k1 & k2) >> 8) {
-			// all three vertices safely outside one plane: clipTriangle returns nothing (see clip_code_safe_out)
+	int tx0 = 255, ty0 = 255, tx1 = 0, ty1 = 0;  // union of the tile rects this thread's direct-path triangles wrote keys into
+	bool has = false;
+	__shared__ __align__(16) unsigned s_idx[SETUP_ROUNDS > 1 ? SETUP_CHUNK * 3 : 4];
+	if (SETUP_ROUNDS > 1) {
+		const unsigned n_here = min(nf - base, (unsigned)SETUP_CHUNK);  // faces of this chunk
+		const unsigned* src = mesh.idx + 3u * base;                       // 16-byte aligned: SETUP_CHUNK * 12 is a multiple of 16
+		if (n_here == SETUP_CHUNK) {
+#pragma unroll
+			for (int k = 0; k < (SETUP_CHUNK * 3 / 4 + SETUP_THREADS - 1) / SETUP_THREADS; ++k) {
+				const unsigned q = threadIdx.x + k * SETUP_THREADS;
+				if (q < SETUP_CHUNK * 3 / 4) reinterpret_cast<uint4*>(s_idx)[q] = __ldg(reinterpret_cast<const uint4*>(src) + q);
+			}
 		} else {
-			clipped = 1;
-			const unsigned c = setup_clipped_face<PEEL>(fp, o, mvp, __ldg(mesh.pos + i0), __ldg(mesh.pos + i1), __ldg(mesh.pos + i2), f);
-			cnt.tris += c & 255u; cnt.small += (c >> 8) & 255u; cnt.binned += c >> 16;
+			for (unsigned w = threadIdx.x; w < n_here * 3u; w += SETUP_THREADS) s_idx[w] = __ldg(src + w);
+		}
+		__syncthreads();
+#pragma unroll
+		for (int r = 0; r < SETUP_ROUNDS; ++r) {
+			const unsigned l = r * SETUP_THREADS + threadIdx.x;
+			if (l < n_here) { prefetch_l1(sv + s_idx[3u * l]); prefetch_l1(sv + s_idx[3u * l + 1]); prefetch_l1(sv + s_idx[3u * l + 2]); }
 		}
 	}
-	__syncwarp();
-	// Tile flags of the direct path, warp-aggregated: the 32 consecutive faces of a warp land in the same one or two tiles, so lane 0
+#pragma unroll 1
+	for (int r = 0; r < SETUP_ROUNDS; ++r) {
+		const unsigned l = r * SETUP_THREADS + threadIdx.x;
+		const unsigned f = base + l;
+		bool clip = false;
+		if (f < nf) {
+			unsigned i0, i1, i2;
+			if (SETUP_ROUNDS > 1) {
+				i0 = s_idx[3u * l]; i1 = s_idx[3u * l + 1]; i2 = s_idx[3u * l + 2];
+			} else {
+				const unsigned* ip = mesh.idx + 3u * f;
+				i0 = __ldg(ip); i1 = __ldg(ip + 1); i2 = __ldg(ip + 2);
+			}
+			const float4 s0 = __ldg(sv + i0), s1 = __ldg(sv + i1), s2 = __ldg(sv + i2);
+			const unsigned k0 = __float_as_uint(s0.w), k1 = __float_as_uint(s1.w), k2 = __float_as_uint(s2.w);
+			if (((k0 | k1 | k2) & 0x3fu) == 0) {
+				// every vertex inside every plane: clipTriangle returns the triangle unchanged (reference src/pipeline.cpp:322-325)
+				if (!is_backface(s0.x, s0.y, s1.x, s1.y, s2.x, s2.y)) {
+					const unsigned touched = emit_triangle<PEEL, true>(fp, o, s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, f * 8u, cnt);
+					if (touched != NO_TOUCH) {
+						has = true;
+						tx0 = min(tx0, (int)(touched & 255u)); ty0 = min(ty0, (int)((touched >> 8) & 255u));
+						tx1 = max(tx1, (int)((touched >> 16) & 255u)); ty1 = max(ty1, (int)(touched >> 24));
+					}
+				}
+			} else if ((k0 & k1 & k2) >> 8) {
+				// all three vertices safely outside one plane: clipTriangle returns nothing (see clip_code_safe_out)
+			} else {
+				clip = true;  // needs the clipper: k_setup_clipped, the next kernel on the stream
+			}
+		}
+		__syncwarp();
+		// Faces for the clipper: warp-aggregated append (any order: keys carry the face ordinal, bins are order-free)
+		const unsigned cm = __ballot_sync(0xffffffffu, clip);
+		if (cm) {
+			unsigned at = 0;
+			if (lane == 0) at = atomicAdd(o.n_clip_faces, (unsigned)__popc(cm));
+			at = __shfl_sync(0xffffffffu, at, 0);
+			if (clip) o.clip_faces[at + __popc(cm & ((1u << lane) - 1u))] = f;
+		}
+	}
+	// Tile flags of the direct path, warp-aggregated: the consecutive faces of a warp land in the same one or two tiles, so lane 0
 	// flags the union of their tile rects (a superset costs an empty staging pass in the tile kernel, nothing else); scattered faces
 	// (union of more than 4 tiles) flag their own.
-	const bool has = touched != NO_TOUCH;
 	if (__ballot_sync(0xffffffffu, has)) {
-		const int tx0 = has ? (int)(touched & 255u) : 255, ty0 = has ? (int)((touched >> 8) & 255u) : 255;
-		const int tx1 = has ? (int)((touched >> 16) & 255u) : 0, ty1 = has ? (int)(touched >> 24) : 0;
 		const int ux0 = __reduce_min_sync(0xffffffffu, tx0), uy0 = __reduce_min_sync(0xffffffffu, ty0);
 		const int ux1 = __reduce_max_sync(0xffffffffu, tx1), uy1 = __reduce_max_sync(0xffffffffu, ty1);
 		if ((ux1 - ux0 + 1) * (uy1 - uy0 + 1) <= 4) {
@@ -419,45 +541,71 @@ __global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(
 				for (int tx = tx0; tx <= tx1; ++tx) touch_tile(fp, o, tx, ty);
 		}
 	}
-	// Counters: warp reduce, then one fire-and-forget reduction per non-zero counter per warp into one of STAT_STRIPES stripes (no hot
+	// Counters: warp sums, then one fire-and-forget reduction per non-zero counter per warp into one of STAT_STRIPES stripes (no hot
 	// address). Warps whose faces were all culled have nothing to add.
-	if (__ballot_sync(0xffffffffu, (cnt.tris | clipped) != 0u)) {
-		const unsigned w0 = __reduce_add_sync(0xffffffffu, clipped), w1 = __reduce_add_sync(0xffffffffu, cnt.tris);
-		const unsigned w2 = __reduce_add_sync(0xffffffffu, cnt.small), w3 = __reduce_add_sync(0xffffffffu, cnt.binned);
+	if (__ballot_sync(0xffffffffu, cnt.tris != 0u)) {
+		const unsigned w1 = __reduce_add_sync(0xffffffffu, cnt.tris), w2 = __reduce_add_sync(0xffffffffu, cnt.small);
+		const unsigned w3 = __reduce_add_sync(0xffffffffu, cnt.binned);
 		if (lane == 0) {
-			const unsigned stripe = (blockIdx.x * (SETUP_THREADS / 32) + (threadIdx.x >> 5)) % STAT_STRIPES;
-			if (w0) atomicAdd(&o.status->stripes[0][stripe], w0);
-			if (w1) atomicAdd(&o.status->stripes[1][stripe], w1);
+			const unsigned stripe = (chunk * (SETUP_THREADS / 32) + (threadIdx.x >> 5)) % STAT_STRIPES;
+			atomicAdd(&o.status->stripes[1][stripe], w1);
 			if (w2) atomicAdd(&o.status->stripes[2][stripe], w2);
 			if (w3) atomicAdd(&o.status->stripes[3][stripe], w3);
 		}
 	}
 }
 
-// Folds the striped counters of k_setup_raster and publishes the draw's status to the host (one small CTA behind the setup kernel;
-// a last-CTA-done ticket inside the setup kernel was measured: its barrier keeps every CTA resident until its slowest warp is done,
-// C3 171 -> 239 us).
-constexpr int FOLD_THREADS = 128;
-__global__ void __launch_bounds__(FOLD_THREADS) k_fold_status(DrawStatus* status, DrawStatus* host_status, int bins_enabled) {
-	__shared__ unsigned long long s_fold[4][FOLD_THREADS / 32];
+// The faces k_setup_raster left for the clipper (usually a few thousand, often none), one thread per face; the CTA that finishes
+// last then folds the striped counters of both kernels and publishes the draw's status to the host. (The ticket lives in this small
+// kernel: inside k_setup_raster its barrier keeps every CTA resident until its slowest warp is done, C3 171 -> 239 us.)
+constexpr int CLIPSETUP_THREADS = 64, CLIPSETUP_CTAS = 148;
+template <bool PEEL>
+__global__ void __launch_bounds__(CLIPSETUP_THREADS) k_setup_clipped(const __grid_constant__ MeshView mesh, const __grid_constant__ m4 mvp,
+                                                                    const __grid_constant__ FrameParams fp, const __grid_constant__ SetupOut o,
+                                                                    DrawStatus* host_status) {
+	__shared__ unsigned long long s_fold[4][CLIPSETUP_THREADS / 32];
+	__shared__ unsigned s_last;
+	const unsigned n = *o.n_clip_faces;
+	unsigned tris = 0, small = 0, binned = 0;
+	for (unsigned i = blockIdx.x * CLIPSETUP_THREADS + threadIdx.x; i < n; i += gridDim.x * CLIPSETUP_THREADS) {
+		const unsigned f = o.clip_faces[i];
+		const unsigned* ip = mesh.idx + 3u * f;
+		const unsigned c = setup_clipped_face<PEEL>(fp, o, mvp, __ldg(mesh.pos + __ldg(ip)), __ldg(mesh.pos + __ldg(ip + 1)), __ldg(mesh.pos + __ldg(ip + 2)), f);
+		tris += c & 255u; small += (c >> 8) & 255u; binned += c >> 16;
+	}
+	if (tris) {
+		const unsigned stripe = (blockIdx.x * CLIPSETUP_THREADS + threadIdx.x) % STAT_STRIPES;
+		atomicAdd(&o.status->stripes[1][stripe], tris);
+		if (small) atomicAdd(&o.status->stripes[2][stripe], small);
+		if (binned) atomicAdd(&o.status->stripes[3][stripe], binned);
+	}
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0) s_last = atomicAdd(&o.status->pad, 1u) == gridDim.x - 1 ? 1u : 0u;
+	__syncthreads();
+	if (!s_last) return;
+	__threadfence();
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-	for (int c = 0; c < 4; ++c) {
+	for (int c = 1; c < 4; ++c) {
 		unsigned long long acc = 0;
-		for (int i = threadIdx.x; i < STAT_STRIPES; i += FOLD_THREADS) acc += status->stripes[c][i];
+		for (int i = threadIdx.x; i < STAT_STRIPES; i += CLIPSETUP_THREADS) acc += __ldcg(&o.status->stripes[c][i]);
 		for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
 		if (lane == 0) s_fold[c][warp] = acc;
 	}
 	__syncthreads();
 	if (threadIdx.x < 4) {
-		unsigned long long sum = 0;
-		for (int w = 0; w < FOLD_THREADS / 32; ++w) sum += s_fold[threadIdx.x][w];
-		(&status->clipped_faces)[threadIdx.x] = sum;
-		if (threadIdx.x == 3 && sum != 0 && !bins_enabled) status->overflow = OVF_NEED_BINS;
+		unsigned long long sum = n;  // clipped_faces
+		if (threadIdx.x) {
+			sum = 0;
+			for (int w = 0; w < CLIPSETUP_THREADS / 32; ++w) sum += s_fold[threadIdx.x][w];
+		}
+		(&o.status->clipped_faces)[threadIdx.x] = sum;
+		if (threadIdx.x == 3 && sum != 0 && !o.bins_enabled) o.status->overflow = OVF_NEED_BINS;
 	}
 	__syncthreads();
 	// bin_refs and (with bins) overflow are k_scan_tiles' to fill in; it publishes those words again
-	if (threadIdx.x < 6) publish_status(status, host_status, threadIdx.x);
+	if (threadIdx.x < 6) publish_status(o.status, host_status, threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------ bins: scan + scatter

@@ -10,16 +10,19 @@ from axiomr_b200 import build as b  # noqa: E402
 # Compile-time knobs of axr_kernels.cuh (launch shapes). The defaults are the winners of the round-1 A/B runs
 # (profiles/r01_ab_*.jsonl); these variants bracket them.
 VARIANTS = {
-    "setup_loop0": ["AXR_SETUP_LOOP=0"],
-    "setup_mb12": ["AXR_SETUP_MINB=12"],
-    "setup_mb10": ["AXR_SETUP_MINB=10"],
-    "setup_loop0_mb12": ["AXR_SETUP_LOOP=0", "AXR_SETUP_MINB=12"],
-    "setup_t256_mb6": ["AXR_SETUP_THREADS=256", "AXR_SETUP_MINB=6"],
+    "noswz": ["AXR_SETUP_SWZ_K=1"],
+    "swz8": ["AXR_SETUP_SWZ_K=8"],
+    "swz32": ["AXR_SETUP_SWZ_K=32"],
+    "swz16_g32": ["AXR_SETUP_SWZ_GROUP=32"],
+    "swz64_g32": ["AXR_SETUP_SWZ_K=64", "AXR_SETUP_SWZ_GROUP=32"],
+    "r4_mb10": ["AXR_SETUP_ROUNDS=4", "AXR_SETUP_MINB=10", "AXR_SETUP_SWZ_GROUP=32"],
+    "r2_mb10": ["AXR_SETUP_ROUNDS=2", "AXR_SETUP_MINB=10", "AXR_SETUP_SWZ_GROUP=64"],
+    "mb16": ["AXR_SETUP_MINB=16"],
 }
 
 def _one(name: str) -> str:
     out = os.path.join(ROOT, "variants_tmp", f"lib_{name}.so")
-    b.build(force=True, defines=VARIANTS[name], out=out)
+    b.build(force=True, defines=VARIANTS[name], out=out, verbose="-v" in sys.argv)
     return f"{out} {VARIANTS[name]}"
 
 
@@ -27,5 +30,5 @@ if __name__ == "__main__":
     from concurrent.futures import ThreadPoolExecutor
     os.makedirs(os.path.join(ROOT, "variants_tmp"), exist_ok=True)
     with ThreadPoolExecutor(4) as ex:  # nvcc runs as a subprocess: four at a time, ~75 s each
-        for line in ex.map(_one, sys.argv[1:] or list(VARIANTS)):
+        for line in ex.map(_one, [a for a in sys.argv[1:] if a != "-v"] or list(VARIANTS)):
             print(line, flush=True)
