@@ -372,7 +372,7 @@ __device__ __noinline__ unsigned setup_clipped_face(const FrameParams& fp, const
 	a[1].clip = mul(mvp, V4(p1.x, p1.y, p1.z, 1.0f));
 	a[2].clip = mul(mvp, V4(p2.x, p2.y, p2.z, 1.0f));
 	ClipPos* out;
-	int n = clip_triangle(a, b, &out);
+	int n = clip_triangle(a, b, &out, clip_planes_needed(a[0].clip, a[1].clip, a[2].clip));
 	const float fW = (float)fp.W, fH = (float)fp.H;
 	for (int j = 0; j + 2 < n; j += 3) {
 		float x0, y0, z0, x1, y1, z1, x2, y2, z2;
@@ -800,7 +800,7 @@ __device__ bool shade_pixel_clipped(const MeshView& mesh, const Uniforms& u, con
 		a[k].n = v.n; a[k].t = v.t; a[k].b = v.b;
 	}
 	ClipFull* out;
-	const int n = clip_triangle(a, b, &out);
+	const int n = clip_triangle(a, b, &out, clip_planes_needed(a[0].clip, a[1].clip, a[2].clip));
 	const int sub = (int)(ordinal & 7u);
 	if (sub * 3 + 2 >= n) return false;
 	const ClipFull* c = out + sub * 3;
@@ -1015,17 +1015,34 @@ template <typename Shader, int SMP>
 __global__ void __launch_bounds__(CLIP_SHADE_THREADS) k_shade_clipped(const __grid_constant__ MeshView mesh, const __grid_constant__ Uniforms u,
                                                                      const __grid_constant__ FrameParams fp, const __grid_constant__ TileIn in) {
 	constexpr bool PEEL = Shader::DISCARDS;
+	__shared__ unsigned long long s_key[GT_PIX];
+	__shared__ unsigned short s_pix[GT_PIX];
+	__shared__ unsigned s_n;
 	const unsigned n = *in.n_clip_tiles;
 	for (unsigned t = blockIdx.x; t < n; t += gridDim.x) {
 		const int tile = (int)in.clip_tiles[t];
 		const int x0 = (tile % fp.ntx) * GT, y0 = (tile / fp.ntx) * GT;
-		for (int p = threadIdx.x; p < GT_PIX; p += CLIP_SHADE_THREADS) {
+		if (threadIdx.x == 0) s_n = 0u;
+		__syncthreads();
+		// the keys k_tile_shade handed back (all loads of a thread in flight together), compacted so that every thread gets its share
+#pragma unroll
+		for (int i = 0; i < GT_PIX / CLIP_SHADE_THREADS; ++i) {
+			const int p = i * CLIP_SHADE_THREADS + threadIdx.x;
 			const int px = x0 + (p & (GT - 1)), py = y0 + (p / GT);
 			if (px >= fp.W || py < fp.y_lo || py >= fp.y_hi) continue;
 			unsigned long long* g = in.vis + (size_t)py * fp.W + px;
 			const unsigned long long k = *g;
 			if (k == KEY_EMPTY) continue;
 			*g = KEY_EMPTY;
+			const unsigned at = atomicAdd(&s_n, 1u);
+			s_key[at] = k; s_pix[at] = (unsigned short)p;
+		}
+		__syncthreads();
+		const unsigned m = s_n;
+		for (unsigned i = threadIdx.x; i < m; i += CLIP_SHADE_THREADS) {
+			const unsigned long long k = s_key[i];
+			const int p = s_pix[i];
+			const int px = x0 + (p & (GT - 1)), py = y0 + (p / GT);
 			const bool discarded = shade_pixel_clipped<Shader, SMP>(mesh, u, fp, in, (unsigned)(k & 0xFFFFFFFFull), px, py);
 			if constexpr (PEEL) {
 				in.floor[(size_t)py * fp.W + px] = discarded ? k : KEY_EMPTY;
@@ -1034,6 +1051,7 @@ __global__ void __launch_bounds__(CLIP_SHADE_THREADS) k_shade_clipped(const __gr
 				(void)discarded;
 			}
 		}
+		__syncthreads();
 	}
 }
 

@@ -127,14 +127,35 @@ __device__ int clip_single_plane(int plane, CV& v0, CV& v1, CV& v2, CV& v3) {
 	v2 = v3;
 	return 3;
 }
+// Planes the clipper has to visit for a triangle with clip-space vertices c0, c1, c2: bit k clear <=> all three vertices are inside
+// plane k by more than 1e-4 * (largest |w| + |c| among them) + 1e-6. Every vertex the other planes create is a chain of at most
+// six convex combinations x*(1-t) + y*t, t in [0,1], of such vertices; the rounding of the products, the sums and of 1-t moves d_k
+// by a few 2^-24 of that largest magnitude per generation, three orders of magnitude below the margin, so at plane k every
+// sub-triangle has d >= 0 on all vertices and clip_single_plane hands it on unchanged (:322-325): skipping the plane is exact.
+__device__ __forceinline__ unsigned clip_planes_needed(v4 c0, v4 c1, v4 c2) {
+	const float aw = fmaxf(fmaxf(fabsf(c0.w), fabsf(c1.w)), fabsf(c2.w));
+	const float mx = 1e-4f * (aw + fmaxf(fmaxf(fabsf(c0.x), fabsf(c1.x)), fabsf(c2.x))) + 1e-6f;
+	const float my = 1e-4f * (aw + fmaxf(fmaxf(fabsf(c0.y), fabsf(c1.y)), fabsf(c2.y))) + 1e-6f;
+	const float mz = 1e-4f * (aw + fmaxf(fmaxf(fabsf(c0.z), fabsf(c1.z)), fabsf(c2.z))) + 1e-6f;
+	unsigned need = 0;
+	need |= ((c0.x + c0.w) > mx && (c1.x + c1.w) > mx && (c2.x + c2.w) > mx) ? 0u : 1u;
+	need |= ((c0.w - c0.x) > mx && (c1.w - c1.x) > mx && (c2.w - c2.x) > mx) ? 0u : 2u;
+	need |= ((c0.y + c0.w) > my && (c1.y + c1.w) > my && (c2.y + c2.w) > my) ? 0u : 4u;
+	need |= ((c0.w - c0.y) > my && (c1.w - c1.y) > my && (c2.w - c2.y) > my) ? 0u : 8u;
+	need |= ((c0.z + c0.w) > mz && (c1.z + c1.w) > mz && (c2.z + c2.w) > mz) ? 0u : 16u;
+	need |= ((c0.w - c0.z) > mz && (c1.w - c1.z) > mz && (c2.w - c2.z) > mz) ? 0u : 32u;
+	return need;  // NaN anywhere fails the compares: the plane is visited
+}
+
 // reference src/pipeline.cpp:176-228. bufA holds 3 vertices on entry. Returns the vertex count and the
-// buffer (bufA or bufB) holding the result in *out.
+// buffer (bufA or bufB) holding the result in *out. planes: clip_planes_needed() of the three vertices (0x3f = all six).
 template <typename CV>
-__device__ __noinline__ int clip_triangle(CV* bufA, CV* bufB, CV** out) {
+__device__ __noinline__ int clip_triangle(CV* bufA, CV* bufB, CV** out, unsigned planes) {
 	CV* a = bufA;
 	CV* b = bufB;
 	int n = 3;
 	for (int plane = 0; plane < 6; ++plane) {
+		if (!((planes >> plane) & 1u)) continue;
 		int cnt = 0;
 		for (int i = 0; i < n; i += 3) {
 			CV q;

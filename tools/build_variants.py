@@ -10,14 +10,14 @@ from axiomr_b200 import build as b  # noqa: E402
 # Compile-time knobs of axr_kernels.cuh (launch shapes). The defaults are the winners of the round-1 A/B runs
 # (profiles/r01_ab_*.jsonl); these variants bracket them.
 VARIANTS = {
-    "noswz": ["AXR_SETUP_SWZ_K=1"],
-    "swz8": ["AXR_SETUP_SWZ_K=8"],
-    "swz32": ["AXR_SETUP_SWZ_K=32"],
-    "swz16_g32": ["AXR_SETUP_SWZ_GROUP=32"],
-    "swz64_g32": ["AXR_SETUP_SWZ_K=64", "AXR_SETUP_SWZ_GROUP=32"],
-    "r4_mb10": ["AXR_SETUP_ROUNDS=4", "AXR_SETUP_MINB=10", "AXR_SETUP_SWZ_GROUP=32"],
-    "r2_mb10": ["AXR_SETUP_ROUNDS=2", "AXR_SETUP_MINB=10", "AXR_SETUP_SWZ_GROUP=64"],
-    "mb16": ["AXR_SETUP_MINB=16"],
+    "abl1": ["AXR_SETUP_ABLATE=1"],
+    "abl2": ["AXR_SETUP_ABLATE=2"],
+    "abl3": ["AXR_SETUP_ABLATE=3"],
+    "loop0": ["AXR_SETUP_LOOP=0"],
+    "loop2": ["AXR_SETUP_LOOP=2"],
+    "mb10": ["AXR_SETUP_MINB=10"],
+    "t64": ["AXR_SETUP_THREADS=64", "AXR_SETUP_MINB=24", "AXR_SETUP_SWZ_GROUP=256"],
+    "t256": ["AXR_SETUP_THREADS=256", "AXR_SETUP_MINB=6", "AXR_SETUP_SWZ_GROUP=64"],
 }
 
 def _one(name: str) -> str:
