@@ -35,8 +35,9 @@ struct DeviceMesh {
 	Material* d_materials = nullptr;
 	unsigned long long* d_group_first = nullptr;
 	bool materials_dirty = true;
-	bool no_bins = false;  // the last draw of this mesh binned nothing: the next one is issued without the two bin kernels (and
-	                       // re-issued with them should a triangle need them after all, OVF_NEED_BINS)
+	int bin_mode = BINS_LISTS;  // how the next draw of this mesh is issued, learnt from its last one: no triangle went through the bins
+	                            // -> BINS_NONE, a few -> BINS_SCAN (both without the two bin kernels; a draw that turns out to need
+	                            // them raises OVF_NEED_BINS and is re-issued with BINS_LISTS)
 };
 
 struct DeviceTexture {
@@ -232,10 +233,10 @@ int check_pending(axr_ctx* ctx) {
 	DeviceMesh& pm = ctx->meshes[p.mesh];
 	if (!st.overflow) {
 		// learn whether this mesh needs the bin kernels at all (BASELINE configs 2-4: every triangle is rasterised by its setup thread)
-		if (!p.peel) pm.no_bins = st.binned_triangles == 0;
+		if (!p.peel) pm.bin_mode = st.binned_triangles == 0 ? BINS_NONE : (st.binned_triangles <= BINS_SCAN_MAX / 2 ? BINS_SCAN : BINS_LISTS);
 		return AXR_OK;
 	}
-	if (st.overflow & OVF_NEED_BINS) pm.no_bins = false;
+	if (st.overflow & OVF_NEED_BINS) pm.bin_mode = BINS_LISTS;
 	if (p.redo_depth >= 3) return fail(ctx, AXR_ERR_CAPACITY, "bin capacity still exceeded after regrowing (records %llu refs %llu)",
 	                                   (unsigned long long)st.binned_triangles, (unsigned long long)st.bin_refs);
 	CU(cudaStreamSynchronize(ctx->geom_stream));
@@ -357,8 +358,9 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 	so.floor = peel ? ctx->peel_floor : nullptr;
 	so.clip_faces = sl.clip_faces; so.n_clip_faces = sl.n_clip_faces;
 	so.n_chunks = 0; so.swz_rows = 0;
-	const bool bins = peel || !m.no_bins;
-	so.bins_enabled = bins ? 1 : 0;
+	const int bin_mode = peel ? (int)BINS_LISTS : m.bin_mode;
+	const bool bins = bin_mode == BINS_LISTS;
+	so.bins_enabled = bin_mode;
 	{
 		const unsigned grid = m.n_faces ? setup_grid(m.n_faces, so.n_chunks, so.swz_rows) : 0u;
 		if (grid) {
@@ -400,6 +402,7 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 	in.again = peel ? ctx->peel_again : nullptr;
 	in.clip_tiles = sl.clip_tiles; in.n_clip_tiles = sl.n_clip_tiles;
 	in.dirty = ctx->dirty_map;
+	in.bin_mode = bin_mode;
 	switch (ctx->shader_kind) {
 	case AXR_SHADER_FLAT: launches += launch_tile<FlatShader>(ctx, mv, u, in); break;
 	case AXR_SHADER_PHONG: launches += launch_tile<PhongShader>(ctx, mv, u, in); break;

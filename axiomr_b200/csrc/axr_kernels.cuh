@@ -206,14 +206,21 @@ struct SetupOut {
 	unsigned* n_records;         // device counter (also the number wanted when it overflows)
 	DrawStatus* status;
 	int small_dim, small_area;   // direct-raster limits of this draw
-	int bins_enabled;            // 0: the draw was issued without the bin kernels (no triangle of this mesh needed them last time);
-	                             //    a triangle that does need them is counted, k_setup_clipped raises OVF_NEED_BINS and the host re-issues the draw with bins
+	int bins_enabled;            // BINS_*: how triangles too large for the direct path reach their tiles in this draw
 	const unsigned long long* floor;  // depth peeling only (PEEL): per pixel, keys <= floor have been dealt with
 	unsigned* clip_faces;        // faces that need the clipper: appended by k_setup_raster, worked through by k_setup_clipped
 	unsigned* n_clip_faces;      // (capacity: the face count of the mesh, so the list cannot overflow)
 	unsigned n_chunks, swz_rows; // CTA -> face chunk interleave of k_setup_raster (setup_grid())
 };
 constexpr unsigned OVF_RECORDS = 1u, OVF_REFS = 2u, OVF_NEED_BINS = 4u;
+// BINS_NONE:  the mesh had no such triangle last time: no records, no bin kernels; one that turns up is counted, k_setup_clipped raises
+//             OVF_NEED_BINS and the host re-issues the draw with BINS_LISTS.
+// BINS_LISTS: records + per-tile counts -> k_scan_tiles -> k_bin_scatter -> per-tile reference lists.
+// BINS_SCAN:  the mesh had few of them last time (<= BINS_SCAN_MAX): records + per-tile counts only; a tile CTA with a non-zero count
+//             tests every record against its tile itself, which is cheaper than two more kernels in the draw's dependency chain
+//             (C1: 17 us of a 95 us draw). More records than BINS_SCAN_MAX (or than fit) -> OVF_NEED_BINS -> re-issued with lists.
+enum { BINS_NONE = 0, BINS_LISTS = 1, BINS_SCAN = 2 };
+constexpr unsigned BINS_SCAN_MAX = 4096;
 
 struct EmitCounters { unsigned tris, small, binned; };
 
@@ -601,7 +608,10 @@ __global__ void __launch_bounds__(CLIPSETUP_THREADS) k_setup_clipped(const __gri
 			for (int w = 0; w < CLIPSETUP_THREADS / 32; ++w) sum += s_fold[threadIdx.x][w];
 		}
 		(&o.status->clipped_faces)[threadIdx.x] = sum;
-		if (threadIdx.x == 3 && sum != 0 && !o.bins_enabled) o.status->overflow = OVF_NEED_BINS;
+		if (threadIdx.x == 3) {
+			if (o.bins_enabled == BINS_NONE && sum != 0) o.status->overflow = OVF_NEED_BINS;
+			if (o.bins_enabled == BINS_SCAN && (sum > BINS_SCAN_MAX || sum > o.rec_cap)) o.status->overflow = OVF_NEED_BINS;
+		}
 	}
 	__syncthreads();
 	// bin_refs and (with bins) overflow are k_scan_tiles' to fill in; it publishes those words again
@@ -706,6 +716,7 @@ struct TileIn {
 	unsigned* clip_tiles;           // tiles holding pixels owned by a clipped face: shaded by k_shade_clipped, not here
 	unsigned* dirty;                // optional (axr_set_dirty_map): per GPU tile, set to 1 when this draw may store into the tile
 	unsigned* n_clip_tiles;
+	int bin_mode;                   // BINS_* of this draw
 };
 
 // (uint8)(int)(clamp(c, 0, 1) * 255): reference src/tiled_pipeline.cpp:579-582. cvttss2si turns NaN into 0x80000000, whose low byte is 0.
@@ -855,22 +866,33 @@ __device__ __forceinline__ int shade_pixel(const MeshView& mesh, const Uniforms&
 	return run_shader<Shader, SMP, FAST>(mesh, u, in, ordinal >> 3, gi, z, w, v) ? PIX_DISCARDED : PIX_DONE;
 }
 
+// candidates per round of the binned phase: 4 KB (+ 2 KB of candidate ids) of shared memory, so that keys + candidates of four resident CTAs stay inside the
+// 64 KB shared-memory carve-out the keys alone already need (the gathers of the shading phase live on the rest of the L1)
+constexpr int BIN_ROUND = 64, SCAN_CHUNK = 1024;
+static_assert(BIN_ROUND <= TILE_THREADS && SCAN_CHUNK % TILE_THREADS == 0 && SCAN_CHUNK <= 65536, "one candidate per thread; 16-bit chunk-relative ids");
 template <typename Shader, int SMP, bool FAST>
 __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(const __grid_constant__ MeshView mesh, const __grid_constant__ Uniforms u, const __grid_constant__ FrameParams fp,
                                                                              const __grid_constant__ TileIn in) {
 	constexpr bool PEEL = Shader::DISCARDS;
 	__shared__ unsigned long long s_keys[GT_PIX];
-	__shared__ unsigned s_clipped;
+	__shared__ float s_rec[BIN_ROUND][16];  // set-up candidates of one round (edges, 1/area, z, floor(minX), ordinal, tile-relative box)
+	__shared__ unsigned short s_cand[SCAN_CHUNK];  // BINS_SCAN: records of the current chunk that reach into this tile
+	__shared__ unsigned s_clipped, s_nrec, s_ncand;
 	if (in.status->overflow) return;  // the host grows the bins and re-issues the draw
 	const int tx = blockIdx.x, ty = fp.ty_lo + blockIdx.y;
 	const int tile = ty * fp.ntx + tx;
 	const int x0 = tx * GT, y0 = ty * GT;
 	const unsigned touched = in.tile_touched[tile];
-	const unsigned nrec = *in.n_records;
-	const unsigned b0 = nrec ? in.bin_start[tile] : 0u, b1 = nrec ? in.bin_start[tile + 1] : 0u;
+	const unsigned nrec = in.bin_mode == BINS_NONE ? 0u : *in.n_records;
+	// candidates among the binned records: this tile's reference list, or (BINS_SCAN) every record once the tile's count is non-zero
+	unsigned b0 = 0, b1 = 0;
+	if (nrec) {
+		if (in.bin_mode == BINS_LISTS) { b0 = in.bin_start[tile]; b1 = in.bin_start[tile + 1]; }
+		else if (in.tile_cursor[tile]) b1 = nrec;
+	}
 	if (!touched && b0 == b1) return;
 	const int tid = threadIdx.x;
-	if (tid == 0) s_clipped = 0u;
+	if (tid == 0) { s_clipped = 0u; s_nrec = 0u; s_ncand = 0u; }
 	// 1. stage the tile's visibility keys in shared memory (and hand the global buffer back empty for the next draw)
 	for (int p = tid; p < GT_PIX; p += TILE_THREADS) {
 		int px = x0 + (p & (GT - 1)), py = y0 + (p / GT);
@@ -887,59 +909,93 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 		in.tile_touched[tile] = 0u; in.tile_cursor[tile] = 0u;
 		if (in.dirty) in.dirty[tile] = 1u;
 	}
-	// 2. binned triangles. Each warp takes 32 references at a time: every lane loads and sets up ITS record (32 independent
-	//    gathers in flight), then the warp walks the set-up records one by one (setup broadcast by shuffles) and evaluates
-	//    8x4 pixel blocks per step with shared-memory atomicMin.
+	// 2. binned triangles, BIN_ROUND candidates at a time: every thread loads and sets up ITS candidate (all gathers in flight at
+	//    once) and the ones that reach into the tile are parked in shared memory; then warp w walks them over ITS strip of the tile
+	//    (rows 4w .. 4w+3 with 8 warps), an 8x4 pixel block per step. A pixel belongs to one lane of one warp, so the running minimum
+	//    needs no atomics, and a tile with a handful of large triangles (C1) keeps all warps busy instead of one.
 	if (b1 > b0) {
 		const int warp = tid >> 5, lane = tid & 31;
 		const int lx = lane & 7, ly = lane >> 3;
 		const int yb0 = max(y0, fp.y_lo), yb1 = min(min(y0 + GT, fp.H), fp.y_hi);
-		for (unsigned rb = b0 + warp * 32; rb < b1; rb += (TILE_THREADS / 32) * 32) {
-			const unsigned r = rb + lane;
-			Setup s;
-			unsigned ordinal = 0;
-			int bx0 = 0, bx1 = 0, by0 = 0, by1 = 0;
-			bool ok = false;
-			if (r < b1) {
-				const TriRecord t = in.records[in.items[r]];
-				ordinal = t.ordinal;
-				ok = setup_triangle(t.x0, t.y0, t.x1, t.y1, t.x2, t.y2, t.z0, t.z1, t.z2, fp.W, fp.y_lo, fp.y_hi, s);
-				if (ok) {
-					bx0 = max(s.X0, x0); bx1 = min(s.X1, x0 + GT); by0 = max(s.Y0, yb0); by1 = min(s.Y1, yb1);
-					ok = bx0 < bx1 && by0 < by1;
-				}
-			}
-			unsigned todo = __ballot_sync(0xffffffffu, ok);
-			while (todo) {
-				const int src = __ffs(todo) - 1;
-				todo &= todo - 1;
-				Setup q;
-				q.a0 = __shfl_sync(0xffffffffu, s.a0, src); q.b0 = __shfl_sync(0xffffffffu, s.b0, src); q.c0 = __shfl_sync(0xffffffffu, s.c0, src);
-				q.a1 = __shfl_sync(0xffffffffu, s.a1, src); q.b1 = __shfl_sync(0xffffffffu, s.b1, src); q.c1 = __shfl_sync(0xffffffffu, s.c1, src);
-				q.a2 = __shfl_sync(0xffffffffu, s.a2, src); q.b2 = __shfl_sync(0xffffffffu, s.b2, src); q.c2 = __shfl_sync(0xffffffffu, s.c2, src);
-				q.inv_area = __shfl_sync(0xffffffffu, s.inv_area, src);
-				q.z0 = __shfl_sync(0xffffffffu, s.z0, src); q.z1 = __shfl_sync(0xffffffffu, s.z1, src); q.z2 = __shfl_sync(0xffffffffu, s.z2, src);
-				q.fminx = __shfl_sync(0xffffffffu, s.fminx, src);
-				const int qx0 = __shfl_sync(0xffffffffu, bx0, src), qx1 = __shfl_sync(0xffffffffu, bx1, src);
-				const int qy0 = __shfl_sync(0xffffffffu, by0, src), qy1 = __shfl_sync(0xffffffffu, by1, src);
-				const unsigned qord = __shfl_sync(0xffffffffu, ordinal, src);
-				for (int py0 = qy0; py0 < qy1; py0 += 4)
-					for (int px0 = qx0; px0 < qx1; px0 += 8) {
-						const int px = px0 + lx, py = py0 + ly;
-						if (px >= qx1 || py >= qy1) continue;
-						float c0, c1, c2, al, be, ga;
-						if (!coverage(q, px, py, c0, c1, c2)) continue;
-						const float z = interp_z(q, c0, c1, c2, al, be, ga);
-						if (!z_draws(z)) continue;
-						const unsigned long long key = make_key(z, qord);
-						if constexpr (PEEL) {
-							if (!(key > in.floor[(size_t)py * fp.W + px])) continue;
-						}
-						atomicMin(&s_keys[(py - y0) * GT + (px - x0)], key);
+		constexpr int STRIP = GT / (TILE_THREADS / 32);  // rows per warp
+		static_assert(STRIP >= 4 && STRIP % 4 == 0, "a warp's strip is made of 8x4 blocks");
+		// BINS_SCAN: the candidates of a chunk of SCAN_CHUNK records are found first (box test only, a thread's record loads all in
+		// flight), as indices in shared memory; BINS_LISTS: the tile's reference list is the one chunk.
+		const bool scan = in.bin_mode == BINS_SCAN;
+		for (unsigned cb = b0; cb < b1; cb += SCAN_CHUNK) {
+			unsigned m0 = cb, m1 = b1;  // candidates [m0, m1) of this chunk: positions in in.items (lists) or in s_cand (scan)
+			if (scan) {
+#pragma unroll
+				for (int k = 0; k < SCAN_CHUNK / TILE_THREADS; ++k) {
+					const unsigned r = cb + k * TILE_THREADS + tid;
+					if (r < b1) {
+						const TriRecord t = in.records[r];
+						// the pixel box of setup_triangle(), intersected with the tile
+						const int X0 = max(x0, cvtt(floorf(min3f(t.x0, t.x1, t.x2)))), X1 = min(min(x0 + GT, fp.W), cvtt(ceilf(max3f(t.x0, t.x1, t.x2))));
+						const int Y0 = max(yb0, cvtt(floorf(min3f(t.y0, t.y1, t.y2)))), Y1 = min(yb1, cvtt(ceilf(max3f(t.y0, t.y1, t.y2))));
+						if (X0 < X1 && Y0 < Y1) s_cand[atomicAdd(&s_ncand, 1u)] = (unsigned short)(r - cb);
 					}
+				}
+				__syncthreads();
+				m0 = 0; m1 = s_ncand;
+			}
+			for (unsigned rb = m0; rb < m1; rb += BIN_ROUND) {
+				const unsigned r = rb + tid;
+				if (tid < BIN_ROUND && r < m1) {
+					const TriRecord t = in.records[scan ? cb + s_cand[r] : in.items[r]];
+					Setup s;
+					if (setup_triangle(t.x0, t.y0, t.x1, t.y1, t.x2, t.y2, t.z0, t.z1, t.z2, fp.W, fp.y_lo, fp.y_hi, s)) {
+						const int bx0 = max(s.X0, x0), bx1 = min(s.X1, x0 + GT), by0 = max(s.Y0, yb0), by1 = min(s.Y1, yb1);
+						if (bx0 < bx1 && by0 < by1) {
+							const unsigned at = atomicAdd(&s_nrec, 1u);
+							float* d = s_rec[at];
+							d[0] = s.a0; d[1] = s.b0; d[2] = s.c0; d[3] = s.a1; d[4] = s.b1; d[5] = s.c1; d[6] = s.a2; d[7] = s.b2; d[8] = s.c2;
+							d[9] = s.inv_area; d[10] = s.z0; d[11] = s.z1; d[12] = s.z2;
+							d[13] = __uint_as_float((unsigned)s.fminx); d[14] = __uint_as_float(t.ordinal);
+							d[15] = __uint_as_float((unsigned)(bx0 - x0) | ((unsigned)(bx1 - x0) << 8) | ((unsigned)(by0 - y0) << 16) | ((unsigned)(by1 - y0) << 24));
+						}
+					}
+				}
+				__syncthreads();
+				const unsigned m = s_nrec;
+				const int sy0 = warp * STRIP, sy1 = sy0 + STRIP;  // this warp's rows, tile-relative
+				for (unsigned i = 0; i < m; ++i) {
+					const float* d = s_rec[i];
+					const unsigned box = __float_as_uint(d[15]);
+					const int qx0 = (int)(box & 255u), qx1 = (int)((box >> 8) & 255u);
+					const int qy0 = max((int)((box >> 16) & 255u), sy0), qy1 = min((int)(box >> 24), sy1);
+					if (qy0 >= qy1) continue;
+					Setup q;
+					q.a0 = d[0]; q.b0 = d[1]; q.c0 = d[2]; q.a1 = d[3]; q.b1 = d[4]; q.c1 = d[5]; q.a2 = d[6]; q.b2 = d[7]; q.c2 = d[8];
+					q.inv_area = d[9]; q.z0 = d[10]; q.z1 = d[11]; q.z2 = d[12];
+					q.fminx = (int)__float_as_uint(d[13]);
+					const unsigned qord = __float_as_uint(d[14]);
+					for (int ry = qy0; ry < qy1; ry += 4)
+						for (int rx = qx0; rx < qx1; rx += 8) {
+							const int tx_ = rx + lx, ty_ = ry + ly;
+							if (tx_ >= qx1 || ty_ >= qy1) continue;
+							const int px = x0 + tx_, py = y0 + ty_;
+							float c0, c1, c2, al, be, ga;
+							if (!coverage(q, px, py, c0, c1, c2)) continue;
+							const float z = interp_z(q, c0, c1, c2, al, be, ga);
+							if (!z_draws(z)) continue;
+							const unsigned long long key = make_key(z, qord);
+							if constexpr (PEEL) {
+								if (!(key > in.floor[(size_t)py * fp.W + px])) continue;
+							}
+							unsigned long long* slot = &s_keys[ty_ * GT + tx_];
+							if (key < *slot) *slot = key;
+						}
+				}
+				__syncthreads();  // everybody is done with this round's candidates
+				if (tid == 0) s_nrec = 0u;
+				__syncthreads();
+			}
+			if (scan) {
+				if (tid == 0) s_ncand = 0u;
+				__syncthreads();
 			}
 		}
-		__syncthreads();
 	}
 	// 3. deferred shading of the visible triangle of each pixel + framebuffer resolve.
 	//    Not unrolled: one copy of the shading code keeps the kernel inside the instruction cache (unrolled x4 with prefetched

@@ -247,6 +247,54 @@ def test_draw_without_bins_is_redone_when_bins_are_needed(po):
         dev.close()
 
 
+def test_few_large_triangles_are_scanned_by_the_tiles_on_the_next_draw(po):
+    """A mesh whose last draw sent only a few triangles through the bins is drawn without the two bin kernels (BINS_SCAN: every tile
+    with a non-zero count tests all records itself); the frames equal the oracle, also when clipped, huge and small triangles mix,
+    and a later draw with too many records for that mode is re-issued with the reference lists."""
+    from axiomr_b200 import api
+    v, f = S.random_triangles(300, 3, extent=6, size=4.0, zspread=6)      # huge + clipped triangles
+    v2, f2 = S.random_triangles(1500, 7)                                   # mixed sizes
+    sc = S.Scene("scan_mode", 777, 333, np.concatenate([v, v2]), np.concatenate([f, f2 + v.shape[0]]), S.SHADER_PHONG, textures=_tex())
+    c0, d0, _ = po.oracle_render(sc, threads=8)
+    dev = api.Device(sc.width, sc.height)
+    try:
+        mesh = dev.load_scene(sc)
+        launches = []
+        for i in range(3):
+            dev.clear()
+            dev.draw_mesh(mesh, sc.model)
+            c1, d1 = dev.resolve()
+            st = dev.stats()
+            launches.append(st["kernel_launches"])
+            m = po.compare(c1, d1, c0, d0)
+            assert m["coverage_mismatch"] == 0 and m["depth_bit_mismatch"] == 0 and m["color_max_diff"] <= 1, (i, m)
+            assert 0 < st["binned_triangles"] <= 2048, st
+        assert launches[0] == launches[1] + 2 == launches[2] + 2, launches    # scan + scatter kernels gone after the first draw
+        # many more records than the scan mode takes: zoom in until most of the 20 k triangles of a second mesh are large
+        vb, fb = S.random_triangles(30000, 11, extent=1.0, size=0.12, zspread=0.5)
+        big = S.Scene("scan_to_lists", sc.width, sc.height, vb, fb, S.SHADER_FLAT)
+        big.view_proj, big.cam_pos = S.default_camera(sc.width, sc.height, eye=(0.0, 0.0, 1.5))
+        far_vp, far_cam = S.default_camera(sc.width, sc.height, eye=(0.0, 0.0, 90.0))
+        mesh2 = dev.load_scene(big)
+        dev.set_uniforms(far_vp, far_cam)
+        for _ in range(2):
+            dev.clear()
+            dev.draw_mesh(mesh2, big.model)
+        st = dev.stats()
+        assert st["binned_triangles"] <= 2048, st
+        dev.set_uniforms(big.view_proj, big.cam_pos)
+        dev.clear()
+        dev.draw_mesh(mesh2, big.model)
+        c1, d1 = dev.resolve()
+        st = dev.stats()
+        assert st["binned_triangles"] > 4096 and st["redo"] == 1, st
+        cb, db, _ = po.oracle_render(big, threads=8)
+        m = po.compare(c1, d1, cb, db)
+        assert m["coverage_mismatch"] == 0 and m["depth_bit_mismatch"] == 0 and m["color_max_diff"] <= 1, m
+    finally:
+        dev.close()
+
+
 def test_overflowed_draw_is_redone_with_the_state_it_was_issued_with(po):
     """A draw whose bins overflow is re-issued by the next API call; a set_uniforms / set_shader in between must not leak into it."""
     from axiomr_b200 import api
