@@ -75,6 +75,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--overlap", action="store_true", help="also time the same steps with axr_set_overlap(1) (wall clock, no per-kernel events)")
     ap.add_argument("--e2e", action="store_true", help="also time TiledPipeline.drawMesh on a pinned host framebuffer (axr_draw_mesh_host), "
                     "with and without AXR_B200_HOST_DEPTH_ZEROCOPY")
     ap.add_argument("variants", nargs="*")
@@ -120,6 +121,17 @@ def main():
             rec["draw_us"] = round(sum(rec["kernel_us"].values()), 1)
             st = dev.stats()
             rec["stats"] = {k: st[k] for k in ("triangles", "small_triangles", "binned_triangles", "bin_refs")}
+            if a.overlap:
+                dev.set_profiling(False)
+                dev.set_overlap(True)
+                for _ in range(a.warmup):
+                    dev.clear(); dev.draw_mesh(mesh, sc.model)
+                dev.sync()
+                t = time.perf_counter()
+                for _ in range(a.steps * 3):
+                    dev.clear(); dev.draw_mesh(mesh, sc.model)
+                dev.sync()
+                rec["overlap_ms_per_step"] = round((time.perf_counter() - t) / (a.steps * 3) * 1e3, 4)
             dev.close()
             if a.e2e:
                 rec["e2e_ms"] = {}

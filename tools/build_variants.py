@@ -10,14 +10,9 @@ from axiomr_b200 import build as b  # noqa: E402
 # Compile-time knobs of axr_kernels.cuh (launch shapes). The defaults are the winners of the round-1 A/B runs
 # (profiles/r01_ab_*.jsonl); these variants bracket them.
 VARIANTS = {
-    "abl1": ["AXR_SETUP_ABLATE=1"],
-    "abl2": ["AXR_SETUP_ABLATE=2"],
-    "abl3": ["AXR_SETUP_ABLATE=3"],
-    "loop0": ["AXR_SETUP_LOOP=0"],
-    "loop2": ["AXR_SETUP_LOOP=2"],
-    "mb10": ["AXR_SETUP_MINB=10"],
-    "t64": ["AXR_SETUP_THREADS=64", "AXR_SETUP_MINB=24", "AXR_SETUP_SWZ_GROUP=256"],
-    "t256": ["AXR_SETUP_THREADS=256", "AXR_SETUP_MINB=6", "AXR_SETUP_SWZ_GROUP=64"],
+    "idxpf": ["AXR_TILE_IDX_PREFETCH=1"],
+    "idxstash": ["AXR_TILE_IDX_STASH=1"],
+    "t128x8": ["AXR_TILE_THREADS=128", "AXR_TILE_MINB=8"],
 }
 
 def _one(name: str) -> str:
