@@ -61,6 +61,15 @@ class _Group(C.Structure):
     _fields_ = [("first_face", C.c_uint64), ("face_count", C.c_uint64)]
 
 
+class ObjInfo(C.Structure):
+    _fields_ = [("n_verts", C.c_uint64), ("n_faces", C.c_uint64), ("n_groups", C.c_uint32), ("reserved", C.c_uint32),
+                ("first_drawn_face", C.c_uint64)]
+
+
+class MtlEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 128), ("specular_exponent", C.c_float), ("has_map", C.c_int * 5), ("map", (C.c_char * 512) * 5)]
+
+
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("faces", "clipped_faces", "triangles", "small_triangles", "binned_triangles",
                                           "bin_refs", "kernel_launches", "redo")]
@@ -76,6 +85,7 @@ ABI_SYMBOLS = [
     "axr_clear", "axr_upload_framebuffer", "axr_resolve", "axr_draw_mesh", "axr_sync", "axr_get_stats", "axr_host_alloc",
     "axr_host_free", "axr_stream", "axr_framebuffer_device", "axr_set_output", "axr_framebuffer_ipc", "axr_open_ipc",
     "axr_close_ipc", "axr_set_profiling", "axr_get_kernel_times", "axr_set_depth_read", "axr_alloc_shared", "axr_free_shared", "axr_set_overlap", "axr_upload_framebuffer_async", "axr_draw_mesh_host", "axr_generate_tangents", "axr_measure_fp32_issue", "axr_set_color_math", "axr_update_mesh_vertices", "axr_dirty_map_entries", "axr_set_dirty_map", "axr_clear_dirty_tiles",
+    "axr_load_obj", "axr_load_obj_file", "axr_mesh_group_info", "axr_mesh_read", "axr_parse_mtl",
 ]
 STAGES = ["vertex_xform", "setup_raster", "scan_tiles", "bin_scatter", "tile_shade"]
 
@@ -119,6 +129,11 @@ def _bind(lib):
     lib.axr_set_shader.argtypes = [vp, C.c_int, C.POINTER(_ShaderParams), C.c_size_t]
     lib.axr_set_sampler.argtypes = [vp, C.c_int]
     lib.axr_set_color_math.argtypes = [vp, C.c_int]
+    lib.axr_load_obj.argtypes = [vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(ObjInfo)]
+    lib.axr_load_obj_file.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(ObjInfo)]
+    lib.axr_mesh_group_info.argtypes = [vp, C.c_int32, C.c_uint32, C.c_char_p, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.axr_mesh_read.argtypes = [vp, C.c_int32, _f32p, _u32p]
+    lib.axr_parse_mtl.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(MtlEntry), C.c_uint32, C.POINTER(C.c_uint32)]
     lib.axr_clear.argtypes = [vp, C.c_uint32, C.c_float]
     lib.axr_upload_framebuffer.argtypes = [vp, C.c_void_p, C.c_void_p]
     lib.axr_upload_framebuffer_async.argtypes = [vp, C.c_void_p, C.c_void_p]
@@ -222,6 +237,25 @@ class Device:
         self._check(self.lib.axr_generate_tangents(self.h, v.ctypes.data_as(_f32p), v.shape[0], f.ctypes.data_as(_u32p), f.shape[0],
                                                    out.ctypes.data_as(_f32p)))
         return out
+
+    def load_obj(self, text_or_path):
+        """AR::Mesh(path) behind the C ABI (axr_load_obj / axr_load_obj_file): bytes = OBJ text, str = path.
+        Returns (mesh handle, vertices (V,14) f32, faces (T,3) u32, [MaterialGroup...]) — the arrays are the reference loader's."""
+        out, info = C.c_int32(-1), ObjInfo()
+        if isinstance(text_or_path, (bytes, bytearray)):
+            self._check(self.lib.axr_load_obj(self.h, bytes(text_or_path), len(text_or_path), C.byref(out), C.byref(info)))
+        else:
+            self._check(self.lib.axr_load_obj_file(self.h, os.fsencode(text_or_path), C.byref(out), C.byref(info)))
+        v = np.zeros((info.n_verts, 14), dtype=np.float32)
+        f = np.zeros((info.n_faces, 3), dtype=np.uint32)
+        self._check(self.lib.axr_mesh_read(self.h, out.value, v.ctypes.data_as(_f32p), f.ctypes.data_as(_u32p)))
+        groups = []
+        for g in range(info.n_groups):
+            name = C.create_string_buffer(256)
+            first, count = C.c_uint64(), C.c_uint64()
+            self._check(self.lib.axr_mesh_group_info(self.h, out.value, g, name, 256, C.byref(first), C.byref(count)))
+            groups.append(MaterialGroup(name.value.decode("utf-8", "replace"), int(first.value), int(count.value)))
+        return out.value, v, f, groups
 
     def update_mesh_vertices(self, mesh: int, vertices: np.ndarray):
         """Re-send the vertices of an uploaded mesh (same count, same faces)."""
@@ -377,6 +411,21 @@ class Device:
         self.set_shader(scene.shader, scene.light_dir, scene.light_color)
         self.set_sampler(scene.sampler)
         return mesh
+
+
+def parse_mtl(text: bytes):
+    """axr_parse_mtl: [(name, Ns, {slot: path})] for the five texture slots, in file order."""
+    lib = load_library()
+    n = C.c_uint32(0)
+    rc = lib.axr_parse_mtl(text, len(text), None, 0, C.byref(n))
+    if rc:
+        raise AxrError(f"axr_parse_mtl failed: {rc}")
+    arr = (MtlEntry * max(1, n.value))()
+    lib.axr_parse_mtl(text, len(text), arr, n.value, C.byref(n))
+    slots = ("diffuse", "bump", "metallic", "roughness", "ao")
+    return [(arr[i].name.decode("utf-8", "replace"), float(arr[i].specular_exponent),
+             {slots[k]: bytes(arr[i].map[k]).split(b"\0", 1)[0].decode("utf-8", "replace") for k in range(5) if arr[i].has_map[k]})
+            for i in range(n.value)]
 
 
 # ------------------------------------------------------------------------------------------- present

@@ -15,6 +15,7 @@
 #include "../../include/axr_b200.h"
 #include "axr_kernels.cuh"
 #include "axr_tangents.cuh"
+#include "axr_obj.hpp"
 
 using namespace axr;
 
@@ -30,7 +31,10 @@ struct DeviceMesh {
 	unsigned* idx = nullptr;
 	float4* sv[2] = {nullptr, nullptr};  // per-draw screen-space vertex records (16 B each), one per draw slot
 	unsigned long long n_verts = 0, n_faces = 0;
-	std::vector<unsigned long long> group_first;  // n_groups + 1
+	std::vector<unsigned long long> group_first;  // n_groups + 1; faces before group_first[0] belong to no group and are not drawn
+	std::vector<std::string> group_names;         // axr_load_obj only
+	std::vector<float> host_vertices;             // axr_load_obj only: the loader's arrays (AR::Vertex layout), for axr_mesh_read
+	std::vector<uint32_t> host_indices;
 	std::vector<Material> materials;              // host copy
 	Material* d_materials = nullptr;
 	unsigned long long* d_group_first = nullptr;
@@ -325,6 +329,7 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 	mv.material0 = m.materials.empty() ? Material{} : m.materials[0];
 	mv.group_first = m.d_group_first;
 	mv.n_groups = (int)m.materials.size();
+	mv.first_face = (unsigned)m.group_first[0];
 
 	// ---- geometry stages on geom_stream. The slot was last used two draws ago: wait until that draw's tile kernel has
 	//      consumed it (it resets the keys, flags and cursors it read).
@@ -628,7 +633,8 @@ int axr_upload_mesh(axr_ctx* ctx, const float* vertices, uint64_t n_verts, const
 	if (!groups || n_groups == 0) {
 		m.group_first = {0ull, (unsigned long long)n_faces};
 	} else {
-		unsigned long long expect = 0;
+		// (the faces of an OBJ in front of its first `usemtl` belong to no group: drawMesh walks the groups, :176-179, so they are never drawn)
+		unsigned long long expect = groups[0].first_face;
 		for (uint32_t g = 0; g < n_groups; ++g) {
 			if (groups[g].first_face != expect) return fail(ctx, AXR_ERR_INVALID, "axr_upload_mesh: group %u does not start where group %u ends", g, g ? g - 1 : 0);
 			m.group_first.push_back(groups[g].first_face);
@@ -673,6 +679,86 @@ int axr_upload_mesh(axr_ctx* ctx, const float* vertices, uint64_t n_verts, const
 	for (size_t i = 0; i < ctx->meshes.size(); ++i) if (!ctx->meshes[i].live) { slot = i; break; }
 	if (slot == ctx->meshes.size()) ctx->meshes.push_back(std::move(m)); else ctx->meshes[slot] = std::move(m);
 	*out = (axr_mesh)slot;
+	return AXR_OK;
+}
+
+// ---- OBJ / MTL ingestion (reference src/mesh.cpp): text parse + de-duplication on the host (axr_obj.hpp), tangents on the device
+int axr_load_obj(axr_ctx* ctx, const char* text, size_t len, axr_mesh* out, axr_obj_info* info) {
+	if (!ctx) return AXR_ERR_INVALID;
+	if (!out || (len && !text)) return fail(ctx, AXR_ERR_INVALID, "axr_load_obj: null argument");
+	axr_obj::Parsed ps;
+	if (!axr_obj::parse_obj(text, len, ps)) return fail(ctx, AXR_ERR_INVALID, "axr_load_obj: %s", ps.error.c_str());
+	const uint64_t nv = ps.v8.size() / 8, nf = ps.idx.size() / 3;
+	std::vector<float> v14(nv * 14);
+	int rc = axr_generate_tangents(ctx, ps.v8.data(), nv, ps.idx.data(), nf, v14.data());
+	if (rc) return rc;
+	// groups as the reference's loader leaves them; an OBJ without `usemtl` has none and the reference draws nothing of it
+	std::vector<axr_group> groups;
+	for (const auto& g : ps.groups) groups.push_back({g.first_face, g.face_count});
+	if (groups.empty()) groups.push_back({nf, 0});
+	rc = axr_upload_mesh(ctx, v14.data(), nv, ps.idx.data(), nf, groups.data(), (uint32_t)groups.size(), out);
+	if (rc) return rc;
+	DeviceMesh& m = ctx->meshes[*out];
+	for (const auto& g : ps.groups) m.group_names.push_back(g.name);
+	m.host_vertices.swap(v14);
+	m.host_indices.swap(ps.idx);
+	if (info) {
+		info->n_verts = nv; info->n_faces = nf;
+		info->n_groups = (uint32_t)ps.groups.size(); info->reserved = 0;
+		info->first_drawn_face = ps.groups.empty() ? nf : ps.groups[0].first_face;
+	}
+	return AXR_OK;
+}
+
+int axr_load_obj_file(axr_ctx* ctx, const char* path, axr_mesh* out, axr_obj_info* info) {
+	if (!ctx) return AXR_ERR_INVALID;
+	if (!path || !out) return fail(ctx, AXR_ERR_INVALID, "axr_load_obj_file: null argument");
+	FILE* fh = fopen(path, "rb");
+	if (!fh) return fail(ctx, AXR_ERR_INVALID, "axr_load_obj_file: cannot open %s", path);
+	std::string text;
+	char buf[1 << 16];
+	size_t n;
+	while ((n = fread(buf, 1, sizeof buf, fh)) > 0) text.append(buf, n);
+	fclose(fh);
+	return axr_load_obj(ctx, text.data(), text.size(), out, info);
+}
+
+int axr_mesh_group_info(axr_ctx* ctx, axr_mesh mh, uint32_t group, char* name, size_t name_cap, uint64_t* first_face, uint64_t* face_count) {
+	if (!ctx) return AXR_ERR_INVALID;
+	if (!valid_mesh(ctx, mh)) return fail(ctx, AXR_ERR_INVALID, "axr_mesh_group_info: bad mesh handle %d", mh);
+	const DeviceMesh& m = ctx->meshes[mh];
+	if (group >= m.group_names.size()) return fail(ctx, AXR_ERR_INVALID, "axr_mesh_group_info: group %u of %zu (meshes loaded with axr_load_obj only)", group, m.group_names.size());
+	if (name && name_cap) { strncpy(name, m.group_names[group].c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+	if (first_face) *first_face = m.group_first[group];
+	if (face_count) *face_count = m.group_first[group + 1] - m.group_first[group];
+	return AXR_OK;
+}
+
+int axr_mesh_read(axr_ctx* ctx, axr_mesh mh, float* vertices, uint32_t* indices) {
+	if (!ctx) return AXR_ERR_INVALID;
+	if (!valid_mesh(ctx, mh)) return fail(ctx, AXR_ERR_INVALID, "axr_mesh_read: bad mesh handle %d", mh);
+	const DeviceMesh& m = ctx->meshes[mh];
+	if (m.host_vertices.size() != m.n_verts * 14 || m.host_indices.size() != m.n_faces * 3)
+		return fail(ctx, AXR_ERR_INVALID, "axr_mesh_read: the loader's arrays are kept for meshes loaded with axr_load_obj only");
+	if (vertices && m.n_verts) memcpy(vertices, m.host_vertices.data(), m.host_vertices.size() * sizeof(float));
+	if (indices && m.n_faces) memcpy(indices, m.host_indices.data(), m.host_indices.size() * sizeof(uint32_t));
+	return AXR_OK;
+}
+
+int axr_parse_mtl(const char* text, size_t len, axr_mtl_entry* out, uint32_t cap, uint32_t* n_out) {
+	if ((len && !text) || !n_out || (cap && !out)) return AXR_ERR_INVALID;
+	std::vector<axr_obj::MtlEntry> v;
+	axr_obj::parse_mtl(text, len, v);
+	*n_out = (uint32_t)v.size();
+	for (uint32_t i = 0; i < v.size() && i < cap; ++i) {
+		memset(&out[i], 0, sizeof out[i]);
+		strncpy(out[i].name, v[i].name.c_str(), sizeof out[i].name - 1);
+		out[i].specular_exponent = v[i].specular_exponent;
+		for (int k = 0; k < 5; ++k) {
+			out[i].has_map[k] = v[i].has_map[k] ? 1 : 0;
+			strncpy(out[i].map[k], v[i].map[k].c_str(), sizeof out[i].map[k] - 1);
+		}
+	}
 	return AXR_OK;
 }
 

@@ -81,6 +81,7 @@ struct MeshView {
 	Material material0;                     // copy of materials[0]: single-group meshes read it from the kernel parameters (constant bank)
 	const unsigned long long* group_first;  // n_groups + 1 entries (ascending), only read when n_groups > 1
 	int n_groups;
+	unsigned first_face;                    // faces before it belong to no material group and are not drawn
 };
 
 // ------------------------------------------------------------------------------------------------ utility kernels
@@ -497,7 +498,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(
 		const unsigned l = r * SETUP_THREADS + threadIdx.x;
 		const unsigned f = base + l;
 		bool clip = false;
-		if (f < nf) {
+		if (f < nf && f >= mesh.first_face) {
 			unsigned i0, i1, i2;
 			if (SETUP_ROUNDS > 1) {
 				i0 = s_idx[3u * l]; i1 = s_idx[3u * l + 1]; i2 = s_idx[3u * l + 2];

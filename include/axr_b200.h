@@ -110,7 +110,8 @@ int axr_abi_version(void);
  *      (reference src/tiled_pipeline.cpp:157-159,176-179) and Texture(path) data (reference src/texture.cpp:21-36).
  *      vertices: n_verts x 14 f32 in AR::Vertex layout (reference include/mesh.hpp:9-18), 56-byte stride.
  *      indices: 3 u32 per face (reference asserts triangles, src/tiled_pipeline.cpp:202).
- *      groups may be NULL: one group covering every face. */
+ *      groups may be NULL: one group covering every face. Groups are contiguous ascending face ranges ending at n_faces; the first
+ *      may start after face 0: the faces in front of it belong to no group and are not drawn (an OBJ's faces before its first `usemtl`). */
 int axr_upload_mesh(axr_ctx* ctx, const float* vertices, uint64_t n_verts, const uint32_t* indices,
                     uint64_t n_faces, const axr_group* groups, uint32_t n_groups, axr_mesh* out);
 int axr_free_mesh(axr_ctx* ctx, axr_mesh mesh);
@@ -124,6 +125,32 @@ int axr_free_texture(axr_ctx* ctx, axr_tex tex);
  * (reference include/mesh.hpp:20-34). Pass AXR_NO_TEXTURE for absent maps. */
 int axr_set_material(axr_ctx* ctx, axr_mesh mesh, uint32_t group, axr_tex diffuse, axr_tex bump, axr_tex metallic,
                      axr_tex roughness, axr_tex ao, float specular_exponent);
+
+/* ---- mesh ingestion: replaces `AR::Mesh(path)` (reference src/mesh.cpp:8-27): parseModelFile (:300-415 — OBJ text, value
+ *      de-duplication of (position, uv, normal) in first-occurrence order, fan triangulation, one material group per `usemtl`),
+ *      then calculateTangentBitangent (:222-298, on the device) and the upload. The arrays equal the reference loader's bit for bit
+ *      (axr_mesh_read returns them: n_verts x 14 f32 in AR::Vertex layout, 3 u32 per face). As in the reference, faces in front of
+ *      the first `usemtl` belong to no group and are not drawn (drawMesh walks the groups, src/tiled_pipeline.cpp:176-179); an OBJ
+ *      without `usemtl` draws nothing. A face index without digits makes the reference's std::stoi throw; here it is AXR_ERR_INVALID.
+ *      Materials stay with the caller (textures are decoded by stb_image in the reference): axr_parse_mtl lists, per `newmtl`, the
+ *      name, Ns and the texture paths of the five maps the shaders read (loadMaterial / parseMaterialData, :65-220; a later entry
+ *      with the same name replaces an earlier one, as in the reference's map); feed them to axr_upload_texture / axr_set_material. */
+typedef struct axr_obj_info {
+	uint64_t n_verts, n_faces;
+	uint32_t n_groups, reserved;
+	uint64_t first_drawn_face;   /* == n_faces when the OBJ has no `usemtl` */
+} axr_obj_info;
+typedef struct axr_mtl_entry {
+	char name[128];
+	float specular_exponent;     /* Ns */
+	int has_map[5];              /* diffuse (map_Kd), bump (map_Bump | bump | norm), metallic (map_Ks | refl), roughness (map_Ns), ao (map_A0) */
+	char map[5][512];            /* path as written in the file, blanks trimmed; relative to the MTL's directory */
+} axr_mtl_entry;
+int axr_load_obj(axr_ctx* ctx, const char* obj_text, size_t len, axr_mesh* out, axr_obj_info* info /* may be NULL */);
+int axr_load_obj_file(axr_ctx* ctx, const char* path, axr_mesh* out, axr_obj_info* info);
+int axr_mesh_group_info(axr_ctx* ctx, axr_mesh mesh, uint32_t group, char* name, size_t name_cap, uint64_t* first_face, uint64_t* face_count);
+int axr_mesh_read(axr_ctx* ctx, axr_mesh mesh, float* vertices /* n_verts x 14, may be NULL */, uint32_t* indices /* may be NULL */);
+int axr_parse_mtl(const char* mtl_text, size_t len, axr_mtl_entry* out, uint32_t cap, uint32_t* n_out /* entries in the file */);
 
 /* ---- mesh ingestion helper: Mesh::calculateTangentBitangent (reference src/mesh.cpp:222-298) on the device.
  *      in: n_verts x 8 f32 (position3, uv2, normal3) as the OBJ parser leaves them + 3 u32 per face;

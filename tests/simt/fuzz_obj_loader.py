@@ -80,6 +80,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=60.0)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--native", action="store_true", help="check axr_load_obj_file (the C++ loader behind the C ABI) instead of axiomr_b200/obj.py; needs AXR_B200_LIB")
     a = ap.parse_args()
     if not po.ref_available():
         print("reference build not available")
@@ -106,8 +107,16 @@ def main():
             want_v, want_f = po.ref_load_obj(path)
         except Exception as e:  # the reference throws on some inputs (std::stoi on junk); those are not parity cases
             continue
-        m = obj.load_obj(path, texture_loader=lambda p: None, device=dev)
-        got_v, got_f = m.getVertices(), m.getFaces()
+        if a.native:
+            try:
+                mh, got_v, got_f, _ = dev.load_obj(path)
+            except api.AxrError as e:  # the reference accepted the file: the native loader has to as well
+                print(f"MISMATCH seed={a.seed} file #{n}: axr_load_obj_file refused what the reference loaded: {e}", flush=True)
+                sys.exit(1)
+            dev.free_mesh(mh)
+        else:
+            m = obj.load_obj(path, texture_loader=lambda p: None, device=dev)
+            got_v, got_f = m.getVertices(), m.getFaces()
         ok = got_v.shape == want_v.shape and got_f.shape == want_f.shape and np.array_equal(got_f, want_f)
         if ok:
             same = (got_v.view(np.uint32) == want_v.view(np.uint32)) | (np.isnan(got_v) & np.isnan(want_v))
@@ -120,7 +129,7 @@ def main():
             sys.exit(1)
         n += 1
         nfaces += int(want_f.shape[0])
-    print(f"FUZZ OK seed={a.seed}: {n} OBJ files, {nfaces} faces, obj.py{' + CUDA tangent kernels' if dev else ''} == reference loader bit for bit", flush=True)
+    print(f"FUZZ OK seed={a.seed}: {n} OBJ files, {nfaces} faces, {'axr_load_obj_file' if a.native else 'obj.py'}{' + CUDA tangent kernels' if dev else ''} == reference loader bit for bit", flush=True)
 
 
 if __name__ == "__main__":

@@ -714,3 +714,95 @@ def test_discard_shader_composites_bands_and_host_framebuffer(po):
     with pytest.raises(api.AxrError) as e:
         pipe.drawMesh(b.model, api.Mesh(b.vertices, b.indices, {"m0": api.Material("m0")}))
     assert e.value.code == -5
+
+
+def test_obj_ingestion_behind_the_c_abi_matches_the_reference_loader(po, tmp_path):
+    """axr_load_obj / axr_load_obj_file (text parse + value de-duplication in C++, tangents on the device) against the arrays the
+    reference's own loader AR::Mesh(path) produced (tests/golden/obj_loader.npz): vertices incl. tangents / bitangents, vertex order,
+    faces and groups bit for bit; then the loaded mesh renders like the same arrays uploaded by hand."""
+    import os
+    from axiomr_b200 import api
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "obj_loader.npz"))
+    dev = api.Device(320, 240)
+    try:
+        for name in ("head", "quad", "poly"):
+            text = z[name + "_obj"].tobytes()
+            path = tmp_path / f"{name}.obj"
+            path.write_bytes(text)
+            for src in (text, str(path)):
+                mesh, v, f, groups = dev.load_obj(src)
+                want = z[name + "_vertices"]
+                assert np.array_equal(f, z[name + "_faces"]), name
+                assert v.shape == want.shape, name
+                ok = (v.view(np.uint32) == want.view(np.uint32)) | np.isnan(want)
+                assert ok.all() and np.array_equal(np.isnan(v), np.isnan(want)), (name, np.argwhere(~ok)[:5])
+                assert len(groups) == 1 and groups[0].materialName == "m0" and groups[0].startIndex == 0 and groups[0].faceCount == f.shape[0]
+                dev.free_mesh(mesh)
+        # the loaded mesh draws like the same arrays uploaded through axr_upload_mesh
+        mesh, v, f, groups = dev.load_obj(z["head_obj"].tobytes())
+        sc = S.Scene("obj_head", 320, 240, v, f, S.SHADER_FLAT)
+        dev.set_uniforms(sc.view_proj, sc.cam_pos)
+        dev.set_shader(sc.shader, sc.light_dir, sc.light_color)
+        dev.clear()
+        dev.draw_mesh(mesh, sc.model)
+        c1, d1 = dev.resolve()
+        c0, d0, _ = po.oracle_render(sc, threads=4)
+        m = po.compare(c1, d1, c0, d0)
+        assert m["covered"] > 1000 and m["coverage_mismatch"] == 0 and m["depth_bit_mismatch"] == 0 and m["color_max_diff"] <= 1, m
+    finally:
+        dev.close()
+
+
+def test_obj_faces_outside_every_material_group_are_not_drawn(po):
+    """reference src/tiled_pipeline.cpp:176-179 walks the material groups, and parseModelFile (src/mesh.cpp:336-346) opens a group
+    at each `usemtl`: faces in front of the first one belong to none and are never drawn; an OBJ without `usemtl` draws nothing.
+    Also: value-equal vertices from different `v` lines merge, corners with a bad position index are dropped, -0 == +0."""
+    from axiomr_b200 import api
+    obj = b"""# two triangles before any usemtl, then a quad in group a and a triangle in group b
+v -1 -1 0
+v 1 -1 0
+v 0 1 0
+v -1 -1 0
+vt 0 0
+vt 1 0
+vn 0 0 1
+f 1/1/1 2/2/1 3/1/1
+f 4/1/1 2/2/1 3/1/1
+usemtl a
+v -0.5 -0.5 -0.0
+v 0.5 -0.5 0.0
+v 0.5 0.5 0
+v -0.5 0.5 0
+f 5//1 6//1 7//1 8//1 99//1 0//1
+usemtl b
+f 6/1/1 7/2/1 3/1/1
+"""
+    dev = api.Device(200, 150)
+    try:
+        mesh, v, f, groups = dev.load_obj(obj)
+        assert f.shape[0] == 5 and v.shape[0] == 8, (f.shape, v.shape)          # 3 + 4 unique corners + (7, vt 2); `v 4` merges into `v 1`, 6/1/1 into 6//1 (vt 1 is 0 0)
+        assert np.array_equal(f[0], f[1])                                        # value-equal vertices from different lines
+        assert [(g.materialName, g.startIndex, g.faceCount) for g in groups] == [("a", 2, 2), ("b", 4, 1)]
+        sc = S.Scene("obj_groups", 200, 150, v, f[2:], S.SHADER_FLAT)            # what the reference draws: the grouped faces
+        dev.set_uniforms(sc.view_proj, sc.cam_pos)
+        dev.set_shader(sc.shader, sc.light_dir, sc.light_color)
+        dev.clear()
+        dev.draw_mesh(mesh, sc.model)
+        c1, d1 = dev.resolve()
+        assert dev.stats()["faces"] == 5
+        c0, d0, _ = po.oracle_render(sc, threads=2)
+        m = po.compare(c1, d1, c0, d0)
+        assert m["covered"] > 100 and m["coverage_mismatch"] == 0 and m["depth_bit_mismatch"] == 0 and m["color_max_diff"] <= 1, m
+        # no usemtl at all: nothing is drawn
+        mesh2, v2, f2, groups2 = dev.load_obj(b"v -1 -1 0\nv 1 -1 0\nv 0 1 0\nf 1 2 3\n")
+        assert f2.shape[0] == 1 and groups2 == []
+        dev.clear()
+        dev.draw_mesh(mesh2, sc.model)
+        c2, d2 = dev.resolve()
+        assert np.isinf(d2).all()
+        # std::stoi would throw in the reference: an error here, and the context stays usable
+        with pytest.raises(api.AxrError):
+            dev.load_obj(b"v 0 0 0\nf a b c\n")
+        dev.clear()
+    finally:
+        dev.close()

@@ -137,6 +137,22 @@ def test_obj_loader_matches_reference_loader_golden(tmp_path):
     assert abs(m.getMaterial("m0").specularExponent - 0.25) < 1e-7
 
 
+def test_mtl_parse_behind_the_c_abi(tmp_path):
+    """axr_parse_mtl (reference src/mesh.cpp:65-220): names, Ns, the five texture slots with their aliases, trimmed paths with
+    blanks inside, statements before the first newmtl ignored — and the same answers as the Python mirror on the golden MTL."""
+    from axiomr_b200 import api
+    text = (b"Ns 9\nmap_Kd ignored.png\n# comment\nnewmtl first\nNs 0.25\nKd 1 0 0\nmap_Kd   tex/my diffuse.png \t\r\n"
+            b"bump\tb.png\nrefl m.png\nmap_Ns r.png\nmap_A0 a.png\n\nnewmtl second\nnorm n2.png\nmap_Ks k2.png\nNs 1e1\n")
+    got = api.parse_mtl(text)
+    assert [g[0] for g in got] == ["first", "second"]
+    assert got[0][1] == np.float32(0.25) and got[1][1] == 10.0
+    assert got[0][2] == {"diffuse": "tex/my diffuse.png \t\r".rstrip(" \t"), "bump": "b.png", "metallic": "m.png", "roughness": "r.png", "ao": "a.png"}
+    assert got[1][2] == {"bump": "n2.png", "metallic": "k2.png"}
+    z = np.load(os.path.join(ROOT, "tests", "golden", "obj_loader.npz"))
+    got = api.parse_mtl(z["poly_mtl"].tobytes())
+    assert got[0][0] == "m0" and abs(got[0][1] - 0.25) < 1e-7
+
+
 def test_bench_reference_arm_line_and_no_cpu_fallback():
     """bench.py --impl reference prints ONE JSON line with the contract's keys (tiny workload, runs on the CPU);
     the B200 arm refuses to run without a GPU instead of falling back."""

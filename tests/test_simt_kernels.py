@@ -181,6 +181,23 @@ def test_obj_ingestion_fuzz_with_cuda_tangent_kernels():
     assert r.returncode == 0 and "FUZZ OK" in r.stdout and "CUDA tangent kernels" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
 
 
+def test_native_obj_ingestion_fuzz_against_the_reference_loader():
+    """The same fuzzer for 10 s on axr_load_obj_file — the C++ OBJ parse + de-duplication behind the C ABI (csrc/axr_obj.hpp) with the
+    CUDA tangent kernels — against the reference's own loader AR::Mesh(path): every file the reference accepts loads, arrays bit for bit."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libaxr_ref.so")):
+        pytest.skip("reference build not available")
+    sys.path.insert(0, os.path.join(ROOT, "tests", "simt"))
+    try:
+        import build as simt_build
+    finally:
+        sys.path.pop(0)
+    lib = simt_build.build()
+    env = dict(os.environ, AXR_B200_LIB=lib, AXR_SIMT_TESTS_ONLY="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "simt", "fuzz_obj_loader.py"), "--seconds", "10", "--seed", "6", "--native"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "FUZZ OK" in r.stdout and "axr_load_obj_file" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
 def test_ab_harness_dry_run(tmp_path):
     """tools/ab.py (the A/B timing harness the GPU calls use) end to end on the interpreter build: variant discovery, parity spot
     check, timed loop, per-kernel times, e2e column, JSON records. Times mean nothing here; the point is that the tool still runs."""
