@@ -86,6 +86,7 @@ ABI_SYMBOLS = [
     "axr_host_free", "axr_stream", "axr_framebuffer_device", "axr_set_output", "axr_framebuffer_ipc", "axr_open_ipc",
     "axr_close_ipc", "axr_set_profiling", "axr_get_kernel_times", "axr_set_depth_read", "axr_alloc_shared", "axr_free_shared", "axr_set_overlap", "axr_upload_framebuffer_async", "axr_draw_mesh_host", "axr_generate_tangents", "axr_measure_fp32_issue", "axr_set_color_math", "axr_update_mesh_vertices", "axr_dirty_map_entries", "axr_set_dirty_map", "axr_clear_dirty_tiles",
     "axr_load_obj", "axr_load_obj_file", "axr_mesh_group_info", "axr_mesh_read", "axr_parse_mtl",
+    "axr_load_shader_plugin", "axr_set_shader_user",
 ]
 STAGES = ["vertex_xform", "setup_raster", "scan_tiles", "bin_scatter", "tile_shade"]
 
@@ -129,6 +130,8 @@ def _bind(lib):
     lib.axr_set_shader.argtypes = [vp, C.c_int, C.POINTER(_ShaderParams), C.c_size_t]
     lib.axr_set_sampler.argtypes = [vp, C.c_int]
     lib.axr_set_color_math.argtypes = [vp, C.c_int]
+    lib.axr_load_shader_plugin.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int)]
+    lib.axr_set_shader_user.argtypes = [vp, _f32p, C.c_uint32]
     lib.axr_load_obj.argtypes = [vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(ObjInfo)]
     lib.axr_load_obj_file.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(ObjInfo)]
     lib.axr_mesh_group_info.argtypes = [vp, C.c_int32, C.c_uint32, C.c_char_p, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -281,6 +284,16 @@ class Device:
         p.light_dir[:] = [float(x) for x in light_dir]
         p.light_color[:] = [float(x) for x in light_color]
         self._check(self.lib.axr_set_shader(self.h, kind, C.byref(p), C.sizeof(p)))
+
+    def load_shader_plugin(self, path: str) -> int:
+        """A user-written shader functor compiled with tools/build_shader_plugin.py: returns the shader kind for set_shader()."""
+        kind = C.c_int(-1)
+        self._check(self.lib.axr_load_shader_plugin(self.h, os.fsencode(path), C.byref(kind)))
+        return kind.value
+
+    def set_shader_user(self, values=()):
+        v = np.ascontiguousarray(np.asarray(values, dtype=np.float32).reshape(-1))
+        self._check(self.lib.axr_set_shader_user(self.h, v.ctypes.data_as(_f32p) if v.size else None, v.size))
 
     def set_sampler(self, sampler: int):
         self._check(self.lib.axr_set_sampler(self.h, sampler))
@@ -739,6 +752,8 @@ class TiledPipeline(Pipeline):
                 self.invalidate(mesh)
         if k not in self._mesh_cache:
             groups = [(g.startIndex, g.faceCount) for g in mesh.getMaterialGroups()]
+            if not groups:  # no group, nothing to draw (the C ABI reads "no groups given" as one group over every face)
+                groups = [(mesh.getFaces().shape[0], 0)]
             h = self.device.upload_mesh(mesh.getVertices(), mesh.getFaces(), groups)
             self.last_h2d_bytes += mesh.getVertices().nbytes + mesh.getFaces().nbytes
             for gi, g in enumerate(mesh.getMaterialGroups()):

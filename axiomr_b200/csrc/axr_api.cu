@@ -3,6 +3,7 @@
 // uniforms, per-draw buffers sized from counts (instead of the fixed 32 MB arenas, include/tiled_pipeline.hpp:98-107),
 // kernel sequencing on one CUDA stream (instead of ThreadPool futures, :183-248, :281-308).
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cstdarg>
 #include <cstddef>
@@ -50,6 +51,15 @@ struct DeviceTexture {
 	int w = 0, h = 0, tiles_x = 0;
 };
 
+// A shader functor compiled by its author and opened at run time (axr_load_shader_plugin, include/axr_shader_plugin.cuh)
+struct ShaderPlugin {
+	void* handle = nullptr;
+	int (*launch)(const void*, const void*, const void*, const void*, int, int, int, unsigned, unsigned, void*) = nullptr;
+	bool discards = false;
+	unsigned textures = 0;
+	std::string path;
+};
+
 struct PendingDraw {
 	bool valid = false;
 	int slot = 0;
@@ -82,6 +92,8 @@ struct axr_ctx {
 	float cam_pos[3];
 	int shader_kind = AXR_SHADER_FLAT;
 	axr_shader_params shader_params{};
+	float shader_user[8] = {};
+	std::vector<ShaderPlugin> plugins;  // shader kind AXR_SHADER_PLUGIN_BASE + i
 
 	// Raster state of one draw in flight. Two slots alternate so that the geometry stages of draw i+1 (vertex, setup, bins — on
 	// geom_stream) overlap the tile / shading kernel of draw i (on the main stream): the two halves stress different parts of
@@ -268,10 +280,30 @@ cudaEvent_t prof_mark(axr_ctx* ctx, cudaStream_t s) {
 }
 
 
+// which: 0 = k_tile_shade over a gx x gy grid of tiles, 1 = k_shade_clipped (fixed grid)
+using TileLaunch = int (*)(axr_ctx*, const MeshView&, const Uniforms&, const FrameParams&, const TileIn&, int which, unsigned gx, unsigned gy);
+template <typename Shader, int SMP, bool FAST>
+int launch_builtin(axr_ctx* ctx, const MeshView& mv, const Uniforms& u, const FrameParams& fp, const TileIn& in, int which, unsigned gx, unsigned gy) {
+	if (which == 0) k_tile_shade<Shader, SMP, FAST><<<dim3(gx, gy), TILE_THREADS, 0, ctx->stream>>>(mv, u, fp, in);
+	else k_shade_clipped<Shader, SMP><<<CLIP_SHADE_CTAS, CLIP_SHADE_THREADS, 0, ctx->stream>>>(mv, u, fp, in);
+	return AXR_OK;
+}
+int launch_plugin(axr_ctx* ctx, const MeshView& mv, const Uniforms& u, const FrameParams& fp, const TileIn& in, int which, unsigned gx, unsigned gy) {
+	const ShaderPlugin& p = ctx->plugins[ctx->shader_kind - AXR_SHADER_PLUGIN_BASE];
+	const int e = p.launch(&mv, &u, &fp, &in, ctx->device, u.sampler, which, gx, gy, ctx->stream);
+	if (e) return fail(ctx, AXR_ERR_CUDA, "shader plug-in %s: launch failed: %s", p.path.c_str(), cudaGetErrorString((cudaError_t)e));
+	return AXR_OK;
+}
+template <typename Shader>
+TileLaunch builtin_launcher(const axr_ctx* ctx, int sampler) {
+	const bool fast = ctx->color_fast && Shader::HAS_FAST;
+	if (sampler) return fast ? &launch_builtin<Shader, 1, true> : &launch_builtin<Shader, 1, false>;
+	return fast ? &launch_builtin<Shader, 0, true> : &launch_builtin<Shader, 0, false>;
+}
+
 // One launch over all tile rows of the band, or (axr_draw_mesh_host) one launch per uploaded row chunk, each behind its upload;
 // then the small kernel for the pixels owned by clipped faces (k_shade_clipped: a fixed grid over a list that is usually empty).
-template <typename Shader, int SMP, bool FAST>
-int launch_tile_kernels(axr_ctx* ctx, const MeshView& mv, const Uniforms& u, const TileIn& in) {
+int launch_tile_kernels(axr_ctx* ctx, TileLaunch fn, const MeshView& mv, const Uniforms& u, const TileIn& in, uint64_t& launches) {
 	const int chunks = ctx->host_chunks > 0 ? ctx->host_chunks : 1;
 	for (int b = 0; b < chunks; ++b) {
 		FrameParams fp = ctx->fp;
@@ -279,17 +311,18 @@ int launch_tile_kernels(axr_ctx* ctx, const MeshView& mv, const Uniforms& u, con
 			fp.ty_lo = ctx->chunk_ty[b]; fp.ty_hi = ctx->chunk_ty[b + 1];
 			cudaStreamWaitEvent(ctx->stream, ctx->up_done[b], 0);
 		}
-		dim3 grid(fp.ntx, fp.ty_hi - fp.ty_lo);
-		k_tile_shade<Shader, SMP, FAST><<<grid, TILE_THREADS, 0, ctx->stream>>>(mv, u, fp, in);
+		if (int rc = fn(ctx, mv, u, fp, in, 0, (unsigned)fp.ntx, (unsigned)(fp.ty_hi - fp.ty_lo))) return rc;
 	}
-	k_shade_clipped<Shader, SMP><<<CLIP_SHADE_CTAS, CLIP_SHADE_THREADS, 0, ctx->stream>>>(mv, u, ctx->fp, in);
-	return chunks + 1;
+	if (int rc = fn(ctx, mv, u, ctx->fp, in, 1, 0, 0)) return rc;
+	launches += chunks + 1;
+	return AXR_OK;
 }
-template <typename Shader>
-int launch_tile(axr_ctx* ctx, const MeshView& mv, const Uniforms& u, const TileIn& in) {
-	const bool fast = ctx->color_fast && Shader::HAS_FAST;
-	if (u.sampler) return fast ? launch_tile_kernels<Shader, 1, true>(ctx, mv, u, in) : launch_tile_kernels<Shader, 1, false>(ctx, mv, u, in);
-	return fast ? launch_tile_kernels<Shader, 0, true>(ctx, mv, u, in) : launch_tile_kernels<Shader, 0, false>(ctx, mv, u, in);
+
+bool shader_is_plugin(const axr_ctx* ctx, int kind) { return kind >= AXR_SHADER_PLUGIN_BASE && (size_t)(kind - AXR_SHADER_PLUGIN_BASE) < ctx->plugins.size(); }
+// fragment() may return true: the draw is depth-peeled
+bool shader_discards(const axr_ctx* ctx) {
+	if (ctx->shader_kind == AXR_SHADER_CUTOUT) return true;
+	return shader_is_plugin(ctx, ctx->shader_kind) && ctx->plugins[ctx->shader_kind - AXR_SHADER_PLUGIN_BASE].discards;
 }
 
 // One pass of the five kernels. peel: the pass belongs to a depth-peeled draw (draw_peeled below) — the raster sites reject
@@ -297,7 +330,7 @@ int launch_tile(axr_ctx* ctx, const MeshView& mv, const Uniforms& u, const TileI
 int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel) {
 	DeviceMesh& m = ctx->meshes[mh];
 	axr_ctx::DrawSlot& sl = ctx->slot[si];
-	if (peel != (ctx->shader_kind == AXR_SHADER_CUTOUT)) return fail(ctx, AXR_ERR_INVALID, "internal: peel flag does not match the shader");
+	if (peel != shader_discards(ctx)) return fail(ctx, AXR_ERR_INVALID, "internal: peel flag does not match the shader");
 	int rc = sync_materials(ctx, m);
 	if (rc) return rc;
 	// shader / material validation (the reference dereferences null textures, include/shaders/shaders.hpp:178,210)
@@ -308,6 +341,10 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 			return fail(ctx, AXR_ERR_MATERIAL, "CutoutShader needs a diffuse texture on every material group");
 		if (ctx->shader_kind == AXR_SHADER_PBR && (!mat.tex[2].data || !mat.tex[3].data || !mat.tex[4].data))
 			return fail(ctx, AXR_ERR_MATERIAL, "PBRShader needs metallic, roughness and ao textures on every material group");
+		if (shader_is_plugin(ctx, ctx->shader_kind))
+			for (int k = 0; k < 5; ++k)
+				if (((ctx->plugins[ctx->shader_kind - AXR_SHADER_PLUGIN_BASE].textures >> k) & 1u) && !mat.tex[k].data)
+					return fail(ctx, AXR_ERR_MATERIAL, "the plug-in shader needs texture slot %d on every material group", k);
 	}
 	Uniforms u;
 	u.model = load_m4(model);
@@ -320,6 +357,7 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 	u.light_dir = V3(ctx->shader_params.light_dir[0], ctx->shader_params.light_dir[1], ctx->shader_params.light_dir[2]);
 	u.light_color = V3(ctx->shader_params.light_color[0], ctx->shader_params.light_color[1], ctx->shader_params.light_color[2]);
 	u.sampler = ctx->sampler;
+	memcpy(u.user, ctx->shader_user, sizeof u.user);
 
 	MeshView mv;
 	mv.pos = m.pos; mv.attr = m.attr; mv.idx = m.idx; mv.idx4 = m.idx4;
@@ -408,13 +446,18 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 	in.clip_tiles = sl.clip_tiles; in.n_clip_tiles = sl.n_clip_tiles;
 	in.dirty = ctx->dirty_map;
 	in.bin_mode = bin_mode;
+	TileLaunch fn = nullptr;
 	switch (ctx->shader_kind) {
-	case AXR_SHADER_FLAT: launches += launch_tile<FlatShader>(ctx, mv, u, in); break;
-	case AXR_SHADER_PHONG: launches += launch_tile<PhongShader>(ctx, mv, u, in); break;
-	case AXR_SHADER_PBR: launches += launch_tile<PBRShader>(ctx, mv, u, in); break;
-	case AXR_SHADER_CUTOUT: launches += launch_tile<CutoutShader>(ctx, mv, u, in); break;
-	default: return fail(ctx, AXR_ERR_UNSUPPORTED, "unknown shader kind %d", ctx->shader_kind);
+	case AXR_SHADER_FLAT: fn = builtin_launcher<FlatShader>(ctx, u.sampler); break;
+	case AXR_SHADER_PHONG: fn = builtin_launcher<PhongShader>(ctx, u.sampler); break;
+	case AXR_SHADER_PBR: fn = builtin_launcher<PBRShader>(ctx, u.sampler); break;
+	case AXR_SHADER_CUTOUT: fn = builtin_launcher<CutoutShader>(ctx, u.sampler); break;
+	default:
+		if (!shader_is_plugin(ctx, ctx->shader_kind)) return fail(ctx, AXR_ERR_UNSUPPORTED, "unknown shader kind %d", ctx->shader_kind);
+		fn = &launch_plugin;
 	}
+	rc = launch_tile_kernels(ctx, fn, mv, u, in, launches);
+	if (rc) return rc;
 	prof_mark(ctx, ctx->stream);
 	CU(cudaEventRecord(sl.shade_done, ctx->stream));
 	sl.used = true;
@@ -469,7 +512,7 @@ int draw_peeled(axr_ctx* ctx, axr_mesh mh, const float* model, int si) {
 // Entry point of every draw call: picks the raster slot and the plain or the peeled path.
 int draw(axr_ctx* ctx, axr_mesh mh, const float* model) {
 	const int si = (int)(ctx->draw_counter++ & 1u);
-	if (ctx->shader_kind == AXR_SHADER_CUTOUT) return draw_peeled(ctx, mh, model, si);
+	if (shader_discards(ctx)) return draw_peeled(ctx, mh, model, si);
 	return issue_draw(ctx, mh, model, si, false);
 }
 
@@ -591,6 +634,7 @@ void axr_destroy(axr_ctx* ctx) {
 	if (ctx->geom_stream) cudaStreamSynchronize(ctx->geom_stream);
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
 	for (auto& m : ctx->meshes) if (m.live) { cudaFree(m.pos); cudaFree(m.attr); cudaFree(m.idx); cudaFree(m.idx4); cudaFree(m.sv[0]); cudaFree(m.sv[1]); cudaFree(m.d_materials); cudaFree(m.d_group_first); }
+	// shader plug-ins stay mapped: unloading a library with its own static CUDA runtime while the process lives on is not safe
 	for (auto& t : ctx->textures) if (t.live) cudaFree(t.data);
 	for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
 	for (void* p : ctx->shared_allocs) cudaFree(p);
@@ -922,13 +966,49 @@ int axr_set_uniforms(axr_ctx* ctx, const float view_proj[16], const float viewpo
 
 int axr_set_shader(axr_ctx* ctx, int kind, const axr_shader_params* params, size_t params_size) {
 	if (!ctx) return AXR_ERR_INVALID;
-	if (kind != AXR_SHADER_FLAT && kind != AXR_SHADER_PHONG && kind != AXR_SHADER_PBR && kind != AXR_SHADER_CUTOUT)
-		return fail(ctx, AXR_ERR_UNSUPPORTED, "axr_set_shader: no device functor for shader kind %d", kind);
+	if (kind != AXR_SHADER_FLAT && kind != AXR_SHADER_PHONG && kind != AXR_SHADER_PBR && kind != AXR_SHADER_CUTOUT && !shader_is_plugin(ctx, kind))
+		return fail(ctx, AXR_ERR_UNSUPPORTED, "axr_set_shader: no device functor for shader kind %d (a further IShader is added with axr_load_shader_plugin)", kind);
 	if (!params || params_size != sizeof(axr_shader_params)) return fail(ctx, AXR_ERR_INVALID, "axr_set_shader: bad params");
 	CU(cudaSetDevice(ctx->device));
 	if (int rc = check_pending(ctx)) return rc;
 	ctx->shader_kind = kind;
 	ctx->shader_params = *params;
+	return AXR_OK;
+}
+
+int axr_set_shader_user(axr_ctx* ctx, const float* values, uint32_t n) {
+	if (!ctx) return AXR_ERR_INVALID;
+	if (n > 8 || (n && !values)) return fail(ctx, AXR_ERR_INVALID, "axr_set_shader_user: at most 8 floats");
+	CU(cudaSetDevice(ctx->device));
+	if (int rc = check_pending(ctx)) return rc;
+	memset(ctx->shader_user, 0, sizeof ctx->shader_user);
+	if (n) memcpy(ctx->shader_user, values, n * sizeof(float));
+	return AXR_OK;
+}
+
+int axr_load_shader_plugin(axr_ctx* ctx, const char* path, int* kind_out) {
+	if (!ctx) return AXR_ERR_INVALID;
+	if (!path || !kind_out) return fail(ctx, AXR_ERR_INVALID, "axr_load_shader_plugin: null argument");
+	for (size_t i = 0; i < ctx->plugins.size(); ++i)
+		if (ctx->plugins[i].path == path) { *kind_out = AXR_SHADER_PLUGIN_BASE + (int)i; return AXR_OK; }
+	void* h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+	if (!h) return fail(ctx, AXR_ERR_INVALID, "axr_load_shader_plugin: %s", dlerror());
+	auto layout = (unsigned long long (*)(void))dlsym(h, "axr_shader_plugin_layout");
+	auto discards = (int (*)(void))dlsym(h, "axr_shader_plugin_discards");
+	auto textures = (unsigned (*)(void))dlsym(h, "axr_shader_plugin_textures");
+	ShaderPlugin p;
+	p.launch = (decltype(p.launch))dlsym(h, "axr_shader_plugin_launch");
+	if (!layout || !discards || !textures || !p.launch) {
+		dlclose(h);
+		return fail(ctx, AXR_ERR_INVALID, "axr_load_shader_plugin: %s does not export the AXR_SHADER_PLUGIN entry points", path);
+	}
+	if (layout() != plugin_layout_hash()) {
+		dlclose(h);
+		return fail(ctx, AXR_ERR_UNSUPPORTED, "axr_load_shader_plugin: %s was built against other kernel headers than this library (rebuild it)", path);
+	}
+	p.handle = h; p.discards = discards() != 0; p.textures = textures(); p.path = path;
+	ctx->plugins.push_back(p);
+	*kind_out = AXR_SHADER_PLUGIN_BASE + (int)ctx->plugins.size() - 1;
 	return AXR_OK;
 }
 

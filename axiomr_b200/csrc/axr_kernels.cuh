@@ -1112,4 +1112,14 @@ __global__ void __launch_bounds__(CLIP_SHADE_THREADS) k_shade_clipped(const __gr
 	}
 }
 
+// ---- shader plug-ins (include/axr_shader_plugin.cuh): plug-in and library must have been built from the same kernel headers
+// changes whenever a structure that crosses the plugin boundary changes size, or the launch shapes do
+constexpr unsigned long long plugin_layout_hash() {
+	unsigned long long h = 0xA11CE5ull;
+	const unsigned long long parts[] = {sizeof(MeshView), sizeof(Uniforms), sizeof(FrameParams), sizeof(TileIn), sizeof(Material), (unsigned long long)TILE_THREADS,
+	                                    (unsigned long long)GT, (unsigned long long)CLIP_SHADE_THREADS, (unsigned long long)BIN_ROUND, 2ull /* revision */};
+	for (unsigned long long p : parts) h = (h ^ p) * 0x100000001B3ull;
+	return h;
+}
+
 }  // namespace axr

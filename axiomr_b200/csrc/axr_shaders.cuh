@@ -47,6 +47,7 @@ struct Uniforms {
 	v3 light_dir;
 	v3 light_color;
 	int sampler;     // 0 nearest (reference), 1 bilinear (extension)
+	float user[8];   // axr_set_shader_user: free parameters of a plug-in shader (axr_shader_plugin.cuh)
 };
 
 // VertexOutput (reference include/IShader.hpp:11-17) as a flat array of varyings (zNDC is never read by the pipeline).

@@ -178,6 +178,6 @@ def load_obj(path: str, texture_loader=_load_image, device=None) -> Mesh:
     if os.path.exists(mtl):
         with open(mtl, "rb") as fh:
             mats = parse_mtl(fh.read().decode("utf-8", "replace"), directory, texture_loader)
-    if not groups:
-        groups = None
+    # an OBJ without `usemtl` has no material group: drawMesh walks the groups (reference src/tiled_pipeline.cpp:176-179), so the
+    # reference draws nothing of it, and neither does TiledPipeline.drawMesh here (an empty group list stays empty)
     return Mesh(verts, faces, mats if mats else None, groups)

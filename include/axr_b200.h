@@ -44,7 +44,8 @@ typedef enum axr_status {
  * (include/IShader.hpp:38), so the discard branch of the raster loop (src/tiled_pipeline.cpp:571-577) is covered with an
  * alpha-tested Lambert shader written against the reference's IShader contract (oracle/ref_harness.cpp: CutoutShader;
  * needs the diffuse texture, discards where its alpha < 0.5). A draw with it is depth-peeled and synchronous. */
-typedef enum axr_shader_kind { AXR_SHADER_FLAT = 0, AXR_SHADER_PHONG = 1, AXR_SHADER_PBR = 2, AXR_SHADER_CUTOUT = 3 } axr_shader_kind;
+typedef enum axr_shader_kind { AXR_SHADER_FLAT = 0, AXR_SHADER_PHONG = 1, AXR_SHADER_PBR = 2, AXR_SHADER_CUTOUT = 3,
+                               AXR_SHADER_PLUGIN_BASE = 64 /* + i: shaders added at run time, axr_load_shader_plugin */ } axr_shader_kind;
 
 /* Texture::sample mode. NEAREST is the reference (include/texture.hpp:12-34). BILINEAR is an extension
  * (BASELINE.json config 3) with no reference counterpart; it is checked against oracle/axr_oracle.c only. */
@@ -165,6 +166,15 @@ int axr_generate_tangents(axr_ctx* ctx, const float* pos_uv_normal, uint64_t n_v
 int axr_set_uniforms(axr_ctx* ctx, const float view_proj[16], const float viewport[16], const float cam_pos[3]);
 /* replaces Pipeline::setShader(IShader*) (reference src/pipeline.cpp:22-24); params = the shader's public fields. */
 int axr_set_shader(axr_ctx* ctx, int kind, const axr_shader_params* params, size_t params_size);
+/* A further IShader subclass at run time (reference include/IShader.hpp:30-46 — Pipeline::setShader takes any). On the device a shader is
+ * a functor the tile kernels are instantiated with; its author writes it against include/axr_shader_plugin.cuh (the same two
+ * entry points as the plugin contract: vertex() and fragment(), true = discard) and compiles it with nvcc into a shared library
+ * (tools/build_shader_plugin.py). axr_load_shader_plugin opens it, checks that it was built against this library's kernel headers and
+ * returns the shader kind to pass to axr_set_shader (AXR_SHADER_PLUGIN_BASE + i). A plug-in that declares DISCARDS is depth-peeled like
+ * AXR_SHADER_CUTOUT; plug-ins always run the individually rounded (EXACT) colour arithmetic. axr_set_shader_user passes up to 8 floats
+ * to the functor (Uniforms::user) beside the light direction / colour of axr_shader_params. */
+int axr_load_shader_plugin(axr_ctx* ctx, const char* path, int* kind_out);
+int axr_set_shader_user(axr_ctx* ctx, const float* values, uint32_t n);
 int axr_set_sampler(axr_ctx* ctx, int sampler);
 int axr_set_color_math(axr_ctx* ctx, int mode);  /* axr_color_math */
 

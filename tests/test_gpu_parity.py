@@ -806,3 +806,75 @@ f 6/1/1 7/2/1 3/1/1
         dev.clear()
     finally:
         dev.close()
+
+
+def test_shader_plugins_loaded_at_run_time(po):
+    """A user-supplied IShader (reference include/IShader.hpp:30-46): functors written outside the library against
+    include/axr_shader_plugin.cuh, compiled with nvcc (tools/build_shader_plugin.py) and opened with axr_load_shader_plugin.
+    alpha_cut discards (depth-peeled draw) with the arithmetic of CutoutShader — which the unmodified reference pipeline runs as an
+    IShader subclass in oracle/ref_harness.cpp — so its frames must equal the oracle's; lambert_tint is a shader the library does
+    not ship, pinned through its tint = 1 special case and checked to react to its Uniforms::user parameters."""
+    import os
+    import sys
+    if os.environ.get("AXR_SIMT_TESTS_ONLY") == "1":
+        pytest.skip("plug-ins are nvcc-built device code: nothing for the interpreter to run")
+    from axiomr_b200 import api
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    try:
+        from build_shader_plugin import build_plugin
+    finally:
+        sys.path.pop(0)
+    cut = build_plugin(os.path.join(root, "tests", "plugins", "alpha_cut.cu"))
+    tint = build_plugin(os.path.join(root, "tests", "plugins", "lambert_tint.cu"))
+    sc = S.cutout_layers()
+    c0, d0, _ = po.oracle_render(sc, threads=4)
+    dev = api.Device(sc.width, sc.height, sampler=sc.sampler)
+    try:
+        mesh = dev.load_scene(sc)
+        k_cut = dev.load_shader_plugin(cut)
+        assert k_cut >= 64 and dev.load_shader_plugin(cut) == k_cut            # loading twice gives the same kind
+        dev.set_shader(k_cut, sc.light_dir, sc.light_color)
+        dev.set_shader_user([0.5])
+        dev.clear()
+        dev.draw_mesh(mesh, sc.model)
+        c1, d1 = dev.resolve()
+        m = po.compare(c1, d1, c0, d0)
+        assert m["covered"] > 1000 and m["coverage_mismatch"] == 0 and m["depth_bit_mismatch"] == 0 and m["color_max_diff"] <= 1, m
+        assert dev.stats()["kernel_launches"] > 12                             # several peeling passes
+        # threshold 0: nothing is discarded any more, the front layer owns every pixel it covers
+        dev.set_shader_user([0.0])
+        dev.clear()
+        dev.draw_mesh(mesh, sc.model)
+        c2, d2 = dev.resolve()
+        assert (d2 <= d1).all() and (d2 < d1).any()
+        # a shader of our own making: equals the built-in cutout shader where nothing is discarded and the tint is 1
+        k_tint = dev.load_shader_plugin(tint)
+        assert k_tint == k_cut + 1
+        dev.set_shader(k_tint, sc.light_dir, sc.light_color)
+        dev.set_shader_user([1.0, 1.0, 1.0])
+        dev.clear()
+        dev.draw_mesh(mesh, sc.model)
+        c3, d3 = dev.resolve()
+        assert np.array_equal(d3.view(np.uint32), d2.view(np.uint32)) and np.array_equal(c3, c2)
+        dev.set_shader_user([0.5, 1.0, 0.25])
+        dev.clear()
+        dev.draw_mesh(mesh, sc.model)
+        c4, d4 = dev.resolve()
+        vis = np.isfinite(d4)
+        assert np.array_equal(d4.view(np.uint32), d3.view(np.uint32))
+        # colour bytes are B,G,R,A: red halves, green stays, blue quarters (truncation: within one step)
+        assert np.abs(c4[vis][:, 2].astype(int) - c3[vis][:, 2].astype(int) // 2).max() <= 1
+        assert np.array_equal(c4[vis][:, 1], c3[vis][:, 1])
+        assert np.abs(c4[vis][:, 0].astype(int) - c3[vis][:, 0].astype(int) // 4).max() <= 1
+        # not a plug-in / unknown kind: refused, context stays usable
+        with pytest.raises(api.AxrError):
+            dev.load_shader_plugin(os.path.join(root, "oracle", "libaxr_oracle.so"))
+        with pytest.raises(api.AxrError):
+            dev.set_shader(k_tint + 5, sc.light_dir, sc.light_color)
+        dev.set_shader(S.SHADER_FLAT, sc.light_dir, sc.light_color)
+        dev.clear()
+        dev.draw_mesh(mesh, sc.model)
+        dev.sync()
+    finally:
+        dev.close()
