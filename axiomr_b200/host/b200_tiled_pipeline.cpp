@@ -122,8 +122,16 @@ void B200TiledPipeline::drawMesh(const glm::mat4& modelMatrix, const Mesh& mesh)
 		kind = AXR_SHADER_PBR;
 		sp.light_dir[0] = b->lightDirection.x; sp.light_dir[1] = b->lightDirection.y; sp.light_dir[2] = b->lightDirection.z;
 		sp.light_color[0] = b->lightColor.x; sp.light_color[1] = b->lightColor.y; sp.light_color[2] = b->lightColor.z;
+	} else if (auto* u = dynamic_cast<B200PluginShader*>(m_Shader)) {
+		int rcp = axr_load_shader_plugin(m_Ctx, u->path.c_str(), &kind);  // opened once per context, then looked up by path
+		if (rcp != AXR_OK) fail("axr_load_shader_plugin", rcp);
+		sp.light_dir[0] = u->lightDirection.x; sp.light_dir[1] = u->lightDirection.y; sp.light_dir[2] = u->lightDirection.z;
+		sp.light_color[0] = u->lightColor.x; sp.light_color[1] = u->lightColor.y; sp.light_color[2] = u->lightColor.z;
+		rcp = axr_set_shader_user(m_Ctx, u->user, 8);
+		if (rcp != AXR_OK) fail("axr_set_shader_user", rcp);
 	} else {
-		throw std::runtime_error("B200TiledPipeline: this IShader subclass has no device functor (no CPU fallback by design)");
+		throw std::runtime_error("B200TiledPipeline: this IShader subclass has no device functor (no CPU fallback by design); "
+		                         "compile it as a plug-in (include/axr_shader_plugin.cuh) and pass a B200PluginShader");
 	}
 	int rc = axr_set_shader(m_Ctx, kind, &sp, sizeof sp);
 	if (rc != AXR_OK) fail("axr_set_shader", rc);

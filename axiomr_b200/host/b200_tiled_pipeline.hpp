@@ -10,11 +10,14 @@
 //
 // Semantics kept: borrowed pointers, silent return without shader/camera/framebuffer (src/tiled_pipeline.cpp:146), composites
 // onto the framebuffer's current contents with the strict depth test, complete on return. Differences: the thread count is
-// ignored; IShader subclasses other than Flat/Phong/PBRShader throw std::runtime_error (host virtuals cannot run on the device
-// and there is deliberately no CPU fallback); capacity problems surface as std::runtime_error with the axr error text instead
+// ignored; host virtuals cannot run on the device and there is deliberately no CPU fallback, so an IShader subclass other than
+// Flat/Phong/PBRShader is given as a B200PluginShader (below): the handle of a device functor its author compiled with
+// tools/build_shader_plugin.py; any other subclass throws std::runtime_error; capacity problems surface as std::runtime_error with the axr error text instead
 // of std::bad_alloc from the 16 MB arena.
 #pragma once
 #include <cstddef>
+#include <stdexcept>
+#include <string>
 #include <unordered_map>
 #include <vector>
 
@@ -23,6 +26,20 @@
 struct axr_ctx;
 
 namespace AR {
+
+// Pipeline::setShader(IShader*) for a shader of the user's own: the device code lives in a plug-in library (include/axr_shader_plugin.cuh),
+// this object carries its path and parameters. Its host virtuals are never called by B200TiledPipeline (and throw if the reference's
+// CPU pipelines are handed one).
+struct B200PluginShader : public IShader {
+	explicit B200PluginShader(const std::string& pluginPath) : path(pluginPath) {}
+	std::string path;
+	glm::vec3 lightDirection{0.0f, -1.0f, 0.0f};
+	glm::vec3 lightColor{1.0f, 1.0f, 1.0f};
+	float user[8] = {};  // Uniforms::user of the functor
+private:
+	VertexOutput vertex(const Vertex&, int) override { throw std::runtime_error("B200PluginShader has device code only"); }
+	bool fragment(glm::vec3&, glm::vec4&, const VSTransformedTriangle&) override { throw std::runtime_error("B200PluginShader has device code only"); }
+};
 
 class B200TiledPipeline : public Pipeline {
 public:
