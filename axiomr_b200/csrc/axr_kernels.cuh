@@ -454,9 +454,13 @@ __device__ __forceinline__ void prefetch_l1(const void* p) {
 // 16-byte loads (all of them in flight at once), prefetches the screen records they name into L1, and then works through the faces
 // in rounds of one face per thread: the kernel's dependent index -> record latency is paid once per chunk instead of once per face
 // (with one face per thread the load phase is bound by latency x resident warps: loads + cull alone are 70 us of C3's setup kernel).
+#ifndef AXR_CLIP_INLINE
+#define AXR_CLIP_INLINE 0  // 1: a face that needs the clipper is clipped by its own thread inside k_setup_raster (out-of-line call)
+#endif
 template <bool PEEL>
 __global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(const __grid_constant__ MeshView mesh, const float4* __restrict__ sv,
-                                                                const __grid_constant__ FrameParams fp, const __grid_constant__ SetupOut o) {
+                                                                const __grid_constant__ m4 mvp, const __grid_constant__ FrameParams fp,
+                                                                const __grid_constant__ SetupOut o) {
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned nf = (unsigned)mesh.n_faces;  // faces < 2^29 (axr_upload_mesh): 32-bit index arithmetic throughout
 	// CTA -> chunk: the hardware hands out CTAs in index order, so the ~1800 resident ones would all sit in one stretch of the index
@@ -522,12 +526,21 @@ __global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(
 				// all three vertices safely outside one plane: clipTriangle returns nothing (see clip_code_safe_out)
 			} else {
 				clip = true;  // needs the clipper: k_setup_clipped, the next kernel on the stream
+#if AXR_CLIP_INLINE
+				const unsigned c = setup_clipped_face<PEEL>(fp, o, mvp, __ldg(mesh.pos + i0), __ldg(mesh.pos + i1), __ldg(mesh.pos + i2), f);
+				cnt.tris += c & 255u; cnt.small += (c >> 8) & 255u; cnt.binned += c >> 16;
+#endif
 			}
 		}
 		__syncwarp();
 		// Faces for the clipper: warp-aggregated append (any order: keys carry the face ordinal, bins are order-free)
 		const unsigned cm = __ballot_sync(0xffffffffu, clip);
+#if AXR_CLIP_INLINE
+		if (cm && lane == 0) atomicAdd(&o.status->stripes[0][(chunk * (SETUP_THREADS / 32) + (threadIdx.x >> 5)) % STAT_STRIPES], (unsigned)__popc(cm));
+		if (false) {
+#else
 		if (cm) {
+#endif
 			unsigned at = 0;
 			if (lane == 0) at = atomicAdd(o.n_clip_faces, (unsigned)__popc(cm));
 			at = __shfl_sync(0xffffffffu, at, 0);
@@ -595,7 +608,7 @@ __global__ void __launch_bounds__(CLIPSETUP_THREADS) k_setup_clipped(const __gri
 	__threadfence();
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-	for (int c = 1; c < 4; ++c) {
+	for (int c = 0; c < 4; ++c) {
 		unsigned long long acc = 0;
 		for (int i = threadIdx.x; i < STAT_STRIPES; i += CLIPSETUP_THREADS) acc += __ldcg(&o.status->stripes[c][i]);
 		for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
@@ -603,11 +616,8 @@ __global__ void __launch_bounds__(CLIPSETUP_THREADS) k_setup_clipped(const __gri
 	}
 	__syncthreads();
 	if (threadIdx.x < 4) {
-		unsigned long long sum = n;  // clipped_faces
-		if (threadIdx.x) {
-			sum = 0;
-			for (int w = 0; w < CLIPSETUP_THREADS / 32; ++w) sum += s_fold[threadIdx.x][w];
-		}
+		unsigned long long sum = threadIdx.x ? 0ull : (unsigned long long)n;  // clipped_faces: the list (+ the ones clipped in k_setup_raster)
+		for (int w = 0; w < CLIPSETUP_THREADS / 32; ++w) sum += s_fold[threadIdx.x][w];
 		(&o.status->clipped_faces)[threadIdx.x] = sum;
 		if (threadIdx.x == 3) {
 			if (o.bins_enabled == BINS_NONE && sum != 0) o.status->overflow = OVF_NEED_BINS;
