@@ -542,6 +542,15 @@ def main():
             "composite_parity": composite_parity,
             "clocks": clk,
         }
+        # the same figure for every stage (the dominant one changes from round to round: setup and shading are within 10 % of each other)
+        try:
+            tj = json.load(open(tp)).get(args.workload, {})
+        except Exception:
+            tj = {}
+        line["roofline_kernels"] = {k: {"algorithmic_bytes": per_stage.get(k, 0), "kernel_ms": kavg[k],
+                                        "achieved": (per_stage.get(k, 0) / (kavg[k] * 1e-3) / 1e9) if kavg[k] > 0 else 0.0,
+                                        "frac": (per_stage.get(k, 0) / (kavg[k] * 1e-3) / 1e9 / peak) if kavg[k] > 0 else 0.0,
+                                        "traffic": tj.get(k)} for k in kavg if per_stage.get(k, 0)}
         # per-kernel binding bound = max(T_hbm, T_fp32_issue): instruction counts are ncu's for this workload (profiles/traffic.json)
         counters = {}
         try:
