@@ -407,8 +407,8 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 	{
 		const unsigned grid = m.n_faces ? setup_grid(m.n_faces, so.n_chunks, so.swz_rows) : 0u;
 		if (grid) {
-			if (peel) k_setup_raster<true><<<grid, SETUP_THREADS, 0, g>>>(mv, m.sv[si], u.mvp, ctx->fp, so);
-			else k_setup_raster<false><<<grid, SETUP_THREADS, 0, g>>>(mv, m.sv[si], u.mvp, ctx->fp, so);
+			if (peel) k_setup_raster<true><<<grid, SETUP_THREADS, 0, g>>>(mv, m.sv[si], ctx->fp, so);
+			else k_setup_raster<false><<<grid, SETUP_THREADS, 0, g>>>(mv, m.sv[si], ctx->fp, so);
 			++launches;
 		}
 		// the faces that need the clipper + (its last CTA) the fold of the draw's counters into the status the host reads

@@ -59,9 +59,10 @@ struct DrawStatus {
 	unsigned overflow;                                                                // OVF_* bits
 	unsigned pad;
 	// per-warp partial counters are spread over STAT_STRIPES slots (no single hot address); the last CTA of k_setup_clipped folds them
-	unsigned stripes[4][512];
+	unsigned stripes[512][4];  // [stripe][STRIPE_*]: triangles and small triangles adjacent (one 64-bit reduction adds both)
 };
 constexpr int STAT_STRIPES = 512;
+enum { STRIPE_TRIS = 0, STRIPE_SMALL = 1, STRIPE_BINNED = 2, STRIPE_SPARE = 3 };
 
 struct FrameParams {
 	int W, H;
@@ -287,7 +288,8 @@ __device__ __forceinline__ bool raster_small(const FrameParams& fp, const SetupO
 		for (int py = s.Y0; py < s.Y1; ++py) {
 			const float pyc = small_int_to_f32(py) + 0.5f;
 			float r0 = p0 + s.b0 * pyc + s.c0, r1 = p1 + s.b1 * pyc + s.c1, r2 = p2 + s.b2 * pyc + s.c2;
-			if (hi) { r0 = r0 + s.a0 * 8.0f; r1 = r1 + s.a1 * 8.0f; r2 = r2 + s.a2 * 8.0f; }
+			// a * 8 is exact (a power of two), so the fused form rounds once, exactly where r + a*8 does: same bits, one instruction
+			if (hi) { r0 = __fmaf_rn(s.a0, 8.0f, r0); r1 = __fmaf_rn(s.a1, 8.0f, r1); r2 = __fmaf_rn(s.a2, 8.0f, r2); }
 #if AXR_SETUP_LOOP == 2
 			// four pixels at a time, branch-free: twelve independent chains instead of one pixel's dependent one (the loop is bound by
 			// the latency of its own chain, not by issue slots); the rare covered pixel recomputes its three values in hit4()
@@ -325,7 +327,7 @@ __device__ __forceinline__ bool raster_small(const FrameParams& fp, const SetupO
 // DEFER_TOUCH: the caller flags the tiles later (warp-aggregated); the return value is the tile rect of the pixel box packed as
 // tx0 | ty0<<8 | tx1<<16 | ty1<<24 in units of GPU tiles (frames up to 8160 px), or NO_TOUCH when there is nothing to flag.
 constexpr unsigned NO_TOUCH = 0xFFFFFFFFu;
-template <bool PEEL, bool DEFER_TOUCH>
+template <bool PEEL, bool DEFER_TOUCH, bool IN_FRAME = false>
 __device__ __forceinline__ unsigned emit_triangle(const FrameParams& fp, const SetupOut& o, float x0, float y0, float x1, float y1,
                                                   float x2, float y2, float z0, float z1, float z2, unsigned ordinal, EmitCounters& cnt) {
 	cnt.tris++;
@@ -333,7 +335,7 @@ __device__ __forceinline__ unsigned emit_triangle(const FrameParams& fp, const S
 	return NO_TOUCH;
 #endif
 	Setup s;
-	if (!setup_triangle(x0, y0, x1, y1, x2, y2, z0, z1, z2, fp.W, fp.y_lo, fp.y_hi, s)) return NO_TOUCH;
+	if (!setup_triangle<IN_FRAME>(x0, y0, x1, y1, x2, y2, z0, z1, z2, fp.W, fp.y_lo, fp.y_hi, s)) return NO_TOUCH;
 	const int bw = s.X1 - s.X0, bh = s.Y1 - s.Y0;
 	if (bw <= o.small_dim && bh <= o.small_dim && bw * bh <= o.small_area) {
 		cnt.small++;
@@ -420,11 +422,7 @@ __device__ __forceinline__ void publish_status(const DrawStatus* d, DrawStatus* 
 	reinterpret_cast<volatile unsigned long long*>(h)[word] = reinterpret_cast<const volatile unsigned long long*>(d)[word];
 }
 
-#ifndef AXR_SETUP_ROUNDS
-#define AXR_SETUP_ROUNDS 1  // faces per thread
-#endif
-constexpr int SETUP_ROUNDS = AXR_SETUP_ROUNDS;
-constexpr int SETUP_CHUNK = SETUP_THREADS * SETUP_ROUNDS;  // faces per CTA
+constexpr int SETUP_CHUNK = SETUP_THREADS;  // faces per CTA, one per thread
 #ifndef AXR_SETUP_SWZ_K
 #define AXR_SETUP_SWZ_K 16
 #endif
@@ -442,27 +440,13 @@ inline unsigned setup_grid(unsigned long long n_faces, unsigned& n_chunks, unsig
 	return swz_rows * SETUP_SWZ_K * SETUP_SWZ_GROUP;
 }
 
-__device__ __forceinline__ void prefetch_l1(const void* p) {
-#ifdef __CUDA_ARCH__
-	asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#else
-	(void)p;
-#endif
-}
-
-// A CTA owns SETUP_CHUNK consecutive faces. With SETUP_ROUNDS > 1 it first brings the chunk's indices into shared memory with
-// 16-byte loads (all of them in flight at once), prefetches the screen records they name into L1, and then works through the faces
-// in rounds of one face per thread: the kernel's dependent index -> record latency is paid once per chunk instead of once per face
-// (with one face per thread the load phase is bound by latency x resident warps: loads + cull alone are 70 us of C3's setup kernel).
-#ifndef AXR_CLIP_INLINE
-#define AXR_CLIP_INLINE 0  // 1: a face that needs the clipper is clipped by its own thread inside k_setup_raster (out-of-line call)
-#endif
+// One face per thread. (Measured and rejected: two or four faces per thread with the later faces' indices staged in shared memory
+// and their screen records prefetched into L1 — the load phase alone gets faster, 70 -> 58 us on C3, the kernel does not: 166-194
+// against 161 us; the clipper called from here instead of from its own kernel: 178 us.)
 template <bool PEEL>
 __global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(const __grid_constant__ MeshView mesh, const float4* __restrict__ sv,
-                                                                const __grid_constant__ m4 mvp, const __grid_constant__ FrameParams fp,
-                                                                const __grid_constant__ SetupOut o) {
+                                                                const __grid_constant__ FrameParams fp, const __grid_constant__ SetupOut o) {
 	const unsigned lane = threadIdx.x & 31u;
-	const unsigned nf = (unsigned)mesh.n_faces;  // faces < 2^29 (axr_upload_mesh): 32-bit index arithmetic throughout
 	// CTA -> chunk: the hardware hands out CTAs in index order, so the ~1800 resident ones would all sit in one stretch of the index
 	// buffer, and meshes are laid out coherently: whole stretches are back-facing (their warps only wait for loads) or front-facing
 	// (their warps only compute), the two phases alternate GPU-wide and never overlap. Groups of SETUP_SWZ_GROUP consecutive chunks are
@@ -473,105 +457,56 @@ __global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(
 		chunk = ((g % SETUP_SWZ_K) * o.swz_rows + g / SETUP_SWZ_K) * SETUP_SWZ_GROUP + j;
 		if (chunk >= o.n_chunks) return;
 	}
-	const unsigned base = chunk * SETUP_CHUNK;
-	EmitCounters cnt = {0, 0, 0};
-	int tx0 = 255, ty0 = 255, tx1 = 0, ty1 = 0;  // union of the tile rects this thread's direct-path triangles wrote keys into
-	bool has = false;
-	__shared__ __align__(16) unsigned s_idx[SETUP_ROUNDS > 1 ? SETUP_CHUNK * 3 : 4];
-	if (SETUP_ROUNDS > 1) {
-		const unsigned n_here = min(nf - base, (unsigned)SETUP_CHUNK);  // faces of this chunk
-		const unsigned* src = mesh.idx + 3u * base;                       // 16-byte aligned: SETUP_CHUNK * 12 is a multiple of 16
-		if (n_here == SETUP_CHUNK) {
-#pragma unroll
-			for (int k = 0; k < (SETUP_CHUNK * 3 / 4 + SETUP_THREADS - 1) / SETUP_THREADS; ++k) {
-				const unsigned q = threadIdx.x + k * SETUP_THREADS;
-				if (q < SETUP_CHUNK * 3 / 4) reinterpret_cast<uint4*>(s_idx)[q] = __ldg(reinterpret_cast<const uint4*>(src) + q);
-			}
+	const unsigned f = chunk * SETUP_CHUNK + threadIdx.x;  // faces < 2^29 (axr_upload_mesh): 32-bit index arithmetic throughout
+	EmitCounters cnt = {0, 0, 0};  // each 0 or 1 here: a face that is not clipped is one triangle
+	unsigned touched = NO_TOUCH;   // tile rect the direct path wrote keys into (packed, see emit_triangle)
+	bool clip = false;
+	if (f < (unsigned)mesh.n_faces && f >= mesh.first_face) {
+		const unsigned* ip = mesh.idx + 3u * f;
+		const unsigned i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
+		const float4 s0 = __ldg(sv + i0), s1 = __ldg(sv + i1), s2 = __ldg(sv + i2);
+		const unsigned k0 = __float_as_uint(s0.w), k1 = __float_as_uint(s1.w), k2 = __float_as_uint(s2.w);
+		if (((k0 | k1 | k2) & 0x3fu) == 0) {
+			// every vertex inside every plane: clipTriangle returns the triangle unchanged (reference src/pipeline.cpp:322-325)
+			if (!is_backface(s0.x, s0.y, s1.x, s1.y, s2.x, s2.y))
+				touched = emit_triangle<PEEL, true, true>(fp, o, s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, f * 8u, cnt);
+		} else if ((k0 & k1 & k2) >> 8) {
+			// all three vertices safely outside one plane: clipTriangle returns nothing (see clip_code_safe_out)
 		} else {
-			for (unsigned w = threadIdx.x; w < n_here * 3u; w += SETUP_THREADS) s_idx[w] = __ldg(src + w);
-		}
-		__syncthreads();
-#pragma unroll
-		for (int r = 0; r < SETUP_ROUNDS; ++r) {
-			const unsigned l = r * SETUP_THREADS + threadIdx.x;
-			if (l < n_here) { prefetch_l1(sv + s_idx[3u * l]); prefetch_l1(sv + s_idx[3u * l + 1]); prefetch_l1(sv + s_idx[3u * l + 2]); }
+			clip = true;  // needs the clipper: k_setup_clipped, the next kernel on the stream
 		}
 	}
-#pragma unroll 1
-	for (int r = 0; r < SETUP_ROUNDS; ++r) {
-		const unsigned l = r * SETUP_THREADS + threadIdx.x;
-		const unsigned f = base + l;
-		bool clip = false;
-		if (f < nf && f >= mesh.first_face) {
-			unsigned i0, i1, i2;
-			if (SETUP_ROUNDS > 1) {
-				i0 = s_idx[3u * l]; i1 = s_idx[3u * l + 1]; i2 = s_idx[3u * l + 2];
-			} else {
-				const unsigned* ip = mesh.idx + 3u * f;
-				i0 = __ldg(ip); i1 = __ldg(ip + 1); i2 = __ldg(ip + 2);
-			}
-			const float4 s0 = __ldg(sv + i0), s1 = __ldg(sv + i1), s2 = __ldg(sv + i2);
-			const unsigned k0 = __float_as_uint(s0.w), k1 = __float_as_uint(s1.w), k2 = __float_as_uint(s2.w);
-			if (((k0 | k1 | k2) & 0x3fu) == 0) {
-				// every vertex inside every plane: clipTriangle returns the triangle unchanged (reference src/pipeline.cpp:322-325)
-				if (!is_backface(s0.x, s0.y, s1.x, s1.y, s2.x, s2.y)) {
-					const unsigned touched = emit_triangle<PEEL, true>(fp, o, s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, f * 8u, cnt);
-					if (touched != NO_TOUCH) {
-						has = true;
-						tx0 = min(tx0, (int)(touched & 255u)); ty0 = min(ty0, (int)((touched >> 8) & 255u));
-						tx1 = max(tx1, (int)((touched >> 16) & 255u)); ty1 = max(ty1, (int)(touched >> 24));
-					}
-				}
-			} else if ((k0 & k1 & k2) >> 8) {
-				// all three vertices safely outside one plane: clipTriangle returns nothing (see clip_code_safe_out)
-			} else {
-				clip = true;  // needs the clipper: k_setup_clipped, the next kernel on the stream
-#if AXR_CLIP_INLINE
-				const unsigned c = setup_clipped_face<PEEL>(fp, o, mvp, __ldg(mesh.pos + i0), __ldg(mesh.pos + i1), __ldg(mesh.pos + i2), f);
-				cnt.tris += c & 255u; cnt.small += (c >> 8) & 255u; cnt.binned += c >> 16;
-#endif
-			}
-		}
-		__syncwarp();
-		// Faces for the clipper: warp-aggregated append (any order: keys carry the face ordinal, bins are order-free)
-		const unsigned cm = __ballot_sync(0xffffffffu, clip);
-#if AXR_CLIP_INLINE
-		if (cm && lane == 0) atomicAdd(&o.status->stripes[0][(chunk * (SETUP_THREADS / 32) + (threadIdx.x >> 5)) % STAT_STRIPES], (unsigned)__popc(cm));
-		if (false) {
-#else
-		if (cm) {
-#endif
-			unsigned at = 0;
-			if (lane == 0) at = atomicAdd(o.n_clip_faces, (unsigned)__popc(cm));
-			at = __shfl_sync(0xffffffffu, at, 0);
-			if (clip) o.clip_faces[at + __popc(cm & ((1u << lane) - 1u))] = f;
+	__syncwarp();
+	// Faces for the clipper: warp-aggregated append (any order: keys carry the face ordinal, bins are order-free)
+	const unsigned cm = __ballot_sync(0xffffffffu, clip);
+	if (cm) {
+		unsigned at = 0;
+		if (lane == 0) at = atomicAdd(o.n_clip_faces, (unsigned)__popc(cm));
+		at = __shfl_sync(0xffffffffu, at, 0);
+		if (clip) o.clip_faces[at + __popc(cm & ((1u << lane) - 1u))] = f;
+	}
+	// Tile flags of the direct path: the 32 consecutive faces of a warp mostly land in the same tile (or the same pair), and then one
+	// lane flags it for all of them; otherwise every lane flags its own (test before set, see touch_tile).
+	const unsigned hm = __ballot_sync(0xffffffffu, touched != NO_TOUCH);
+	if (hm) {
+		const unsigned first = __shfl_sync(0xffffffffu, touched, __ffs(hm) - 1);
+		const bool uniform = __ballot_sync(0xffffffffu, touched == NO_TOUCH || touched == first) == 0xffffffffu;
+		if (uniform ? lane == 0 : touched != NO_TOUCH) {
+			const unsigned r = uniform ? first : touched;
+			const int tx1 = (int)((r >> 16) & 255u), ty1 = (int)(r >> 24);
+			for (int ty = (int)((r >> 8) & 255u); ty <= ty1; ++ty)
+				for (int tx = (int)(r & 255u); tx <= tx1; ++tx) touch_tile(fp, o, tx, ty);
 		}
 	}
-	// Tile flags of the direct path, warp-aggregated: the consecutive faces of a warp land in the same one or two tiles, so lane 0
-	// flags the union of their tile rects (a superset costs an empty staging pass in the tile kernel, nothing else); scattered faces
-	// (union of more than 4 tiles) flag their own.
-	if (__ballot_sync(0xffffffffu, has)) {
-		const int ux0 = __reduce_min_sync(0xffffffffu, tx0), uy0 = __reduce_min_sync(0xffffffffu, ty0);
-		const int ux1 = __reduce_max_sync(0xffffffffu, tx1), uy1 = __reduce_max_sync(0xffffffffu, ty1);
-		if ((ux1 - ux0 + 1) * (uy1 - uy0 + 1) <= 4) {
-			if (lane == 0)
-				for (int ty = uy0; ty <= uy1; ++ty)
-					for (int tx = ux0; tx <= ux1; ++tx) touch_tile(fp, o, tx, ty);
-		} else if (has) {
-			for (int ty = ty0; ty <= ty1; ++ty)
-				for (int tx = tx0; tx <= tx1; ++tx) touch_tile(fp, o, tx, ty);
-		}
-	}
-	// Counters: warp sums, then one fire-and-forget reduction per non-zero counter per warp into one of STAT_STRIPES stripes (no hot
-	// address). Warps whose faces were all culled have nothing to add.
+	// Counters: one warp sum of the three packed counters (each at most 32), then fire-and-forget reductions into one of STAT_STRIPES
+	// stripes (no hot address): triangles and small triangles sit next to each other and go up with one 64-bit reduction. Warps whose
+	// faces were all culled have nothing to add.
 	if (__ballot_sync(0xffffffffu, cnt.tris != 0u)) {
-		const unsigned w1 = __reduce_add_sync(0xffffffffu, cnt.tris), w2 = __reduce_add_sync(0xffffffffu, cnt.small);
-		const unsigned w3 = __reduce_add_sync(0xffffffffu, cnt.binned);
+		const unsigned w = __reduce_add_sync(0xffffffffu, cnt.tris | (cnt.small << 8) | (cnt.binned << 16));
 		if (lane == 0) {
-			const unsigned stripe = (chunk * (SETUP_THREADS / 32) + (threadIdx.x >> 5)) % STAT_STRIPES;
-			atomicAdd(&o.status->stripes[1][stripe], w1);
-			if (w2) atomicAdd(&o.status->stripes[2][stripe], w2);
-			if (w3) atomicAdd(&o.status->stripes[3][stripe], w3);
+			unsigned* st = o.status->stripes[(chunk * (SETUP_THREADS / 32) + (threadIdx.x >> 5)) % STAT_STRIPES];
+			atomicAdd(reinterpret_cast<unsigned long long*>(st + STRIPE_TRIS), (unsigned long long)(w & 255u) | ((unsigned long long)((w >> 8) & 255u) << 32));
+			if (w >> 16) atomicAdd(st + STRIPE_BINNED, w >> 16);
 		}
 	}
 }
@@ -595,10 +530,10 @@ __global__ void __launch_bounds__(CLIPSETUP_THREADS) k_setup_clipped(const __gri
 		tris += c & 255u; small += (c >> 8) & 255u; binned += c >> 16;
 	}
 	if (tris) {
-		const unsigned stripe = (blockIdx.x * CLIPSETUP_THREADS + threadIdx.x) % STAT_STRIPES;
-		atomicAdd(&o.status->stripes[1][stripe], tris);
-		if (small) atomicAdd(&o.status->stripes[2][stripe], small);
-		if (binned) atomicAdd(&o.status->stripes[3][stripe], binned);
+		unsigned* st = o.status->stripes[(blockIdx.x * CLIPSETUP_THREADS + threadIdx.x) % STAT_STRIPES];
+		atomicAdd(st + STRIPE_TRIS, tris);
+		if (small) atomicAdd(st + STRIPE_SMALL, small);
+		if (binned) atomicAdd(st + STRIPE_BINNED, binned);
 	}
 	__threadfence();
 	__syncthreads();
@@ -608,16 +543,20 @@ __global__ void __launch_bounds__(CLIPSETUP_THREADS) k_setup_clipped(const __gri
 	__threadfence();
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-	for (int c = 0; c < 4; ++c) {
+	for (int c = 0; c < 3; ++c) {
 		unsigned long long acc = 0;
-		for (int i = threadIdx.x; i < STAT_STRIPES; i += CLIPSETUP_THREADS) acc += __ldcg(&o.status->stripes[c][i]);
+		for (int i = threadIdx.x; i < STAT_STRIPES; i += CLIPSETUP_THREADS) acc += __ldcg(&o.status->stripes[i][c]);
 		for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
 		if (lane == 0) s_fold[c][warp] = acc;
 	}
 	__syncthreads();
 	if (threadIdx.x < 4) {
-		unsigned long long sum = threadIdx.x ? 0ull : (unsigned long long)n;  // clipped_faces: the list (+ the ones clipped in k_setup_raster)
-		for (int w = 0; w < CLIPSETUP_THREADS / 32; ++w) sum += s_fold[threadIdx.x][w];
+		// status words: clipped_faces (= the list), triangles, small_triangles, binned_triangles
+		unsigned long long sum = n;
+		if (threadIdx.x) {
+			sum = 0;
+			for (int w = 0; w < CLIPSETUP_THREADS / 32; ++w) sum += s_fold[threadIdx.x - 1][w];
+		}
 		(&o.status->clipped_faces)[threadIdx.x] = sum;
 		if (threadIdx.x == 3) {
 			if (o.bins_enabled == BINS_NONE && sum != 0) o.status->overflow = OVF_NEED_BINS;

@@ -219,16 +219,20 @@ __device__ __forceinline__ bool setup_edges(float x0, float y0, float x1, float 
 }
 
 // Returns false when the reference would draw nothing for this triangle (empty box or the degenerate-area return).
+// IN_FRAME: the three vertices passed all six clip planes (clip code 0), so their screen coordinates are finite and within a rounding
+// error of [0, W] x [0, H]: the float -> int conversions cannot leave the int range and need no cvttss2si emulation.
+template <bool IN_FRAME = false>
 __device__ __forceinline__ bool setup_triangle(float x0, float y0, float x1, float y1, float x2, float y2, float z0,
                                                float z1, float z2, int W, int y_lo, int y_hi, Setup& s) {
 	float minx = min3f(x0, x1, x2), miny = min3f(y0, y1, y2);
 	float maxx = max3f(x0, x1, x2), maxy = max3f(y0, y1, y2);
 	// Union over the reference's 16x16 tiles of [max(tile.startX, floor(minX)), min(tile.endX, ceil(maxX))) (:436-440)
-	s.fminx = cvtt(floorf(minx));
+	auto to_int = [](float v) { return IN_FRAME ? (int)v : cvtt(v); };
+	s.fminx = to_int(floorf(minx));
 	s.X0 = max(0, s.fminx);
-	s.X1 = min(W, cvtt(ceilf(maxx)));
-	s.Y0 = max(y_lo, cvtt(floorf(miny)));
-	s.Y1 = min(y_hi, cvtt(ceilf(maxy)));
+	s.X1 = min(W, to_int(ceilf(maxx)));
+	s.Y0 = max(y_lo, to_int(floorf(miny)));
+	s.Y1 = min(y_hi, to_int(ceilf(maxy)));
 	if (s.X0 >= s.X1 || s.Y0 >= s.Y1) return false;
 	return setup_edges(x0, y0, x1, y1, x2, y2, z0, z1, z2, s);
 }
