@@ -124,6 +124,9 @@ struct axr_ctx {
 	unsigned draw_counter = 0;
 	cudaStream_t geom_stream = nullptr;
 	unsigned* dirty_map = nullptr;  // axr_set_dirty_map
+	bool fill = false;              // axr_set_output_fill
+	uint32_t fill_color = 0;
+	float fill_depth = 0.f;
 	bool color_fast = true;  // axr_set_color_math: fused colour arithmetic in the shading stage (default) or the reference's individually rounded one
 	bool overlap = false;  // axr_set_overlap: geometry stages on geom_stream (else everything on the main stream)
 	PendingDraw pending;
@@ -284,8 +287,17 @@ cudaEvent_t prof_mark(axr_ctx* ctx, cudaStream_t s) {
 using TileLaunch = int (*)(axr_ctx*, const MeshView&, const Uniforms&, const FrameParams&, const TileIn&, int which, unsigned gx, unsigned gy);
 template <typename Shader, int SMP, bool FAST>
 int launch_builtin(axr_ctx* ctx, const MeshView& mv, const Uniforms& u, const FrameParams& fp, const TileIn& in, int which, unsigned gx, unsigned gy) {
-	if (which == 0) k_tile_shade<Shader, SMP, FAST><<<dim3(gx, gy), TILE_THREADS, 0, ctx->stream>>>(mv, u, fp, in);
-	else k_shade_clipped<Shader, SMP><<<CLIP_SHADE_CTAS, CLIP_SHADE_THREADS, 0, ctx->stream>>>(mv, u, fp, in);
+	if (which == 0) {
+		if constexpr (!Shader::DISCARDS) {  // axr_set_output_fill is refused for shaders that discard
+			if (in.fill) {
+				k_tile_shade<Shader, SMP, FAST, true><<<dim3(gx, gy), TILE_THREADS, 0, ctx->stream>>>(mv, u, fp, in);
+				return AXR_OK;
+			}
+		}
+		k_tile_shade<Shader, SMP, FAST, false><<<dim3(gx, gy), TILE_THREADS, 0, ctx->stream>>>(mv, u, fp, in);
+	} else {
+		k_shade_clipped<Shader, SMP><<<CLIP_SHADE_CTAS, CLIP_SHADE_THREADS, 0, ctx->stream>>>(mv, u, fp, in);
+	}
 	return AXR_OK;
 }
 int launch_plugin(axr_ctx* ctx, const MeshView& mv, const Uniforms& u, const FrameParams& fp, const TileIn& in, int which, unsigned gx, unsigned gy) {
@@ -331,6 +343,8 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 	DeviceMesh& m = ctx->meshes[mh];
 	axr_ctx::DrawSlot& sl = ctx->slot[si];
 	if (peel != shader_discards(ctx)) return fail(ctx, AXR_ERR_INVALID, "internal: peel flag does not match the shader");
+	if (ctx->fill && (peel || ctx->host_chunks > 0))
+		return fail(ctx, AXR_ERR_UNSUPPORTED, "axr_set_output_fill: not for shaders that discard (several passes per draw) nor for host framebuffers");
 	int rc = sync_materials(ctx, m);
 	if (rc) return rc;
 	// shader / material validation (the reference dereferences null textures, include/shaders/shaders.hpp:178,210)
@@ -446,6 +460,7 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 	in.clip_tiles = sl.clip_tiles; in.n_clip_tiles = sl.n_clip_tiles;
 	in.dirty = ctx->dirty_map;
 	in.bin_mode = bin_mode;
+	in.fill = ctx->fill ? 1 : 0; in.fill_color = ctx->fill_color; in.fill_depth = ctx->fill_depth;
 	TileLaunch fn = nullptr;
 	switch (ctx->shader_kind) {
 	case AXR_SHADER_FLAT: fn = builtin_launcher<FlatShader>(ctx, u.sampler); break;
@@ -1266,6 +1281,25 @@ int axr_clear_dirty_tiles(axr_ctx* ctx, void* bgra_dev, void* depth_dev, void* d
 	return AXR_OK;
 }
 
+int axr_set_output_fill(axr_ctx* ctx, int enabled, uint32_t packed_argb, float depth) {
+	if (!ctx) return AXR_ERR_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	if (int rc = check_pending(ctx)) return rc;
+	ctx->fill = enabled != 0; ctx->fill_color = packed_argb; ctx->fill_depth = depth;
+	return AXR_OK;
+}
+
+int axr_clear_stale_tiles(axr_ctx* ctx, void* bgra_dev, void* depth_dev, void* dirty_prev_dev, void* dirty_now_dev, int count, uint32_t packed_argb, float depth,
+                          void* stream) {
+	if (!ctx) return AXR_ERR_INVALID;
+	if (!bgra_dev || !depth_dev || !dirty_prev_dev || !dirty_now_dev || count <= 0 || count > 65535) return fail(ctx, AXR_ERR_INVALID, "axr_clear_stale_tiles: bad argument");
+	CU(cudaSetDevice(ctx->device));
+	k_clear_stale_tiles<<<dim3(ctx->fp.ntx, ctx->fp.nty, count), 256, 0, stream ? (cudaStream_t)stream : ctx->stream>>>(
+		(unsigned*)bgra_dev, (float*)depth_dev, (unsigned*)dirty_prev_dev, (const unsigned*)dirty_now_dev, ctx->fp.W, ctx->fp.H, ctx->fp.ntx, GT, packed_argb, depth);
+	CU(cudaGetLastError());
+	return AXR_OK;
+}
+
 int axr_set_overlap(axr_ctx* ctx, int enabled) {
 	if (!ctx) return AXR_ERR_INVALID;
 	CU(cudaSetDevice(ctx->device));
@@ -1300,6 +1334,8 @@ int axr_alloc_shared(axr_ctx* ctx, size_t bytes, void** dev_ptr_out, void* handl
 	CU(cudaSetDevice(ctx->device));
 	void* p = nullptr;
 	CU(cudaMalloc(&p, bytes));
+	CU(cudaMemsetAsync(p, 0, bytes, ctx->stream));  // dirty maps start out clean
+	CU(cudaStreamSynchronize(ctx->stream));
 	cudaError_t e = cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64_out, p);
 	if (e != cudaSuccess) { cudaFree(p); return fail(ctx, AXR_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
 	ctx->shared_allocs.push_back(p);

@@ -130,6 +130,27 @@ __global__ void __launch_bounds__(256) k_clear_dirty_tiles(unsigned* color, floa
 		}
 	}
 }
+// Companion of axr_set_output_fill: a tile that was stored into the previous time the target was used (`prev`) and not this time (`now`)
+// still holds the old frame and is cleared here; `prev` is handed back all zero (it is the next frame's `now`). Same layout as above.
+__global__ void __launch_bounds__(256) k_clear_stale_tiles(unsigned* color, float* depth, unsigned* prev, const unsigned* now, int W, int H, int ntx,
+                                                           int tile_px, unsigned packed, float z) {
+	const size_t npx = (size_t)W * H;
+	const int tile = blockIdx.y * ntx + blockIdx.x;
+	const size_t map = (size_t)blockIdx.z * ((size_t)gridDim.x * gridDim.y) + tile;
+	const unsigned was = prev[map], is = now[map];
+	if (was == 0u) return;
+	__syncthreads();
+	if (threadIdx.x == 0) prev[map] = 0u;
+	if (is) return;
+	const int x0 = blockIdx.x * tile_px, y0 = blockIdx.y * tile_px;
+	for (int p = threadIdx.x; p < tile_px * tile_px; p += blockDim.x) {
+		const int px = x0 + p % tile_px, py = y0 + p / tile_px;
+		if (px < W && py < H) {
+			const size_t gi = (size_t)blockIdx.z * npx + (size_t)py * W + px;
+			color[gi] = packed; depth[gi] = z;
+		}
+	}
+}
 // AoS AR::Vertex (56 B) -> position float4 + attributes (done once at mesh upload)
 __global__ void k_split_vertices(const float* __restrict__ raw, unsigned long long n, unsigned long long n_plane, float4* __restrict__ pos,
                                  float4* __restrict__ attr) {
@@ -667,6 +688,12 @@ struct TileIn {
 	unsigned* dirty;                // optional (axr_set_dirty_map): per GPU tile, set to 1 when this draw may store into the tile
 	unsigned* n_clip_tiles;
 	int bin_mode;                   // BINS_* of this draw
+	// axr_set_output_fill: the draw overwrites EVERY pixel of the tiles it touches — the shaded colour where a triangle is visible,
+	// (fill_color, fill_depth) elsewhere — and its merge test sees fill_depth: for a target that holds exactly one draw on top of a
+	// clear (a multi-GPU composite slot), so that the target's owner never clears the tiles the next frame touches again
+	int fill;
+	unsigned fill_color;
+	float fill_depth;
 };
 
 // (uint8)(int)(clamp(c, 0, 1) * 255): reference src/tiled_pipeline.cpp:579-582. cvttss2si turns NaN into 0x80000000, whose low byte is 0.
@@ -773,7 +800,7 @@ __device__ bool shade_pixel_clipped(const MeshView& mesh, const Uniforms& u, con
 	coverage(s, px, py, c0, c1, c2);
 	const float z = interp_z(s, c0, c1, c2, w[0], w[1], w[2]);
 	const size_t gi = (size_t)py * fp.W + px;
-	if (!(z < (in.read_depth ? in.depth_read[gi] : INFINITY))) return false;
+	if (!(z < (in.fill ? in.fill_depth : (in.read_depth ? in.depth_read[gi] : INFINITY)))) return false;
 	VIn v[3];
 	for (int k = 0; k < 3; ++k) { v[k].pos = c[k].pos; v[k].n = c[k].n; v[k].t = c[k].t; v[k].b = c[k].b; v[k].u = c[k].uv[0]; v[k].v = c[k].uv[1]; }
 	return run_shader<Shader, SMP, false>(mesh, u, in, ordinal >> 3, gi, z, w, v);
@@ -781,7 +808,7 @@ __device__ bool shade_pixel_clipped(const MeshView& mesh, const Uniforms& u, con
 
 // One visible pixel: all gathers that depend only on the vertex indices are issued together (screen records, positions,
 // attributes, framebuffer depth), then edge setup -> barycentrics -> depth test -> shader.
-enum { PIX_DONE = 0, PIX_DISCARDED = 1, PIX_CLIPPED = 2 };
+enum { PIX_DONE = 0, PIX_DISCARDED = 1, PIX_CLIPPED = 2, PIX_LOST = 3 };  // stored / discarded by the shader / left to k_shade_clipped / lost the merge test
 template <typename Shader, int SMP, bool FAST>
 __device__ __forceinline__ int shade_pixel(const MeshView& mesh, const Uniforms& u, const FrameParams& fp, const TileIn& in, unsigned ordinal,
                                            unsigned i0, unsigned i1, unsigned i2, int px, int py, float fbz) {
@@ -812,7 +839,7 @@ __device__ __forceinline__ int shade_pixel(const MeshView& mesh, const Uniforms&
 	coverage(s, px, py, c0, c1, c2);
 	const float z = interp_z(s, c0, c1, c2, w[0], w[1], w[2]);
 	// mergeTileResults: strict tileZ < fbZ (reference src/tiled_pipeline.cpp:1148-1156)
-	if (!(z < fbz)) return PIX_DONE;
+	if (!(z < fbz)) return PIX_LOST;
 	return run_shader<Shader, SMP, FAST>(mesh, u, in, ordinal >> 3, gi, z, w, v) ? PIX_DISCARDED : PIX_DONE;
 }
 
@@ -820,7 +847,9 @@ __device__ __forceinline__ int shade_pixel(const MeshView& mesh, const Uniforms&
 // 64 KB shared-memory carve-out the keys alone already need (the gathers of the shading phase live on the rest of the L1)
 constexpr int BIN_ROUND = 64, SCAN_CHUNK = 1024;
 static_assert(BIN_ROUND <= TILE_THREADS && SCAN_CHUNK % TILE_THREADS == 0 && SCAN_CHUNK <= 65536, "one candidate per thread; 16-bit chunk-relative ids");
-template <typename Shader, int SMP, bool FAST>
+// FILL: axr_set_output_fill (TileIn::fill) as a compile-time switch, so that the plain kernel does not carry it (as a run-time flag it
+// cost the C3 shading stage 6 us in registers and spills).
+template <typename Shader, int SMP, bool FAST, bool FILL = false>
 __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(const __grid_constant__ MeshView mesh, const __grid_constant__ Uniforms u, const __grid_constant__ FrameParams fp,
                                                                              const __grid_constant__ TileIn in) {
 	constexpr bool PEEL = Shader::DISCARDS;
@@ -983,12 +1012,18 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 		const int p = in.row_major ? blk * GT + (tid & 31) : ((blk >> 2) * 4 + ((tid & 31) >> 3)) * GT + (blk & 3) * 8 + (tid & 7);
 #endif
 		const unsigned long long k = s_keys[p];
-		if (k == KEY_EMPTY) continue;
-		const unsigned ord = (unsigned)(k & 0xFFFFFFFFull);
 		const int px = x0 + (p & (GT - 1)), py = y0 + (p / GT);
+		if (k == KEY_EMPTY) {
+			if (FILL && px < fp.W && py >= fp.y_lo && py < fp.y_hi) {
+				in.color[(size_t)py * fp.W + px] = in.fill_color;
+				in.depth[(size_t)py * fp.W + px] = in.fill_depth;
+			}
+			continue;
+		}
+		const unsigned ord = (unsigned)(k & 0xFFFFFFFFull);
 		// the framebuffer depth for the merge test does not depend on the triangle: issued first, so that a read that crosses PCIe
 		// (host framebuffer, axr_draw_mesh_host) or NVLink has the index -> vertex gathers to hide behind
-		const float fbz = in.read_depth ? in.depth_read[(size_t)py * fp.W + px] : INFINITY;
+		const float fbz = FILL ? in.fill_depth : (in.read_depth ? in.depth_read[(size_t)py * fp.W + px] : INFINITY);
 #if AXR_TILE_IDX_STASH
 		const unsigned i0 = s_idx[0][p], i1 = s_idx[1][p], i2 = s_idx[2][p];
 #elif AXR_IDX_PAD
@@ -999,6 +1034,10 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 		const unsigned i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2);
 #endif
 		const int res = shade_pixel<Shader, SMP, FAST>(mesh, u, fp, in, ord, i0, i1, i2, px, py, fbz);
+		if (FILL && res != PIX_DONE) {  // not drawn (yet: k_shade_clipped may still store it)
+			in.color[(size_t)py * fp.W + px] = in.fill_color;
+			in.depth[(size_t)py * fp.W + px] = in.fill_depth;
+		}
 		if (res == PIX_CLIPPED) {
 			// owned by a clipped face: the key goes back to the global buffer and the tile onto the list k_shade_clipped works through
 			in.vis[(size_t)py * fp.W + px] = k;
@@ -1066,7 +1105,7 @@ __global__ void __launch_bounds__(CLIP_SHADE_THREADS) k_shade_clipped(const __gr
 constexpr unsigned long long plugin_layout_hash() {
 	unsigned long long h = 0xA11CE5ull;
 	const unsigned long long parts[] = {sizeof(MeshView), sizeof(Uniforms), sizeof(FrameParams), sizeof(TileIn), sizeof(Material), (unsigned long long)TILE_THREADS,
-	                                    (unsigned long long)GT, (unsigned long long)CLIP_SHADE_THREADS, (unsigned long long)BIN_ROUND, 2ull /* revision */};
+	                                    (unsigned long long)GT, (unsigned long long)CLIP_SHADE_THREADS, (unsigned long long)BIN_ROUND, 4ull /* revision */};
 	for (unsigned long long p : parts) h = (h ^ p) * 0x100000001B3ull;
 	return h;
 }

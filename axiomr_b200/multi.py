@@ -14,9 +14,12 @@ from __future__ import annotations
 REF_TILE = 16  # reference include/tiled_pipeline.hpp:28
 
 
-def band_rows(height: int, world: int):
-    """Split ceil(H/16) reference tile rows into `world` contiguous bands, as evenly as possible
-    (8K: 270 tile rows -> 34,34,34,34,34,34,33,33). Returns [(y0, y1)] in pixels; empty bands are not produced."""
+def band_rows(height: int, world: int, granule: int = REF_TILE):
+    """Split ceil(H/granule) rows of `granule` pixels into `world` contiguous bands, as evenly as possible (granule 16, the
+    reference tile: 8K -> 270 tile rows -> 34,34,34,34,34,34,33,33). Any multiple of 16 gives the same pixels; the fused peer
+    composite uses 32 (the GPU tile) so that no tile — the unit its dirty flags track — belongs to two ranks.
+    Returns [(y0, y1)] in pixels; empty bands are not produced."""
+    REF_TILE = granule  # noqa: N806 (local alias: the arithmetic below is the same for either granule)
     rows = (height + REF_TILE - 1) // REF_TILE
     world = max(1, min(world, rows))
     base, extra = divmod(rows, world)
@@ -26,6 +29,11 @@ def band_rows(height: int, world: int):
         out.append((r * REF_TILE, min((r + n) * REF_TILE, height)))
         r += n
     return out
+
+
+def band_granule(transport: str | None) -> int:
+    """Band alignment in pixels: the reference tile (16) in general; the fused peer composite tracks 32-px GPU tiles."""
+    return 32 if (transport or "peer") == "peer" else REF_TILE
 
 
 def views_for_rank(rank: int, world: int, n_views: int):
@@ -95,28 +103,31 @@ class Compositor:
       targets (colour + depth + a dirty-tile map each); frame i uses set i % 2:
         views : one target per rank r > 0 (GPU 0 renders its own view into its own framebuffer);
         bands : one full-frame target every rank, GPU 0 included, renders its rows into.
-      A rank's tile kernel stores the covered pixels of the frame straight into the target (no depth read over NVLink: the target
-      is freshly cleared, axr_set_depth_read(0)) and flags the 32x32 tiles it touches in the target's dirty map. While frame i
-      renders, GPU 0 clears the tiles flagged in the OTHER set (axr_clear_dirty_tiles on a side stream: a fraction of the frame
-      instead of all of it), and one 4-byte NCCL all-reduce per frame on the render streams orders "all stores of frame i are
-      done" before "the set is cleared again". Only covered pixels cross NVLink.
+      A rank's tile kernel stores into the target directly (no depth read over NVLink: the target holds a clear plus this one draw)
+      and overwrites EVERY pixel of the 32x32 tiles it touches — shaded colour or the clear values (axr_set_output_fill) — in whole
+      128-byte rows, flagging those tiles in the target's dirty map. Nothing has to be cleared in front of a frame that way: GPU 0
+      only clears the tiles the target's previous use touched and this one did not (axr_clear_stale_tiles on a side stream; two maps
+      per target alternate; no tile at all while the cameras stand still), and one 4-byte NCCL all-reduce per frame on the render
+      streams orders "all stores of frame i are done" before the set's next use. Only the touched tiles cross NVLink.
+      (fill=False keeps the previous scheme: covered pixels only, GPU 0 re-clears the flagged tiles, axr_clear_dirty_tiles.)
     transport "nccl" — the baseline: grouped send/recv of whole regions after each frame (bands: in place; views:
       double-buffered, on a second stream, overlapping the next frame).
     """
 
-    def __init__(self, dev, rank: int, world: int, mode: str, band, stream, transport: str | None = None):
+    def __init__(self, dev, rank: int, world: int, mode: str, band, stream, transport: str | None = None, fill: bool = True):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.dev, self.rank, self.world, self.mode, self.stream = dev, rank, world, mode, stream
         self.transport = transport or "peer"
+        self.fill = bool(fill) and self.transport == "peer"
         self.launches_per_step = 0
         self.color, self.depth = framebuffer_tensors(dev)
         self.step = 0
         dv = self.color.device
         self.H, self.W = dev.height, dev.width
         if mode == "bands":
-            self.bands = band_rows(dev.height, world)
+            self.bands = band_rows(dev.height, world, band_granule(self.transport))
         if self.transport == "peer":
             self._setup_peer()
         elif mode == "views":
@@ -135,13 +146,13 @@ class Compositor:
     def n_targets(self) -> int:
         return self.world - 1 if self.mode == "views" else 1
 
-    def _offsets(self, b: int, t: int):
-        """Byte offsets of (colour, depth, dirty map) of target t of set b inside the shared allocation.
-        Per set: [colour planes][depth planes][dirty maps], each group contiguous (what axr_clear_dirty_tiles walks)."""
+    def _offsets(self, b: int, t: int, m: int = 0):
+        """Byte offsets of (colour, depth, dirty map m) of target t of set b inside the shared allocation.
+        Per set: [colour planes][depth planes][dirty maps 0][dirty maps 1], each group contiguous (what the clear kernels walk)."""
         npx, nt, n = self.H * self.W, self.n_tiles, self.n_targets
-        set_bytes = n * (npx * 8 + nt * 4)
+        set_bytes = n * (npx * 8 + 2 * nt * 4)
         base = b * set_bytes
-        return base + t * npx * 4, base + n * npx * 4 + t * npx * 4, base + n * npx * 8 + t * nt * 4
+        return base + t * npx * 4, base + n * npx * 4 + t * npx * 4, base + n * npx * 8 + m * n * nt * 4 + t * nt * 4
 
     def _target_index(self) -> int:
         return self.rank - 1 if self.mode == "views" else 0
@@ -150,7 +161,8 @@ class Compositor:
         torch, dist = self.torch, self.dist
         npx = self.H * self.W
         self.n_tiles = self.dev.dirty_map_entries()
-        total = 2 * self.n_targets * (npx * 8 + self.n_tiles * 4)
+        total = 2 * self.n_targets * (npx * 8 + 2 * self.n_tiles * 4)
+        self.uses = [0, 0]   # how often each set has been rendered into: picks which of its two dirty maps is "now"
         handles = [None]
         if self.rank == 0:
             self._shared_ptr, h = self.dev.alloc_shared(total)
@@ -165,7 +177,7 @@ class Compositor:
                 co, do, mo = self._offsets(b, 0)
                 c = torch.as_tensor(_DevArray(self._shared_ptr + co, (n, self.H, self.W), "<i4"), device=dv)
                 d = torch.as_tensor(_DevArray(self._shared_ptr + do, (n, self.H, self.W), "<f4"), device=dv)
-                m = torch.as_tensor(_DevArray(self._shared_ptr + mo, (n, self.n_tiles), "<i4"), device=dv)
+                m = torch.as_tensor(_DevArray(self._shared_ptr + mo, (2, n, self.n_tiles), "<i4"), device=dv)
                 c.fill_(-16777216)   # 0xFF000000
                 d.fill_(float("inf"))
                 m.zero_()
@@ -176,6 +188,8 @@ class Compositor:
             self._shared_ptr = self.dev.open_ipc(handles[0])
         if self.rank != 0 or self.mode == "bands":
             self.dev.set_depth_read(False)   # the target is freshly cleared and receives exactly this draw
+            if self.fill:
+                self.dev.set_output_fill(True)
         dist.barrier()
 
     # ------------------------------------------------------------------ per frame
@@ -197,18 +211,31 @@ class Compositor:
                 c, d = self.bufs[b]
                 self.dev.set_output(c.data_ptr(), d.data_ptr())
             return
+        now = self.uses[b] % 2 if self.fill else 0   # every rank counts the uses of a set alike
         if self.rank != 0 or self.mode == "bands":
-            co, do, mo = self._offsets(b, self._target_index())
+            co, do, mo = self._offsets(b, self._target_index(), now)
             self.dev.set_output(self._shared_ptr + co, self._shared_ptr + do)
             self.dev.set_dirty_map(self._shared_ptr + mo)
         if self.rank == 0:
-            # Clear the other set's dirty tiles for the next frame while this one renders, on a side stream, ordered after the
-            # previous frame's all-reduce.
+            # The other set (the previous frame's, complete since that frame's all-reduce) is put in order for its next use while this
+            # frame renders, on a side stream.
             ready = self.torch.cuda.Event()
             ready.record(self.stream)
-            nb = (b + 1) % 2
-            co, do, mo = self._offsets(nb, 0)
             self.side.wait_event(ready)
+            self._tidy((b + 1) % 2)
+        self.uses[b] += 1
+
+    def _tidy(self, nb: int):
+        """GPU 0, side stream: fill mode clears the tiles the set's last use no longer touched (idempotent), else all flagged tiles."""
+        if self.fill:
+            if self.uses[nb] > 0:
+                last = (self.uses[nb] - 1) % 2   # the map the set's last use flagged; the other one holds the use before it
+                co, do, m_now = self._offsets(nb, 0, last)
+                m_prev = self._offsets(nb, 0, 1 - last)[2]
+                self.dev.clear_stale_tiles(self._shared_ptr + co, self._shared_ptr + do, self._shared_ptr + m_prev, self._shared_ptr + m_now,
+                                           self.n_targets, stream=self.side.cuda_stream)
+        else:
+            co, do, mo = self._offsets(nb, 0)
             self.dev.clear_dirty_tiles(self._shared_ptr + co, self._shared_ptr + do, self._shared_ptr + mo, self.n_targets,
                                        stream=self.side.cuda_stream)
 
@@ -244,6 +271,11 @@ class Compositor:
             if self.mode == "views":
                 self.stream.wait_stream(self.comm)
         elif self.rank == 0:
+            if self.fill and self.step > 0:   # the last frame's set: tiles its previous use touched and this one did not
+                ready = self.torch.cuda.Event()
+                ready.record(self.stream)
+                self.side.wait_event(ready)
+                self._tidy(self.last_set())
             self.stream.wait_stream(self.side)
 
     def last_set(self) -> int:
@@ -263,3 +295,4 @@ class Compositor:
         if self.transport == "peer":
             self.dev.set_output(None, None)
             self.dev.set_dirty_map(None)
+            self.dev.set_output_fill(False)

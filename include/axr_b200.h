@@ -240,6 +240,15 @@ int axr_set_output(axr_ctx* ctx, void* bgra_dev, void* depth_dev);
 int axr_dirty_map_entries(const axr_ctx* ctx);
 int axr_set_dirty_map(axr_ctx* ctx, void* dirty_dev);
 int axr_clear_dirty_tiles(axr_ctx* ctx, void* bgra_dev, void* depth_dev, void* dirty_dev, int count, uint32_t packed_argb, float depth, void* stream);
+/* The same targets without clearing what the next frame overwrites anyway. With axr_set_output_fill on, a draw overwrites EVERY pixel of
+ * the 32x32 tiles it touches: the shaded colour where a triangle is visible, (packed_argb, depth) elsewhere, and its merge test sees
+ * `depth` instead of reading the target — valid for a target that holds exactly one draw on top of a clear to those values, which is
+ * what a composite slot is (not for shaders that discard, nor for axr_draw_mesh_host). The owner of the targets then keeps two dirty maps
+ * per target, alternating per use: axr_clear_stale_tiles clears only the tiles flagged in `prev` (the previous use) and not in `now`
+ * (this use) — none at all while the camera stands still — and hands `prev` back all zero. Same layouts as axr_clear_dirty_tiles. */
+int axr_set_output_fill(axr_ctx* ctx, int enabled, uint32_t packed_argb, float depth);
+int axr_clear_stale_tiles(axr_ctx* ctx, void* bgra_dev, void* depth_dev, void* dirty_prev_dev, void* dirty_now_dev, int count, uint32_t packed_argb,
+                          float depth, void* stream);
 /* Overlap consecutive draws: with overlap on, the geometry stages (vertex, setup, bins) of draw i+1 are enqueued on a second,
  * higher-priority stream and run beside the tile / shading kernel of draw i (two sets of per-draw buffers alternate). Results
  * are identical; throughput of back-to-back draws rises by a few percent (C3: 0.464 -> 0.433 ms per frame). Default: off, which
@@ -250,7 +259,7 @@ int axr_set_overlap(axr_ctx* ctx, int enabled);
  * another GPU, where that read would cross NVLink), the read can be turned off: every drawable z passes `z < +inf`.
  * Default: enabled. */
 int axr_set_depth_read(axr_ctx* ctx, int enabled);
-/* Device memory that other processes can map (cudaMalloc + cudaIpcGetMemHandle): composite targets on GPU 0. */
+/* Device memory that other processes can map (cudaMalloc + cudaIpcGetMemHandle), zero-filled: composite targets + dirty maps on GPU 0. */
 int axr_alloc_shared(axr_ctx* ctx, size_t bytes, void** dev_ptr_out, void* handle64_out);
 int axr_free_shared(axr_ctx* ctx, void* dev_ptr);
 /* CUDA IPC handles (64 bytes each) of the own framebuffer allocations, for one-process-per-GPU compositing. */

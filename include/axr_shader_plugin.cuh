@@ -31,8 +31,18 @@ inline int plugin_launch(const void* mv, const void* u, const void* fp, const vo
 	const TileIn& t = *static_cast<const TileIn*>(in);
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
 	if (which == 0) {
-		if (sampler) k_tile_shade<Shader, 1, false><<<dim3(gx, gy), TILE_THREADS, 0, s>>>(m, un, f, t);
-		else k_tile_shade<Shader, 0, false><<<dim3(gx, gy), TILE_THREADS, 0, s>>>(m, un, f, t);
+		bool filled = false;
+		if constexpr (!Shader::DISCARDS) {  // axr_set_output_fill (multi-GPU composite slots): a second instantiation
+			if (t.fill) {
+				if (sampler) k_tile_shade<Shader, 1, false, true><<<dim3(gx, gy), TILE_THREADS, 0, s>>>(m, un, f, t);
+				else k_tile_shade<Shader, 0, false, true><<<dim3(gx, gy), TILE_THREADS, 0, s>>>(m, un, f, t);
+				filled = true;
+			}
+		}
+		if (!filled) {
+			if (sampler) k_tile_shade<Shader, 1, false, false><<<dim3(gx, gy), TILE_THREADS, 0, s>>>(m, un, f, t);
+			else k_tile_shade<Shader, 0, false, false><<<dim3(gx, gy), TILE_THREADS, 0, s>>>(m, un, f, t);
+		}
 	} else {
 		if (sampler) k_shade_clipped<Shader, 1><<<CLIP_SHADE_CTAS, CLIP_SHADE_THREADS, 0, s>>>(m, un, f, t);
 		else k_shade_clipped<Shader, 0><<<CLIP_SHADE_CTAS, CLIP_SHADE_THREADS, 0, s>>>(m, un, f, t);

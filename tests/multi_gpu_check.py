@@ -27,7 +27,7 @@ def full_frame(scene):
 ok = True
 # ---- bands
 for transport in ("peer", "nccl"):
-    band = multi.band_rows(H, world)[rank]
+    band = multi.band_rows(H, world, multi.band_granule(transport))[rank]
     dev = api.Device(W, H, device=local, band=band)
     mesh = dev.load_scene(base)
     stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local))
@@ -61,7 +61,8 @@ for transport in ("peer", "nccl"):
     mesh = dev.load_scene(sc)
     stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local))
     comp = multi.Compositor(dev, rank, world, "views", None, stream, transport=transport)
-    for _ in range(5):
+    for j in (3, 1, 2, 5, 0):   # the camera moves from frame to frame (stale tiles in the shared slots); the last frame is view `rank`
+        dev.set_uniforms(*S.view_matrix_for((rank + j) % 8, 8, W, H))
         comp.begin_step()
         if comp.clears_own_target:
             dev.clear()
@@ -76,8 +77,8 @@ for transport in ("peer", "nccl"):
             other = S.Scene("t", W, H, v, f, S.SHADER_PHONG, model=base.model, textures=base.textures)
             other.view_proj, other.cam_pos = S.view_matrix_for(r, 8, W, H)
             c0, d0 = full_frame(other)
-            # peer: the last frame went to set last_set() and the other set has been cleared for the next one; nccl: both sets hold frames
-            for b in ((comp.last_set(),) if transport == "peer" else (0, 1)):
+            # the last frame went to set last_set() (the other set holds an earlier frame, taken with another camera, or is being tidied)
+            for b in (comp.last_set(),):
                 cs, ds = (comp.view_slot(b, r) if transport == "peer" else (comp.slots[b][0][r - 1], comp.slots[b][1][r - 1]))
                 c = cs.contiguous().cpu().numpy().view(np.uint8).reshape(H, W, 4)
                 d = ds.contiguous().cpu().numpy()

@@ -878,3 +878,44 @@ def test_shader_plugins_loaded_at_run_time(po):
         dev.sync()
     finally:
         dev.close()
+
+
+def test_output_fill_and_stale_tile_clears_keep_a_target_equal_to_clear_plus_draw(po):
+    """The composite-slot protocol of axiomr_b200/multi.py on one GPU: a target that is cleared ONCE, then receives one draw per frame
+    with axr_set_output_fill (every pixel of a touched tile is overwritten: shaded colour or the clear values; no depth read) while its
+    owner only clears the tiles the previous frame touched and this one did not (axr_clear_stale_tiles, two alternating dirty maps).
+    After every frame the target must equal `clear + that frame's draw` — the camera moves between frames, clipped, huge and small
+    triangles mix."""
+    from axiomr_b200 import api
+    v, f = S.random_triangles(1200, 21)
+    v2, f2 = S.icosphere(4, 1.2)
+    W, H = 416, 288
+    base = S.Scene("fill", W, H, np.concatenate([v, v2]), np.concatenate([f, f2 + v.shape[0]]), S.SHADER_PHONG, textures=_tex())
+    eyes = [(0.0, 0.0, 5.0), (2.5, 0.5, 4.0), (-3.0, -1.0, 6.0), (0.0, 0.0, 5.0), (0.3, 2.0, 9.0)]
+    dev = api.Device(W, H)
+    try:
+        mesh = dev.load_scene(base)
+        npx, nt = W * H, dev.dirty_map_entries()
+        ptr, _ = dev.alloc_shared(npx * 8 + 2 * nt * 4)        # colour | depth | dirty map 0 | dirty map 1 (zero-filled)
+        color_p, depth_p, maps = ptr, ptr + npx * 4, (ptr + npx * 8, ptr + npx * 8 + nt * 4)
+        dev.set_output(color_p, depth_p)
+        dev.clear()                                              # the one real clear of the target
+        dev.set_depth_read(False)
+        dev.set_output_fill(True)
+        for use, eye in enumerate(eyes):
+            sc = S.Scene(f"fill{use}", W, H, base.vertices, base.indices, S.SHADER_PHONG, textures=base.textures)
+            sc.view_proj, sc.cam_pos = S.default_camera(W, H, eye=eye)
+            dev.set_uniforms(sc.view_proj, sc.cam_pos)
+            dev.set_dirty_map(maps[use % 2])
+            dev.draw_mesh(mesh, sc.model)
+            dev.clear_stale_tiles(color_p, depth_p, maps[1 - use % 2], maps[use % 2])
+            c1, d1 = dev.resolve()
+            c0, d0, _ = po.oracle_render(sc, threads=4)
+            m = po.compare(c1, d1, c0, d0)
+            assert m["covered"] > 500 and m["coverage_mismatch"] == 0 and m["depth_bit_mismatch"] == 0 and m["color_max_diff"] <= 1, (use, m)
+        dev.set_output_fill(False)
+        dev.set_dirty_map(None)
+        dev.set_output(None, None)
+        dev.set_depth_read(True)
+    finally:
+        dev.close()

@@ -10,9 +10,7 @@ from axiomr_b200 import build as b  # noqa: E402
 # Compile-time knobs of axr_kernels.cuh (launch shapes). The defaults are the winners of the round-1 A/B runs
 # (profiles/r01_ab_*.jsonl); these variants bracket them.
 VARIANTS = {
-    "tile128x7": ["AXR_TILE_THREADS=128", "AXR_TILE_MINB=7"],
-    "tile128x6": ["AXR_TILE_THREADS=128", "AXR_TILE_MINB=6"],
-    "tile128x8": ["AXR_TILE_THREADS=128", "AXR_TILE_MINB=8"],
+    "idxpad": ["AXR_IDX_PAD=1"],
 }
 
 def _one(name: str) -> str:
