@@ -125,6 +125,7 @@ struct axr_ctx {
 	cudaStream_t geom_stream = nullptr;
 	unsigned* dirty_map = nullptr;  // axr_set_dirty_map
 	bool fill = false;              // axr_set_output_fill
+	bool out_rows = false;          // axr_set_output_rows
 	uint32_t fill_color = 0;
 	float fill_depth = 0.f;
 	bool color_fast = true;  // axr_set_color_math: fused colour arithmetic in the shading stage (default) or the reference's individually rounded one
@@ -454,7 +455,7 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 	in.items = sl.items; in.records = sl.records; in.n_records = sl.n_records; in.status = sl.d_status; in.sv = m.sv[si];
 	in.color = ctx->out_color; in.depth = ctx->out_depth; in.read_depth = ctx->read_depth;
 	in.depth_read = ctx->depth_read_override ? ctx->depth_read_override : ctx->out_depth;
-	in.row_major = ctx->host_chunks > 0 ? 1 : 0;
+	in.row_major = (ctx->host_chunks > 0 || ctx->out_rows) ? 1 : 0;
 	in.floor = peel ? ctx->peel_floor : nullptr;
 	in.again = peel ? ctx->peel_again : nullptr;
 	in.clip_tiles = sl.clip_tiles; in.n_clip_tiles = sl.n_clip_tiles;
@@ -1286,6 +1287,14 @@ int axr_set_output_fill(axr_ctx* ctx, int enabled, uint32_t packed_argb, float d
 	CU(cudaSetDevice(ctx->device));
 	if (int rc = check_pending(ctx)) return rc;
 	ctx->fill = enabled != 0; ctx->fill_color = packed_argb; ctx->fill_depth = depth;
+	return AXR_OK;
+}
+
+int axr_set_output_rows(axr_ctx* ctx, int enabled) {
+	if (!ctx) return AXR_ERR_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	if (int rc = check_pending(ctx)) return rc;
+	ctx->out_rows = enabled != 0;
 	return AXR_OK;
 }
 

@@ -114,13 +114,14 @@ class Compositor:
       double-buffered, on a second stream, overlapping the next frame).
     """
 
-    def __init__(self, dev, rank: int, world: int, mode: str, band, stream, transport: str | None = None, fill: bool = True):
+    def __init__(self, dev, rank: int, world: int, mode: str, band, stream, transport: str | None = None, fill: bool = True, rows: bool = True):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.dev, self.rank, self.world, self.mode, self.stream = dev, rank, world, mode, stream
         self.transport = transport or "peer"
         self.fill = bool(fill) and self.transport == "peer"
+        self.rows = bool(rows) and self.transport == "peer"   # remote stores in 128-byte rows
         self.launches_per_step = 0
         self.color, self.depth = framebuffer_tensors(dev)
         self.step = 0
@@ -190,6 +191,8 @@ class Compositor:
             self.dev.set_depth_read(False)   # the target is freshly cleared and receives exactly this draw
             if self.fill:
                 self.dev.set_output_fill(True)
+            if self.rows and self.rank != 0:
+                self.dev.set_output_rows(True)
         dist.barrier()
 
     # ------------------------------------------------------------------ per frame
@@ -296,3 +299,4 @@ class Compositor:
             self.dev.set_output(None, None)
             self.dev.set_dirty_map(None)
             self.dev.set_output_fill(False)
+            self.dev.set_output_rows(False)

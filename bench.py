@@ -264,7 +264,7 @@ def _parity_counts(torch, c_a, d_a, c_b, d_b):
     return cov, dbits, cmax
 
 
-def _run_multi(torch, dist, api, multi, sc, rank, world, local, mode, transport, steps, warmup, views_total=None, check=True, fill=True):
+def _run_multi(torch, dist, api, multi, sc, rank, world, local, mode, transport, steps, warmup, views_total=None, check=True, fill=True, rows=True):
     """One multi-GPU (or, at world == 1, single-GPU) figure: K timed frames of `sc` sharded by `mode`, then — on GPU 0, outside the
     timed region — a bit comparison of what landed there with GPU 0's own single-GPU render of the same view / frame.
     views_total: every rank renders its share of that many camera views per step (BASELINE config 5's 64 views) instead of one."""
@@ -274,7 +274,7 @@ def _run_multi(torch, dist, api, multi, sc, rank, world, local, mode, transport,
     mesh = dev.load_scene(sc)
     dev.set_overlap(True)
     stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local))
-    comp = multi.Compositor(dev, rank, world, mode, band, stream, transport=transport, fill=fill) if world > 1 else None
+    comp = multi.Compositor(dev, rank, world, mode, band, stream, transport=transport, fill=fill, rows=rows) if world > 1 else None
     n_cams = max(world, 8) if views_total is None else views_total
     my_views = [rank] if views_total is None else multi.views_for_rank(rank, world, views_total)
     if mode == "bands":
@@ -355,6 +355,7 @@ def main():
     ap.add_argument("--mode", default="views", choices=["views", "bands"], help="multi-GPU sharding (N>1)")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"], help="composite to GPU 0: fused peer stores or NCCL gather")
     ap.add_argument("--no-fill", action="store_true", help="peer transport without axr_set_output_fill: covered pixels only, GPU 0 re-clears the flagged tiles")
+    ap.add_argument("--no-rows", action="store_true", help="peer transport with 8x4-pixel blocks per warp on every rank (32-byte remote stores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the BASELINE config 5 figures (8K bands, 64 views) and the sustained pass")
@@ -389,7 +390,7 @@ def main():
     dev = api.Device(W, H, device=local, sampler=sc.sampler, band=band)
     mesh = dev.load_scene(sc)
     stream = torch.cuda.ExternalStream(dev.stream, device=torch.device("cuda", local))
-    comp = multi.Compositor(dev, rank, world, args.mode, band, stream, transport=args.transport, fill=not args.no_fill) if world > 1 else None
+    comp = multi.Compositor(dev, rank, world, args.mode, band, stream, transport=args.transport, fill=not args.no_fill, rows=not args.no_rows) if world > 1 else None
 
     def step(_i=0):
         if comp:
@@ -583,10 +584,10 @@ def main():
         dev = None
         k5 = max(3, args.steps // 4)
         sc8k = build_workload("c5")
-        extras["bands_c5"] = _run_multi(torch, dist, api, multi, sc8k, rank, world, local, "bands", "peer", k5, 3, fill=not args.no_fill)
+        extras["bands_c5"] = _run_multi(torch, dist, api, multi, sc8k, rank, world, local, "bands", "peer", k5, 3, fill=not args.no_fill, rows=not args.no_rows)
         extras["bands_c5"]["workload"] = workload_label("c5", sc8k)
         del sc8k
-        extras["views64"] = _run_multi(torch, dist, api, multi, sc, rank, world, local, "views", "peer", max(1, k5 // 2), 1, views_total=64, fill=not args.no_fill)
+        extras["views64"] = _run_multi(torch, dist, api, multi, sc, rank, world, local, "views", "peer", max(1, k5 // 2), 1, views_total=64, fill=not args.no_fill, rows=not args.no_rows)
         extras["views64"]["workload"] = "64 camera views (yaw = i*2pi/64) of " + workload_label(args.workload, sc)
         if rank == 0:
             line["bands_c5"] = extras["bands_c5"]

@@ -247,6 +247,10 @@ int axr_clear_dirty_tiles(axr_ctx* ctx, void* bgra_dev, void* depth_dev, void* d
  * per target, alternating per use: axr_clear_stale_tiles clears only the tiles flagged in `prev` (the previous use) and not in `now`
  * (this use) — none at all while the camera stands still — and hands `prev` back all zero. Same layouts as axr_clear_dirty_tiles. */
 int axr_set_output_fill(axr_ctx* ctx, int enabled, uint32_t packed_argb, float depth);
+/* Pixel -> lane mapping of the shading stage for outputs behind a link (axr_set_output into another GPU's memory): with rows on, a warp
+ * shades one 32 x 1 pixel row instead of an 8 x 4 block, so its colour and depth stores are 128 contiguous bytes each — NVLink moves
+ * those at about twice the rate of the 32-byte pieces a block row makes (what axr_draw_mesh_host does for PCIe). Results are identical. */
+int axr_set_output_rows(axr_ctx* ctx, int enabled);
 int axr_clear_stale_tiles(axr_ctx* ctx, void* bgra_dev, void* depth_dev, void* dirty_prev_dev, void* dirty_now_dev, int count, uint32_t packed_argb,
                           float depth, void* stream);
 /* Overlap consecutive draws: with overlap on, the geometry stages (vertex, setup, bins) of draw i+1 are enqueued on a second,
