@@ -825,7 +825,7 @@ int axr_parse_mtl(const char* text, size_t len, axr_mtl_entry* out, uint32_t cap
 int axr_generate_tangents(axr_ctx* ctx, const float* v8, uint64_t n_verts, const uint32_t* indices, uint64_t n_faces, float* out14) {
 	if (!ctx) return AXR_ERR_INVALID;
 	if ((n_verts && (!v8 || !out14)) || (n_faces && !indices)) return fail(ctx, AXR_ERR_INVALID, "axr_generate_tangents: null argument");
-	if (n_verts >= (1ull << 32) || n_faces * 3 >= (1ull << 32)) return fail(ctx, AXR_ERR_CAPACITY, "axr_generate_tangents: mesh too large for 32-bit corner ids");
+	if (n_verts >= (1ull << 31) - 1 || n_faces * 3 >= (1ull << 32)) return fail(ctx, AXR_ERR_CAPACITY, "axr_generate_tangents: mesh too large (vertex count for the 32-bit scan, corner ids)");
 	for (uint64_t i = 0; i < n_faces * 3; ++i)
 		if (indices[i] >= n_verts) return fail(ctx, AXR_ERR_INVALID, "axr_generate_tangents: index %u out of range", indices[i]);
 	if (n_verts == 0) return AXR_OK;

@@ -65,12 +65,36 @@ __global__ void k_tan_vertices(const float* __restrict__ v8, unsigned long long 
 	unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (v >= n_verts) return;
 	const unsigned s0 = start[v], s1 = start[v + 1];
-	// corner ids into face order, corner order (insertion sort: valence is small for real meshes)
-	for (unsigned i = s0 + 1; i < s1; ++i) {
-		const unsigned key = corners[i];
-		unsigned j = i;
-		while (j > s0 && corners[j - 1] > key) { corners[j] = corners[j - 1]; --j; }
-		corners[j] = key;
+	// corner ids into face order, corner order. Insertion sort for the valences real meshes have; a pole or fan vertex with thousands
+	// of incident faces would make that one thread quadratic, so long lists take an in-place heapsort (same result, O(n log n)).
+	const unsigned cnt = s1 - s0;
+	unsigned* c = corners + s0;
+	if (cnt <= 32u) {
+		for (unsigned i = 1; i < cnt; ++i) {
+			const unsigned key = c[i];
+			unsigned j = i;
+			while (j > 0 && c[j - 1] > key) { c[j] = c[j - 1]; --j; }
+			c[j] = key;
+		}
+	} else {
+		auto sift = [&](unsigned root, unsigned end) {  // max-heap on c[0, end)
+			const unsigned key = c[root];
+			for (;;) {
+				unsigned child = 2u * root + 1u;
+				if (child >= end) break;
+				if (child + 1u < end && c[child + 1u] > c[child]) ++child;
+				if (!(c[child] > key)) break;
+				c[root] = c[child];
+				root = child;
+			}
+			c[root] = key;
+		};
+		for (unsigned i = cnt / 2u; i-- > 0;) sift(i, cnt);
+		for (unsigned end = cnt - 1u; end > 0; --end) {
+			const unsigned top = c[0];
+			c[0] = c[end]; c[end] = top;
+			sift(0, end);
+		}
 	}
 	v3 ts = V3(0.f, 0.f, 0.f), bs = V3(0.f, 0.f, 0.f);
 	for (unsigned i = s0; i < s1; ++i) {

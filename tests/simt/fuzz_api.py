@@ -35,6 +35,8 @@ class Model:
 
 
 def main():
+    # bit-identical colours need the individually rounded colour arithmetic (the default fused mode is within 1 LSB by contract)
+    os.environ.setdefault("AXR_B200_COLOR_MATH", "exact")
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=60.0)
     ap.add_argument("--seed", type=int, default=0)

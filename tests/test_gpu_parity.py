@@ -919,3 +919,27 @@ def test_output_fill_and_stale_tile_clears_keep_a_target_equal_to_clear_plus_dra
         dev.set_depth_read(True)
     finally:
         dev.close()
+
+
+def test_tangents_of_a_pole_vertex_with_thousands_of_faces():
+    """axr_generate_tangents puts each vertex's incident corners into face order before summing (the reference accumulates in face
+    order, src/mesh.cpp:222-298); a pole / fan vertex must not make that quadratic. 3000 faces around one vertex, shuffled:
+    bit-equal with the numpy mirror of the reference loader's arithmetic."""
+    from axiomr_b200 import api, obj
+    n = 3000
+    ang = np.linspace(0, 2 * np.pi, n + 1)[:-1]
+    v8 = np.zeros((n + 1, 8), np.float32)
+    v8[1:, 0] = np.cos(ang); v8[1:, 1] = np.sin(ang); v8[1:, 2] = 0.1 * np.sin(3 * ang)
+    v8[:, 3] = v8[:, 0] * 0.5 + 0.5 + (0.01 * np.arange(n + 1)) % 0.1
+    v8[:, 4] = v8[:, 1] * 0.5 + 0.5
+    v8[:, 5:8] = [0, 0, 1]
+    f = np.array([[0, 1 + i, 1 + (i + 1) % n] for i in range(n)], np.uint32)
+    f = f[np.random.default_rng(1).permutation(n)]
+    dev = api.Device(16, 16)
+    try:
+        got = dev.generate_tangents(v8, f)
+    finally:
+        dev.close()
+    want = obj.tangents(v8, f)
+    same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+    assert same.all(), np.argwhere(~same)[:5]
