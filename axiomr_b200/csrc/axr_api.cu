@@ -1085,16 +1085,48 @@ int axr_draw_mesh(axr_ctx* ctx, axr_mesh mh, const float model[16]) {
 }
 
 // Device-side alias of a host range, page-locking it on first use. Returns nullptr when the range cannot be mapped.
+// Ranges this context registered are reused only when they contain [p, p + bytes); a registration that starts inside the range but
+// is too small (a freed buffer whose address was reused by a larger framebuffer) is dropped and taken again. Memory the caller
+// pinned itself (axr_host_alloc, cudaHostAlloc) is taken at its word: the allocation has to cover the framebuffer.
 static void* map_host_range(axr_ctx* ctx, void* p, size_t bytes) {
 	void* d = nullptr;
-	if (cudaHostGetDevicePointer(&d, p, 0) == cudaSuccess && d) return d;
+	char* const lo = (char*)p;
+	char* const hi = lo + bytes;
+	for (size_t i = 0; i < ctx->registered.size();) {
+		char* const rlo = (char*)ctx->registered[i].first;
+		char* const rhi = rlo + ctx->registered[i].second;
+		if (lo >= rlo && hi <= rhi) return cudaHostGetDevicePointer(&d, p, 0) == cudaSuccess ? d : nullptr;
+		if (lo < rhi && hi > rlo) {  // overlaps without containing: stale
+			cudaHostUnregister(ctx->registered[i].first);
+			cudaGetLastError();
+			ctx->registered.erase(ctx->registered.begin() + (long)i);
+			continue;
+		}
+		++i;
+	}
+	if (cudaHostGetDevicePointer(&d, p, 0) == cudaSuccess && d) return d;  // pinned by the caller
 	cudaGetLastError();
-	for (auto& r : ctx->registered)
-		if (r.first == p && r.second >= bytes) return cudaHostGetDevicePointer(&d, p, 0) == cudaSuccess ? d : nullptr;
 	if (cudaHostRegister(p, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
 	ctx->registered.emplace_back(p, bytes);
 	if (cudaHostGetDevicePointer(&d, p, 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
 	return d;
+}
+
+int axr_host_release(axr_ctx* ctx, void* host_ptr) {
+	if (!ctx) return AXR_ERR_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	if (int rc = check_pending(ctx)) return rc;
+	if (int rc = sync_all(ctx)) return rc;
+	for (size_t i = 0; i < ctx->registered.size(); ++i) {
+		char* const rlo = (char*)ctx->registered[i].first;
+		if ((char*)host_ptr >= rlo && (char*)host_ptr < rlo + ctx->registered[i].second) {
+			cudaHostUnregister(ctx->registered[i].first);
+			cudaGetLastError();
+			ctx->registered.erase(ctx->registered.begin() + (long)i);
+			return AXR_OK;
+		}
+	}
+	return AXR_OK;  // never registered (pinned by the caller, or not mappable): nothing to release
 }
 
 int axr_draw_mesh_host(axr_ctx* ctx, axr_mesh mh, const float model[16], uint8_t* bgra, float* depth) {

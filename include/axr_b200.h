@@ -204,6 +204,10 @@ int axr_draw_mesh(axr_ctx* ctx, axr_mesh mesh, const float model[16]);
  * AXR_B200_HOST_DEPTH_ZEROCOPY=0 (read once at axr_create) uploads the whole host depth plane in row chunks instead of reading it
  * through the mapping (measured slower on C3: 0.98 against 0.87 ms per call). */
 int axr_draw_mesh_host(axr_ctx* ctx, axr_mesh mesh, const float model[16], uint8_t* bgra, float* depth);
+/* A buffer that axr_draw_mesh_host page-locked stays locked until axr_destroy; a caller that frees such a buffer earlier (a
+ * std::vector, a numpy array) releases it first. A remembered registration is only reused when it contains the whole framebuffer;
+ * one that merely overlaps it (freed memory whose address was reused) is dropped and taken again. Synchronises the context. */
+int axr_host_release(axr_ctx* ctx, void* host_ptr);
 int axr_sync(axr_ctx* ctx);
 int axr_get_stats(axr_ctx* ctx, axr_stats* out);
 

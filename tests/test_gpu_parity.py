@@ -943,3 +943,28 @@ def test_tangents_of_a_pole_vertex_with_thousands_of_faces():
     want = obj.tangents(v8, f)
     same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
     assert same.all(), np.argwhere(~same)[:5]
+
+
+def test_host_framebuffer_registrations_can_be_released_and_retaken(po):
+    """axr_draw_mesh_host page-locks a caller's framebuffer arrays on first use; axr_host_release undoes that (before the caller
+    frees them), a later draw onto the same arrays takes the lock again, and releasing memory that was never locked is a no-op."""
+    from axiomr_b200 import api
+    sc = S.config2(level=4, w=320, h=200)
+    c0, d0, _ = po.oracle_render(sc, threads=4)
+    dev = api.Device(sc.width, sc.height)
+    try:
+        mesh = dev.load_scene(sc)
+        for _ in range(2):
+            color = np.zeros((sc.height, sc.width, 4), np.uint8)
+            color[..., 3] = 255
+            depth = np.full((sc.height, sc.width), np.inf, np.float32)
+            for _ in range(2):   # the second draw composites onto the first: same picture
+                dev.draw_mesh_host(mesh, sc.model, color, depth)
+            m = po.compare(color, depth, c0, d0)
+            assert m["covered"] > 500 and m["coverage_mismatch"] == 0 and m["depth_bit_mismatch"] == 0 and m["color_max_diff"] <= 1, m
+            dev.host_release(color)
+            dev.host_release(depth)
+            dev.host_release(depth)                      # already released
+        dev.host_release(np.zeros(16, np.float32))       # never registered
+    finally:
+        dev.close()
