@@ -402,6 +402,33 @@ def test_cpp_dropin_adapter_vs_reference_in_process(tmp_path, shader):
     assert r.returncode == 0 and "PARITY OK" in r.stdout, (r.stdout, r.stderr)
 
 
+def test_cpp_dropin_user_shader_plugin_vs_reference_running_the_same_ishader(tmp_path):
+    """A shader of the user's own, end to end against the real thing: in ONE process the unmodified reference pipeline runs an
+    IShader subclass written against its plugin contract (LambertTintShader in tests/dropin/dropin_demo.cpp) and
+    AR::B200TiledPipeline runs the device functor compiled from the same formulas (tests/plugins/lambert_tint.cu), handed to
+    Pipeline::setShader as an AR::B200PluginShader; the two host framebuffers are compared."""
+    import subprocess
+    import sys
+    from objutil import write_obj_scene
+    if _os.environ.get("AXR_SIMT_TESTS_ONLY") == "1":
+        pytest.skip("plug-ins are nvcc-built device code")
+    root = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+    exe = _os.path.join(root, "oracle", "_ref", "dropin_demo")
+    if not _os.path.exists(exe):
+        pytest.skip("oracle/_ref/dropin_demo not built (needs /root/reference at build time)")
+    sys.path.insert(0, _os.path.join(root, "tools"))
+    try:
+        from build_shader_plugin import build_plugin
+    finally:
+        sys.path.pop(0)
+    plugin = build_plugin(_os.path.join(root, "tests", "plugins", "lambert_tint.cu"))
+    v, f = S.head_like(24, 23)
+    obj = write_obj_scene(str(tmp_path), "head", v, f, S._pbr_textures(64))
+    r = subprocess.run([exe, obj, "400", "300", "3", plugin], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and "PARITY OK" in r.stdout, (r.stdout, r.stderr)
+
+
 # ---------------------------------------------------------------------------------------------- BASELINE.json full-size configs
 def _full_size(po, sc, min_cov):
     """Full-size config against the CPU checker (the unmodified reference when present and the mode is nearest), in both colour
