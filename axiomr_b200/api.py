@@ -86,7 +86,7 @@ ABI_SYMBOLS = [
     "axr_host_free", "axr_stream", "axr_framebuffer_device", "axr_set_output", "axr_framebuffer_ipc", "axr_open_ipc",
     "axr_close_ipc", "axr_set_profiling", "axr_get_kernel_times", "axr_set_depth_read", "axr_alloc_shared", "axr_free_shared", "axr_set_overlap", "axr_upload_framebuffer_async", "axr_draw_mesh_host", "axr_generate_tangents", "axr_measure_fp32_issue", "axr_set_color_math", "axr_update_mesh_vertices", "axr_dirty_map_entries", "axr_set_dirty_map", "axr_clear_dirty_tiles",
     "axr_load_obj", "axr_load_obj_file", "axr_mesh_group_info", "axr_mesh_read", "axr_parse_mtl",
-    "axr_load_shader_plugin", "axr_set_shader_user", "axr_set_output_fill", "axr_clear_stale_tiles", "axr_set_output_rows", "axr_host_release",
+    "axr_load_shader_plugin", "axr_set_shader_user", "axr_set_output_fill", "axr_clear_stale_tiles", "axr_set_output_rows", "axr_host_release", "axr_measure_gather",
 ]
 STAGES = ["vertex_xform", "setup_raster", "scan_tiles", "bin_scatter", "tile_shade"]
 
@@ -164,6 +164,7 @@ def _bind(lib):
     lib.axr_set_output_fill.argtypes = [vp, C.c_int, C.c_uint32, C.c_float]
     lib.axr_set_output_rows.argtypes = [vp, C.c_int]
     lib.axr_host_release.argtypes = [vp, vp]
+    lib.axr_measure_gather.argtypes = [vp, C.POINTER(C.c_double)]
     lib.axr_clear_stale_tiles.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_uint32, C.c_float, vp]
     lib.axr_alloc_shared.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.c_void_p]
     lib.axr_free_shared.argtypes = [vp, vp]
@@ -404,6 +405,12 @@ class Device:
     def set_output_fill(self, enabled: bool, packed_argb: int = 0xFF000000, depth: float = float("inf")):
         """Draws overwrite every pixel of the tiles they touch (shaded colour or these values): see axr_set_output_fill."""
         self._check(self.lib.axr_set_output_fill(self.h, 1 if enabled else 0, packed_argb, depth))
+
+    def measure_gather(self) -> float:
+        """Randomly placed 32-byte DRAM sectors per second (16-byte gathers): the shading stage's other bound."""
+        v = C.c_double(0.0)
+        self._check(self.lib.axr_measure_gather(self.h, C.byref(v)))
+        return v.value
 
     def host_release(self, array: np.ndarray):
         """Undo the page-lock axr_draw_mesh_host took on a host framebuffer array (before the array is freed)."""

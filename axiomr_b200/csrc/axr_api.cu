@@ -1265,6 +1265,46 @@ int axr_measure_fp32_issue(axr_ctx* ctx, double* fmul_fadd_winst_per_s, double* 
 	return AXR_OK;
 }
 
+int axr_measure_gather(axr_ctx* ctx, double* sectors_per_s) {
+	if (!ctx || !sectors_per_s) return AXR_ERR_INVALID;
+	const int span = getenv("AXR_GATHER_SPAN") ? atoi(getenv("AXR_GATHER_SPAN")) : 1;  // measurement knob: 2 / 4 consecutive sectors per position
+	CU(cudaSetDevice(ctx->device));
+	int rc = check_pending(ctx);
+	if (rc) return rc;
+	rc = sync_all(ctx);
+	if (rc) return rc;
+	const unsigned long long n_sectors = 1ull << 25;  // 1 GiB, 8x the L2
+	const int ctas = 148 * 8, threads = 256, steps = 64;
+	constexpr int ILP = 8;
+	uint4* buf = nullptr;
+	unsigned* out = nullptr;
+	CU(cudaMalloc(&buf, n_sectors * 32));
+	if (cudaMalloc(&out, (size_t)ctas * threads * 4) != cudaSuccess) { cudaFree(buf); return fail(ctx, AXR_ERR_CUDA, "axr_measure_gather: out of device memory"); }
+	cudaMemsetAsync(buf, 0x5a, n_sectors * 32, ctx->stream);
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	float best = 1e30f;
+	for (int rep = 0; rep < 4; ++rep) {  // first repetition warms up
+		cudaEventRecord(e0, ctx->stream);
+		if (span == 4) k_gather_peak<ILP / 2, 4><<<ctas, threads, 0, ctx->stream>>>(buf, n_sectors, steps, out);
+		else if (span == 2) k_gather_peak<ILP / 2, 2><<<ctas, threads, 0, ctx->stream>>>(buf, n_sectors, steps, out);
+		else k_gather_peak<ILP, 1><<<ctas, threads, 0, ctx->stream>>>(buf, n_sectors, steps, out);
+		cudaEventRecord(e1, ctx->stream);
+		cudaEventSynchronize(e1);
+		float ms = 0.f;
+		cudaEventElapsedTime(&ms, e0, e1);
+		if (rep && ms < best) best = ms;
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(buf);
+	cudaFree(out);
+	CU(cudaGetLastError());
+	*sectors_per_s = (double)ctas * threads * steps * (span == 1 ? ILP : (ILP / 2) * span) / (best * 1e-3);
+	return AXR_OK;
+}
+
 void* axr_host_alloc(size_t bytes) {
 	void* p = nullptr;
 	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) return nullptr;

@@ -198,6 +198,34 @@ __global__ void __launch_bounds__(256) k_fp32_peak(float* out, float a, float b,
 	out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
 
+// ------------------------------------------------------------------------------------------------ random-gather micro-benchmark
+// The shading stage reads its vertices and texels as data-dependent 16-byte gathers, one 32-byte DRAM sector each when nothing is
+// shared; how many such sectors per second the memory system delivers is the bound that matters for it, not the streaming bandwidth.
+// Every thread issues `ILP` independent 16-byte loads per step at pseudo-random 32-byte-aligned offsets of a buffer much larger
+// than L2 (the offsets of a warp's lanes are unrelated: 32 sectors per warp-wide load), and chains the next step's offsets on the
+// loaded data so that nothing can be hoisted.
+// SPAN: consecutive sectors fetched per random position (1: a lone 32-byte sector; 2: a 64-byte record; 4: a whole 128-byte line)
+template <int ILP, int SPAN = 1>
+__global__ void __launch_bounds__(256) k_gather_peak(const uint4* __restrict__ buf, unsigned long long n_sectors, int steps, unsigned* out) {
+	unsigned long long x = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+	unsigned acc = 0;
+	for (int s = 0; s < steps; ++s) {
+		uint4 v[ILP];
+#pragma unroll
+		for (int k = 0; k < ILP; ++k) {
+			x = x * 6364136223846793005ull + 1442695040888963407ull;
+			const uint4* p = buf + (((x >> 20) % n_sectors) / SPAN) * (2ull * SPAN);  // aligned to SPAN sectors
+			v[k] = __ldg(p);  // the first half of a sector
+#pragma unroll
+			for (int j = 1; j < SPAN; ++j) { const uint4 w = __ldg(p + 2 * j); v[k].x ^= w.x; v[k].w ^= w.y; }
+		}
+#pragma unroll
+		for (int k = 0; k < ILP; ++k) acc += v[k].x ^ v[k].w;
+		x += acc & 1u;
+	}
+	out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
 // ------------------------------------------------------------------------------------------------ vertex stage
 // reference src/tiled_pipeline.cpp:210-212 (mvp * vec4(pos,1)) + :57-66 (perspective divide), once per unique vertex
 // It also zeroes the draw's device counters (k_setup_raster, the next kernel on the stream, is their first user), which

@@ -471,6 +471,7 @@ def main():
 
     # ---- FP32 issue micro-benchmark: the measured issue rate turns the kernels' instruction counts into a floor
     fp32_rate, ffma_rate = dev.measure_fp32_issue()
+    gather_rate = dev.measure_gather()   # randomly placed 32-byte DRAM sectors per second (16-byte gathers)
 
     # covered pixels (for the texture term of the algorithmic bytes) — outside the timed region
     if comp and args.transport == "peer" and args.mode == "bands":
@@ -549,6 +550,16 @@ def main():
             tj = json.load(open(tp)).get(args.workload, {})
         except Exception:
             tj = {}
+        # The shading stage reads vertices, attributes and texels as data-dependent 16-byte gathers: its DRAM traffic (ncu) is held against
+        # both ends — the streaming peak and the measured rate of randomly placed sectors on this GPU. It sits between the two.
+        ts_bytes, ts_ms = tj.get("tile_shade"), kavg.get("tile_shade")
+        if ts_bytes and ts_ms:
+            line["roofline_gather"] = {"kernel": "tile_shade", "dram_bytes": ts_bytes, "kernel_ms": ts_ms, "achieved": ts_bytes / (ts_ms * 1e-3) / 1e9,
+                                       "unit": "GB/s", "random_sector_peak": gather_rate * 32 / 1e9, "streaming_peak": peak,
+                                       "frac_of_random_sector_peak": ts_bytes / (ts_ms * 1e-3) / (gather_rate * 32),
+                                       "note": "axr_measure_gather: 16-byte loads at random 32-byte-aligned offsets of a 1 GiB buffer, 8 in flight per "
+                                               "thread; fetching 2 or 4 consecutive sectors per position gives the same sectors/s, i.e. the memory "
+                                               "system's limit for scattered reads is per sector, about a fifth of the streaming bandwidth"}
         line["roofline_kernels"] = {k: {"algorithmic_bytes": per_stage.get(k, 0), "kernel_ms": kavg[k],
                                         "achieved": (per_stage.get(k, 0) / (kavg[k] * 1e-3) / 1e9) if kavg[k] > 0 else 0.0,
                                         "frac": (per_stage.get(k, 0) / (kavg[k] * 1e-3) / 1e9 / peak) if kavg[k] > 0 else 0.0,

@@ -223,6 +223,11 @@ int axr_get_kernel_times(axr_ctx* ctx, float ms_out[AXR_NUM_STAGES], uint64_t* d
 /* ---- FP32 issue micro-benchmark: measured warp-instructions per second of this GPU for (0) separate
  *      FMUL + FADD, which is what the path executes (no contraction, for parity), and (1) FFMA. One warp-instruction = 32 lanes. */
 int axr_measure_fp32_issue(axr_ctx* ctx, double* fmul_fadd_winst_per_s, double* ffma_winst_per_s);
+/* The same for the other bound of the shading stage: data-dependent 16-byte gathers, one 32-byte DRAM sector each (vertex records,
+ * attributes, texels of neighbouring pixels share little at one triangle per pixel). Measures how many randomly placed sectors per
+ * second this GPU delivers (1 GiB buffer, 8 loads in flight per thread, 2368 CTAs): x 32 bytes = the random-sector bandwidth the
+ * stage's DRAM traffic is held against (bench.py: roofline_gather). */
+int axr_measure_gather(axr_ctx* ctx, double* sectors_per_s);
 
 /* ---- pinned host memory for framebuffers / staging (cudaHostAlloc): makes axr_upload_framebuffer / axr_resolve
  *      run at full PCIe rate. Plain malloc'ed memory works too, just slower. */
