@@ -10,7 +10,7 @@ from axiomr_b200 import build as b  # noqa: E402
 # Compile-time knobs of axr_kernels.cuh (launch shapes). The defaults are the winners of the round-1 A/B runs
 # (profiles/r01_ab_*.jsonl); these variants bracket them.
 VARIANTS = {
-    "idxpad": ["AXR_IDX_PAD=1"],
+    "recompute_sv": ["AXR_TILE_RECOMPUTE_SV=1"],
 }
 
 def _one(name: str) -> str:
