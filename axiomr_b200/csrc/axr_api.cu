@@ -1104,7 +1104,9 @@ static void* map_host_range(axr_ctx* ctx, void* p, size_t bytes) {
 		}
 		++i;
 	}
-	if (cudaHostGetDevicePointer(&d, p, 0) == cudaSuccess && d) return d;  // pinned by the caller
+	cudaPointerAttributes attr;  // (asking for the device pointer of pageable memory is an error; asking what the memory is, is not)
+	if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost)
+		return cudaHostGetDevicePointer(&d, p, 0) == cudaSuccess ? d : nullptr;  // pinned by the caller
 	cudaGetLastError();
 	if (cudaHostRegister(p, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
 	ctx->registered.emplace_back(p, bytes);

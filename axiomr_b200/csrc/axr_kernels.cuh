@@ -918,7 +918,7 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 	}
 	// 2. binned triangles, BIN_ROUND candidates at a time: every thread loads and sets up ITS candidate (all gathers in flight at
 	//    once) and the ones that reach into the tile are parked in shared memory; then warp w walks them over ITS strip of the tile
-	//    (rows 4w .. 4w+3 with 8 warps), an 8x4 pixel block per step. A pixel belongs to one lane of one warp, so the running minimum
+	//    (rows 4w .. 4w+3 with 8 warps), an 8x4 pixel block of the tile's own grid per step. A pixel belongs to one lane of one warp, so the running minimum
 	//    needs no atomics, and a tile with a handful of large triangles (C1) keeps all warps busy instead of one.
 	if (b1 > b0) {
 		const int warp = tid >> 5, lane = tid & 31;
@@ -977,10 +977,11 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 					q.inv_area = d[9]; q.z0 = d[10]; q.z1 = d[11]; q.z2 = d[12];
 					q.fminx = (int)__float_as_uint(d[13]);
 					const unsigned qord = __float_as_uint(d[14]);
-					for (int ry = qy0; ry < qy1; ry += 4)
-						for (int rx = qx0; rx < qx1; rx += 8) {
+					// blocks on the tile's own 8x4 grid: pixel (x, y) is always lane (x & 7, y & 3) of its strip's warp, whatever the record
+					for (int ry = qy0 & ~3; ry < qy1; ry += 4)
+						for (int rx = qx0 & ~7; rx < qx1; rx += 8) {
 							const int tx_ = rx + lx, ty_ = ry + ly;
-							if (tx_ >= qx1 || ty_ >= qy1) continue;
+							if (tx_ < qx0 || tx_ >= qx1 || ty_ < qy0 || ty_ >= qy1) continue;
 							const int px = x0 + tx_, py = y0 + ty_;
 							float c0, c1, c2, al, be, ga;
 							if (!coverage(q, px, py, c0, c1, c2)) continue;
@@ -999,6 +1000,7 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 				__syncthreads();
 			}
 			if (scan) {
+				__syncthreads();  // (a chunk without candidates has no barrier between reading the count and this reset)
 				if (tid == 0) s_ncand = 0u;
 				__syncthreads();
 			}

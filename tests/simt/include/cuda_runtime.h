@@ -235,6 +235,15 @@ cudaError_t cudaHostUnregister(void* p);
 cudaError_t simt_host_device_pointer(void** d, void* h);
 template <typename T>
 static inline cudaError_t cudaHostGetDevicePointer(T** d, void* h, unsigned) { return simt_host_device_pointer((void**)d, h); }
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes { cudaMemoryType type; int device; void* devicePointer; void* hostPointer; };
+// what cudaPointerGetAttributes answers for host memory: page-locked (cudaHostAlloc / cudaHostRegister) or not
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {
+	void* d = nullptr;
+	a->type = simt_host_device_pointer(&d, const_cast<void*>(p)) == cudaSuccess ? cudaMemoryTypeHost : cudaMemoryTypeUnregistered;
+	a->device = 0; a->devicePointer = d; a->hostPointer = const_cast<void*>(p);
+	return cudaSuccess;
+}
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMemcpyKind, cudaStream_t);
 cudaError_t cudaMemsetAsync(void* dst, int v, size_t n, cudaStream_t);
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t*, unsigned);
