@@ -125,6 +125,11 @@ struct axr_ctx {
 	cudaStream_t geom_stream = nullptr;
 	unsigned* dirty_map = nullptr;  // axr_set_dirty_map
 	bool fill = false;              // axr_set_output_fill
+	// The depth plane `fresh_target` was cleared to +inf by axr_clear (or at creation) and nothing has been drawn into it since: the
+	// first draw's merge test `z < fbZ` passes for every drawable z, so it does not read the plane (13 MB of the C3 frame). Off for
+	// good once the raw framebuffer pointers have been handed out (axr_framebuffer_device / _ipc: others may write behind our back).
+	bool depth_fresh = false, depth_external = false;
+	const float* fresh_target = nullptr;
 	bool out_rows = false;          // axr_set_output_rows
 	uint32_t fill_color = 0;
 	float fill_depth = 0.f;
@@ -454,6 +459,9 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 	in.vis = sl.vis; in.tile_touched = sl.tile_touched; in.tile_cursor = sl.tile_count; in.bin_start = sl.bin_start;
 	in.items = sl.items; in.records = sl.records; in.n_records = sl.n_records; in.status = sl.d_status; in.sv = m.sv[si];
 	in.color = ctx->out_color; in.depth = ctx->out_depth; in.read_depth = ctx->read_depth;
+	if (ctx->depth_fresh && !ctx->depth_external && ctx->fresh_target == ctx->out_depth && ctx->out_depth == ctx->depth && ctx->host_chunks == 0 && !peel)
+		in.read_depth = 0;  // (own plane only: a redirected output may have other writers)
+	ctx->depth_fresh = false;  // whatever this draw is, the plane is no longer known to be all +inf
 	in.depth_read = ctx->depth_read_override ? ctx->depth_read_override : ctx->out_depth;
 	in.row_major = (ctx->host_chunks > 0 || ctx->out_rows) ? 1 : 0;
 	in.floor = peel ? ctx->peel_floor : nullptr;
@@ -638,6 +646,7 @@ int axr_create(const axr_config* cfg, axr_ctx** out) {
 	for (int si = 0; si < 2; ++si)
 		if (reset_raster_state(c, si) != AXR_OK) { g_create_error = c->error; axr_destroy(c); return AXR_ERR_CUDA; }
 	k_clear<<<grid_for(npx, 256), 256, 0, c->stream>>>(c->color, c->depth, 0u, INFINITY, 0, npx);  // Framebuffer ctor: colour 0, depth +inf
+	c->depth_fresh = true; c->fresh_target = c->depth;
 	CUC(cudaStreamSynchronize(c->stream));
 #undef CUC
 	*out = c;
@@ -1045,6 +1054,8 @@ int axr_clear(axr_ctx* ctx, uint32_t packed_argb, float depth) {
 	const size_t first = (size_t)ctx->fp.y_lo * ctx->fp.W, n = (size_t)(ctx->fp.y_hi - ctx->fp.y_lo) * ctx->fp.W;
 	k_clear<<<grid_for(n, 256), 256, 0, ctx->stream>>>(ctx->out_color, ctx->out_depth, packed_argb, depth, first, n);
 	CU(cudaGetLastError());
+	ctx->depth_fresh = depth == INFINITY;
+	ctx->fresh_target = ctx->out_depth;
 	return AXR_OK;
 }
 
@@ -1055,7 +1066,10 @@ static int upload_framebuffer(axr_ctx* ctx, const uint8_t* bgra, const float* de
 	if (rc) return rc;
 	const size_t first = (size_t)ctx->fp.y_lo * ctx->fp.W, n = (size_t)(ctx->fp.y_hi - ctx->fp.y_lo) * ctx->fp.W;
 	if (bgra) CU(cudaMemcpyAsync(ctx->out_color + first, bgra + first * 4, n * 4, cudaMemcpyHostToDevice, ctx->stream));
-	if (depth) CU(cudaMemcpyAsync(ctx->out_depth + first, depth + first, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+	if (depth) {
+		CU(cudaMemcpyAsync(ctx->out_depth + first, depth + first, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+		ctx->depth_fresh = false;
+	}
 	if (wait) CU(cudaStreamSynchronize(ctx->stream));
 	return AXR_OK;
 }
@@ -1322,6 +1336,7 @@ int axr_framebuffer_device(axr_ctx* ctx, void** bgra_dev, void** depth_dev) {
 	if (!ctx) return AXR_ERR_INVALID;
 	if (bgra_dev) *bgra_dev = ctx->color;
 	if (depth_dev) *depth_dev = ctx->depth;
+	ctx->depth_external = true;  // whoever holds the pointers may write the planes: no assumptions about their contents any more
 	return AXR_OK;
 }
 
@@ -1445,6 +1460,7 @@ int axr_framebuffer_ipc(axr_ctx* ctx, void* color_handle64, void* depth_handle64
 	CU(cudaSetDevice(ctx->device));
 	CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)color_handle64, ctx->color));
 	CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)depth_handle64, ctx->depth));
+	ctx->depth_external = true;
 	return AXR_OK;
 }
 
