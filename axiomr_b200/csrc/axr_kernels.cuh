@@ -885,12 +885,15 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 	__shared__ float s_rec[BIN_ROUND][16];  // set-up candidates of one round (edges, 1/area, z, floor(minX), ordinal, tile-relative box)
 	__shared__ unsigned short s_cand[SCAN_CHUNK];  // BINS_SCAN: records of the current chunk that reach into this tile
 	__shared__ unsigned s_clipped, s_nrec, s_ncand;
-	if (in.status->overflow) return;  // the host grows the bins and re-issues the draw
 	const int tx = blockIdx.x, ty = fp.ty_lo + blockIdx.y;
 	const int tile = ty * fp.ntx + tx;
 	const int x0 = tx * GT, y0 = ty * GT;
+	// (the three loads that decide whether this CTA has anything to do are independent: issued together, one round trip for the
+	// thousands of CTAs of an untouched tile)
+	const unsigned ovf = in.status->overflow;
 	const unsigned touched = in.tile_touched[tile];
 	const unsigned nrec = in.bin_mode == BINS_NONE ? 0u : *in.n_records;
+	if (ovf) return;  // the host grows the bins and re-issues the draw
 	// candidates among the binned records: this tile's reference list, or (BINS_SCAN) every record once the tile's count is non-zero
 	unsigned b0 = 0, b1 = 0;
 	if (nrec) {
