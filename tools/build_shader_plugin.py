@@ -17,7 +17,12 @@ def build_plugin(src: str, out: str | None = None, force: bool = False) -> str:
     if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps if os.path.exists(d)):
         return out
     cmd = [b.nvcc()] + b.NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "axiomr_b200", "csrc"), "-o", out, src]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True)
+    except OSError as e:  # no compiler on this machine
+        if os.path.exists(out) and not force:
+            return out    # a copy built elsewhere travels with the tree; axr_load_shader_plugin refuses it if it is out of date
+        raise RuntimeError(f"cannot run nvcc to build the shader plug-in {src}: {e}")
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError(f"nvcc failed building the shader plug-in {src}")
