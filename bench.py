@@ -537,7 +537,11 @@ def main():
             "sustained": sustained,
             "kernel_ms": kavg, "draw_ms": draw_ms, "draw_stats": stats, "covered_pixels": covered,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": traffic, "algorithmic_bytes": per_stage[dom], "kernel_ms": dom_ms, "peak_source": peak_src},
+                         "traffic": traffic, "algorithmic_bytes": per_stage[dom], "kernel_ms": dom_ms, "peak_source": peak_src,
+                         "note": "the stage with the longest mean duration in the serial pass; the setup and shading stages are within a few percent of "
+                                 "each other, so which one this is can change from run to run: roofline_kernels carries the same figure for every "
+                                 "stage, roofline_frame the whole frame (the figure of record), roofline_gather / fp32_issue the bounds that bind "
+                                 "the two big stages (scattered DRAM sectors, FP32 issue slots) rather than streaming HBM"},
             "roofline_frame": {"bound": "hbm", "algorithmic_bytes": b_alg, "achieved": b_alg / (ms_step * 1e-3) / 1e9,
                                "peak": peak, "unit": "GB/s", "frac": b_alg / (ms_step * 1e-3) / 1e9 / peak,
                                "note": "BASELINE.md §4 figure of record: B_alg / ms_per_step of the timed region (clear included, frames "
