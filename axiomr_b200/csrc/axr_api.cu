@@ -420,6 +420,8 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 	so.small_area = tput ? SMALL_AREA_TPUT : SMALL_AREA_LAT;
 	so.floor = peel ? ctx->peel_floor : nullptr;
 	so.clip_faces = sl.clip_faces; so.n_clip_faces = sl.n_clip_faces;
+	so.banded = (ctx->fp.y_lo > 0 || ctx->fp.y_hi < ctx->fp.H) ? 1 : 0;
+	so.band_lo = (float)ctx->fp.y_lo; so.band_hi = (float)ctx->fp.y_hi;
 	so.n_chunks = 0; so.swz_rows = 0;
 	const int bin_mode = peel ? (int)BINS_LISTS : m.bin_mode;
 	const bool bins = bin_mode == BINS_LISTS;

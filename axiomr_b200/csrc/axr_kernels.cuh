@@ -262,6 +262,8 @@ struct SetupOut {
 	unsigned* clip_faces;        // faces that need the clipper: appended by k_setup_raster, worked through by k_setup_clipped
 	unsigned* n_clip_faces;      // (capacity: the face count of the mesh, so the list cannot overflow)
 	unsigned n_chunks, swz_rows; // CTA -> face chunk interleave of k_setup_raster (setup_grid())
+	int banded;                  // the context owns rows [band_lo, band_hi) of the frame only
+	float band_lo, band_hi;
 };
 constexpr unsigned OVF_RECORDS = 1u, OVF_REFS = 2u, OVF_NEED_BINS = 4u;
 // BINS_NONE:  the mesh had no such triangle last time: no records, no bin kernels; one that turns up is counted, k_setup_clipped raises
@@ -517,7 +519,12 @@ __global__ void __launch_bounds__(SETUP_THREADS, AXR_SETUP_MINB) k_setup_raster(
 		const unsigned k0 = __float_as_uint(s0.w), k1 = __float_as_uint(s1.w), k2 = __float_as_uint(s2.w);
 		if (((k0 | k1 | k2) & 0x3fu) == 0) {
 			// every vertex inside every plane: clipTriangle returns the triangle unchanged (reference src/pipeline.cpp:322-325)
-			if (!is_backface(s0.x, s0.y, s1.x, s1.y, s2.x, s2.y))
+			// A context that owns a band of the frame (multi-GPU screen bands) first drops the faces whose rows miss it: the pixel box
+			// [max(y_lo, floor(minY)), min(y_hi, ceil(maxY))) is empty exactly when maxY <= y_lo or minY >= y_hi (y_lo, y_hi integers), so
+			// this is setup_triangle()'s own early return, taken before the back-face test and the box arithmetic for the 1 - 1/N of
+			// the replicated geometry that belongs to other ranks. (Such faces are not counted in the draw's statistics.)
+			const bool in_band = !o.banded || !(max3f(s0.y, s1.y, s2.y) <= o.band_lo || min3f(s0.y, s1.y, s2.y) >= o.band_hi);
+			if (in_band && !is_backface(s0.x, s0.y, s1.x, s1.y, s2.x, s2.y))
 				touched = emit_triangle<PEEL, true, true>(fp, o, s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s0.z, s1.z, s2.z, f * 8u, cnt);
 		} else if ((k0 & k1 & k2) >> 8) {
 			// all three vertices safely outside one plane: clipTriangle returns nothing (see clip_code_safe_out)
