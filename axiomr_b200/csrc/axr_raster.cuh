@@ -276,7 +276,8 @@ __device__ __forceinline__ float interp_z(const Setup& s, float c0, float c1, fl
 __device__ __forceinline__ bool z_draws(float z) { return z < INFINITY; }
 __device__ __forceinline__ unsigned long long make_key(float z, unsigned ordinal) {
 	unsigned b = __float_as_uint(z + 0.0f);
-	b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+	// negative: ~b, else b | 0x80000000 — as one shift and one xor: the mask is all ones for a set sign bit, the sign bit alone otherwise
+	b ^= (unsigned)((int)b >> 31) | 0x80000000u;
 	return ((unsigned long long)b << 32) | ordinal;
 }
 
