@@ -10,7 +10,20 @@ from axiomr_b200 import build as b  # noqa: E402
 # Compile-time knobs of axr_kernels.cuh (launch shapes). The defaults are the winners of the round-1 A/B runs
 # (profiles/r01_ab_*.jsonl); these variants bracket them.
 VARIANTS = {
-    "recompute_sv": ["AXR_TILE_RECOMPUTE_SV=1"],
+    # measurement knobs and the alternatives that were timed in round 2 (profiles/r02_ab_summary.md); the defaults are the winners
+    "setup_loop0": ["AXR_SETUP_LOOP=0"],            # closed-form coverage() per pixel in one counted loop
+    "setup_loop2": ["AXR_SETUP_LOOP=2"],            # four pixels per step, branch-free
+    "setup_mb10": ["AXR_SETUP_MINB=10"],            # 48 registers
+    "setup_mb16": ["AXR_SETUP_MINB=16"],            # 32 registers (spills)
+    "setup_noswz": ["AXR_SETUP_SWZ_K=1"],           # CTAs in face order
+    "setup_abl1": ["AXR_SETUP_ABLATE=1"],           # loads + cull only (results are wrong by design: use --no-parity)
+    "setup_abl2": ["AXR_SETUP_ABLATE=2"],           # + triangle setup
+    "setup_abl3": ["AXR_SETUP_ABLATE=3"],           # + coverage loop without the reductions
+    "tile_128x8": ["AXR_TILE_THREADS=128", "AXR_TILE_MINB=8"],
+    "tile_128x6": ["AXR_TILE_THREADS=128", "AXR_TILE_MINB=6"],
+    "tile_idx_pad": ["AXR_IDX_PAD=1"],
+    "tile_idx_stash": ["AXR_TILE_IDX_STASH=1"],
+    "tile_recompute_sv": ["AXR_TILE_RECOMPUTE_SV=1"],
 }
 
 def _one(name: str) -> str:
