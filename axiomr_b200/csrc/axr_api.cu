@@ -405,7 +405,8 @@ int issue_draw(axr_ctx* ctx, axr_mesh mh, const float* model, int si, bool peel)
 	prof_mark(ctx, g);
 	{
 		// at least sizeof(DrawStatus)/4 threads: the kernel also zeroes the draw's counters
-		const unsigned long long threads = m.n_verts > sizeof(DrawStatus) / 4 ? m.n_verts : sizeof(DrawStatus) / 4;
+		const unsigned long long per = (m.n_verts + AXR_VERTEX_PER_THREAD - 1) / AXR_VERTEX_PER_THREAD;
+		const unsigned long long threads = per > sizeof(DrawStatus) / 4 ? per : sizeof(DrawStatus) / 4;
 		k_vertex_xform<<<(unsigned)((threads + 255) / 256), 256, 0, g>>>(m.pos, m.n_verts, u.mvp, (float)ctx->fp.W, (float)ctx->fp.H, m.sv[si],
 		                                                                sl.d_status, sl.n_records, sl.n_clip_tiles, sl.n_clip_faces);
 		++launches;

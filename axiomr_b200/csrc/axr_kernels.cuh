@@ -28,6 +28,9 @@ namespace cg = cooperative_groups;
 
 namespace axr {
 
+#ifndef AXR_VERTEX_PER_THREAD
+#define AXR_VERTEX_PER_THREAD 2  // vertices per thread of k_vertex_xform (two loads in flight per thread: C3 34.9 -> 32.0 us; four: the same)
+#endif
 constexpr int GT = 32;            // GPU tile edge in pixels (a multiple of REF_TILE; keeps rows 128 B wide for the resolve)
 constexpr int GT_PIX = GT * GT;
 // Triangles whose pixel box is at most small_dim on a side and small_area pixels are rasterised by their own thread in
@@ -233,18 +236,29 @@ __global__ void __launch_bounds__(256) k_gather_peak(const uint4* __restrict__ b
 __global__ void __launch_bounds__(256) k_vertex_xform(const float4* __restrict__ pos, unsigned long long n, m4 mvp, float fW,
                                                       float fH, float4* __restrict__ sv, DrawStatus* status, unsigned* n_records, unsigned* n_clip_tiles,
                                                       unsigned* n_clip_faces) {
-	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < sizeof(DrawStatus) / 4) reinterpret_cast<unsigned*>(status)[i] = 0u;
-	if (i == 0) { *n_records = 0u; *n_clip_tiles = 0u; *n_clip_faces = 0u; }
-	if (i >= n) return;
-	float4 p = __ldg(pos + i);
-	v4 c = mul(mvp, V4(p.x, p.y, p.z, 1.0f));
-	float sx, sy, z;
-	to_screen(c, fW, fH, sx, sy, z);
-	// a "safely outside" bit implies the exact bit of the same plane, so the margins are only evaluated for the few vertices
-	// that are outside some plane at all
-	const unsigned code = clip_code(c);
-	sv[i] = make_float4(sx, sy, z, __uint_as_float(code ? (code | (clip_code_safe_out(c) << 8)) : 0u));
+	const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < sizeof(DrawStatus) / 4) reinterpret_cast<unsigned*>(status)[t] = 0u;
+	if (t == 0) { *n_records = 0u; *n_clip_tiles = 0u; *n_clip_faces = 0u; }
+	// AXR_VERTEX_PER_THREAD vertices per thread, a whole grid apart (coalesced), all loads in flight before the first transform
+	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+	float4 p[AXR_VERTEX_PER_THREAD];
+#pragma unroll
+	for (int k = 0; k < AXR_VERTEX_PER_THREAD; ++k) {
+		const unsigned long long i = t + k * stride;
+		if (i < n) p[k] = __ldg(pos + i);
+	}
+#pragma unroll
+	for (int k = 0; k < AXR_VERTEX_PER_THREAD; ++k) {
+		const unsigned long long i = t + k * stride;
+		if (i >= n) continue;
+		v4 c = mul(mvp, V4(p[k].x, p[k].y, p[k].z, 1.0f));
+		float sx, sy, z;
+		to_screen(c, fW, fH, sx, sy, z);
+		// a "safely outside" bit implies the exact bit of the same plane, so the margins are only evaluated for the few vertices
+		// that are outside some plane at all
+		const unsigned code = clip_code(c);
+		sv[i] = make_float4(sx, sy, z, __uint_as_float(code ? (code | (clip_code_safe_out(c) << 8)) : 0u));
+	}
 }
 
 // ------------------------------------------------------------------------------------------------ setup + small raster

@@ -24,6 +24,8 @@ VARIANTS = {
     "tile_idx_pad": ["AXR_IDX_PAD=1"],
     "tile_idx_stash": ["AXR_TILE_IDX_STASH=1"],
     "tile_recompute_sv": ["AXR_TILE_RECOMPUTE_SV=1"],
+    "vertex_x1": ["AXR_VERTEX_PER_THREAD=1"],
+    "vertex_x4": ["AXR_VERTEX_PER_THREAD=4"],
 }
 
 def _one(name: str) -> str:
