@@ -925,15 +925,25 @@ __global__ void __launch_bounds__(TILE_THREADS, AXR_TILE_MINB) k_tile_shade(cons
 	const int tid = threadIdx.x;
 	if (tid == 0) { s_clipped = 0u; s_nrec = 0u; s_ncand = 0u; }
 	// 1. stage the tile's visibility keys in shared memory (and hand the global buffer back empty for the next draw)
-	for (int p = tid; p < GT_PIX; p += TILE_THREADS) {
-		int px = x0 + (p & (GT - 1)), py = y0 + (p / GT);
-		unsigned long long k = KEY_EMPTY;
-		if (touched && px < fp.W && py >= fp.y_lo && py < fp.y_hi) {
-			unsigned long long* g = in.vis + (size_t)py * fp.W + px;
-			k = *g;
-			if (k != KEY_EMPTY) *g = KEY_EMPTY;
+	//    (all of a thread's loads first, then the stores: with the store inside the load loop the compiler keeps the loop rolled and a
+	//    CTA starts with GT_PIX / TILE_THREADS dependent DRAM round trips instead of one)
+	{
+		constexpr int PER = GT_PIX / TILE_THREADS;
+		unsigned long long kk[PER];
+#pragma unroll
+		for (int i = 0; i < PER; ++i) {
+			const int p = tid + i * TILE_THREADS;
+			const int px = x0 + (p & (GT - 1)), py = y0 + (p / GT);
+			kk[i] = KEY_EMPTY;
+			if (touched && px < fp.W && py >= fp.y_lo && py < fp.y_hi) kk[i] = in.vis[(size_t)py * fp.W + px];
 		}
-		s_keys[p] = k;
+#pragma unroll
+		for (int i = 0; i < PER; ++i) {
+			const int p = tid + i * TILE_THREADS;
+			const int px = x0 + (p & (GT - 1)), py = y0 + (p / GT);
+			if (kk[i] != KEY_EMPTY) in.vis[(size_t)py * fp.W + px] = KEY_EMPTY;
+			s_keys[p] = kk[i];
+		}
 	}
 	__syncthreads();
 	if (tid == 0) {
