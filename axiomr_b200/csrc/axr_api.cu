@@ -125,6 +125,8 @@ struct axr_ctx {
 	cudaStream_t geom_stream = nullptr;
 	unsigned* dirty_map = nullptr;  // axr_set_dirty_map
 	bool fill = false;              // axr_set_output_fill
+	unsigned* stale_list = nullptr; // axr_clear_stale_tiles: [2 counters][entries]
+	unsigned stale_cap = 0;
 	// The depth plane `fresh_target` was cleared to +inf by axr_clear (or at creation) and nothing has been drawn into it since: the
 	// first draw's merge test `z < fbZ` passes for every drawable z, so it does not read the plane (13 MB of the C3 frame). Off for
 	// good once the raw framebuffer pointers have been handed out (axr_framebuffer_device / _ipc: others may write behind our back).
@@ -669,6 +671,7 @@ void axr_destroy(axr_ctx* ctx) {
 	for (auto& r : ctx->registered) cudaHostUnregister(r.first);
 	cudaFree(ctx->color); cudaFree(ctx->depth);
 	cudaFree(ctx->peel_floor); cudaFree(ctx->peel_again);
+	cudaFree(ctx->stale_list);
 	for (auto& sl : ctx->slot) {
 		cudaFree(sl.vis); cudaFree(sl.tile_touched); cudaFree(sl.tile_count); cudaFree(sl.bin_start); cudaFree(sl.items);
 		cudaFree(sl.records); cudaFree(sl.n_records); cudaFree(sl.d_status); cudaFree(sl.clip_tiles); cudaFree(sl.n_clip_tiles);
@@ -1395,8 +1398,20 @@ int axr_clear_stale_tiles(axr_ctx* ctx, void* bgra_dev, void* depth_dev, void* d
 	if (!ctx) return AXR_ERR_INVALID;
 	if (!bgra_dev || !depth_dev || !dirty_prev_dev || !dirty_now_dev || count <= 0 || count > 65535) return fail(ctx, AXR_ERR_INVALID, "axr_clear_stale_tiles: bad argument");
 	CU(cudaSetDevice(ctx->device));
-	k_clear_stale_tiles<<<dim3(ctx->fp.ntx, ctx->fp.nty, count), 256, 0, stream ? (cudaStream_t)stream : ctx->stream>>>(
-		(unsigned*)bgra_dev, (float*)depth_dev, (unsigned*)dirty_prev_dev, (const unsigned*)dirty_now_dev, ctx->fp.W, ctx->fp.H, ctx->fp.ntx, GT, packed_argb, depth);
+	cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+	const unsigned n_entries = (unsigned)n_tiles(ctx) * (unsigned)count;
+	if (ctx->stale_cap < n_entries) {  // list of stale (target, tile) entries + its two counters; grown on first use
+		CU(cudaDeviceSynchronize());
+		cudaFree(ctx->stale_list);
+		ctx->stale_list = nullptr; ctx->stale_cap = 0;
+		CU(cudaMalloc(&ctx->stale_list, ((size_t)n_entries + 2) * sizeof(unsigned)));
+		CU(cudaMemsetAsync(ctx->stale_list, 0, 2 * sizeof(unsigned), s));
+		ctx->stale_cap = n_entries;
+	}
+	unsigned* counters = ctx->stale_list;  // [0] entries listed, [1] exit ticket
+	k_find_stale_tiles<<<(n_entries + 255) / 256, 256, 0, s>>>((unsigned*)dirty_prev_dev, (const unsigned*)dirty_now_dev, n_entries, ctx->stale_list + 2, counters);
+	k_clear_listed_tiles<<<148, 256, 0, s>>>((unsigned*)bgra_dev, (float*)depth_dev, ctx->stale_list + 2, counters, ctx->fp.W, ctx->fp.H, ctx->fp.ntx, ctx->fp.nty, GT,
+	                                         packed_argb, depth);
 	CU(cudaGetLastError());
 	return AXR_OK;
 }

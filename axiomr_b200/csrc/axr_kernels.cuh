@@ -134,25 +134,36 @@ __global__ void __launch_bounds__(256) k_clear_dirty_tiles(unsigned* color, floa
 	}
 }
 // Companion of axr_set_output_fill: a tile that was stored into the previous time the target was used (`prev`) and not this time (`now`)
-// still holds the old frame and is cleared here; `prev` is handed back all zero (it is the next frame's `now`). Same layout as above.
-__global__ void __launch_bounds__(256) k_clear_stale_tiles(unsigned* color, float* depth, unsigned* prev, const unsigned* now, int W, int H, int ntx,
-                                                           int tile_px, unsigned packed, float z) {
-	const size_t npx = (size_t)W * H;
-	const int tile = blockIdx.y * ntx + blockIdx.x;
-	const size_t map = (size_t)blockIdx.z * ((size_t)gridDim.x * gridDim.y) + tile;
-	const unsigned was = prev[map], is = now[map];
+// still holds the old frame and has to be cleared; `prev` is handed back all zero (it is the next frame's `now`). Two small kernels:
+// one THREAD per (target, tile) looks at the two flags and lists the stale tiles (usually none: a CTA per tile just to look would put
+// tens of thousands of CTAs on GPU 0 every frame, beside the view it is rendering), then a fixed grid clears the listed ones.
+__global__ void __launch_bounds__(256) k_find_stale_tiles(unsigned* prev, const unsigned* now, unsigned n_entries, unsigned* list, unsigned* n_list) {
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i == 0) n_list[1] = 0u;  // (the clear kernel's exit ticket, see below)
+	if (i >= n_entries) return;
+	const unsigned was = prev[i];
 	if (was == 0u) return;
-	__syncthreads();
-	if (threadIdx.x == 0) prev[map] = 0u;
-	if (is) return;
-	const int x0 = blockIdx.x * tile_px, y0 = blockIdx.y * tile_px;
-	for (int p = threadIdx.x; p < tile_px * tile_px; p += blockDim.x) {
-		const int px = x0 + p % tile_px, py = y0 + p / tile_px;
-		if (px < W && py < H) {
-			const size_t gi = (size_t)blockIdx.z * npx + (size_t)py * W + px;
-			color[gi] = packed; depth[gi] = z;
+	prev[i] = 0u;
+	if (now[i] == 0u) list[atomicAdd(n_list, 1u)] = i;
+}
+__global__ void __launch_bounds__(256) k_clear_listed_tiles(unsigned* color, float* depth, const unsigned* list, unsigned* n_list, int W, int H, int ntx, int nty,
+                                                            int tile_px, unsigned packed, float z) {
+	const size_t npx = (size_t)W * H;
+	const unsigned n = *n_list;
+	for (unsigned e = blockIdx.x; e < n; e += gridDim.x) {
+		const unsigned i = list[e], target = i / (unsigned)(ntx * nty), tile = i % (unsigned)(ntx * nty);
+		const int x0 = (int)(tile % (unsigned)ntx) * tile_px, y0 = (int)(tile / (unsigned)ntx) * tile_px;
+		for (int p = threadIdx.x; p < tile_px * tile_px; p += blockDim.x) {
+			const int px = x0 + p % tile_px, py = y0 + p / tile_px;
+			if (px < W && py < H) {
+				const size_t gi = (size_t)target * npx + (size_t)py * W + px;
+				color[gi] = packed; depth[gi] = z;
+			}
 		}
 	}
+	// the last CTA to leave resets the list for the next call
+	__syncthreads();
+	if (threadIdx.x == 0 && atomicAdd(n_list + 1, 1u) == gridDim.x - 1) n_list[0] = 0u;
 }
 // AoS AR::Vertex (56 B) -> position float4 + attributes (done once at mesh upload)
 __global__ void k_split_vertices(const float* __restrict__ raw, unsigned long long n, unsigned long long n_plane, float4* __restrict__ pos,
