@@ -254,7 +254,9 @@ int axr_clear_dirty_tiles(axr_ctx* ctx, void* bgra_dev, void* depth_dev, void* d
  * `depth` instead of reading the target — valid for a target that holds exactly one draw on top of a clear to those values, which is
  * what a composite slot is (not for shaders that discard, nor for axr_draw_mesh_host). The owner of the targets then keeps two dirty maps
  * per target, alternating per use: axr_clear_stale_tiles clears only the tiles flagged in `prev` (the previous use) and not in `now`
- * (this use) — none at all while the camera stands still — and hands `prev` back all zero. Same layouts as axr_clear_dirty_tiles. */
+ * (this use) — none at all while the camera stands still — and hands `prev` back all zero. Same layouts as axr_clear_dirty_tiles.
+ * Two small kernels (one thread per (target, tile) lists the stale tiles, a fixed grid clears the listed ones) that share a list owned by
+ * the context: calls on one context have to be ordered (one stream, or events between them). */
 int axr_set_output_fill(axr_ctx* ctx, int enabled, uint32_t packed_argb, float depth);
 /* Pixel -> lane mapping of the shading stage for outputs behind a link (axr_set_output into another GPU's memory): with rows on, a warp
  * shades one 32 x 1 pixel row instead of an 8 x 4 block, so its colour and depth stores are 128 contiguous bytes each — NVLink moves
