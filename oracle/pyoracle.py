@@ -24,8 +24,16 @@ _u32p = C.POINTER(C.c_uint32)
 
 
 def build(ref: bool = True) -> None:
-    """Compile the checkers (never the product). `make ref` is a no-op without /root/reference."""
-    subprocess.run(["make", "-s", "-C", HERE, "oracle"] + (["ref"] if ref else []), check=True)
+    """Compile the checkers (never the product). `make ref` is a no-op without /root/reference.
+    Serialised with a file lock: several test workers (pytest -n) calling this at once would otherwise run `make` on the same
+    targets concurrently and link against each other's half-written objects."""
+    import fcntl
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            subprocess.run(["make", "-s", "-C", HERE, "oracle"] + (["ref"] if ref else []), check=True)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
 
 
 class _Scene(C.Structure):
