@@ -317,6 +317,29 @@ __device__ __forceinline__ void touch_tile(const FrameParams& fp, const SetupOut
 #define AXR_SETUP_LOOP 1  // 1: runs x rows x pixels with the run / row terms hoisted (C3: 177 us; 2: four pixels per step, branch-free: 195 us); 0: closed-form coverage() per pixel in one counted loop
 #endif
 
+#ifndef AXR_SETUP_TRIM
+#define AXR_SETUP_TRIM 0  // instruction trims of the pixel loop: bit 0 = float lane counter, bit 1 = one NaN-propagating 3-input minimum + one compare
+#endif
+// c0 >= 0 && c1 >= 0 && c2 >= 0 with NaN failing (_CMP_GE_OQ). min.NaN returns NaN when any input is one, and NaN >= 0 is false;
+// otherwise the minimum is >= 0 exactly when all three are (-0 >= 0 holds, whichever zero the minimum picks).
+__device__ __forceinline__ bool all_ge0(float c0, float c1, float c2) {
+#if defined(__CUDA_ARCH__) && (AXR_SETUP_TRIM & 2)
+	float m;
+	asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(m) : "f"(c0), "f"(c1), "f"(c2));
+	return m >= 0.f;
+#else
+	return c0 >= 0.f && c1 >= 0.f && c2 >= 0.f;
+#endif
+}
+// inverse of small_int_to_f32 for 0 <= f < 2^22, f an integer
+__device__ __forceinline__ int f32_to_small_int(float f) {
+#ifdef __CUDA_ARCH__
+	return (int)(__float_as_uint(f + 8388608.0f) - 0x4B000000u);
+#else
+	return (int)f;
+#endif
+}
+
 // Exact coverage + visibility keys of a triangle whose pixel box is small (at most 12 x 12, 64 px), by the thread that set it up.
 // Returns true when a key was written.
 template <bool PEEL>
@@ -360,6 +383,9 @@ __device__ __forceinline__ bool raster_small(const FrameParams& fp, const SetupO
 		const float sxc = small_int_to_f32(startX) + 0.5f;
 		const float p0 = s.a0 * sxc, p1 = s.a1 * sxc, p2 = s.a2 * sxc;
 		const int i0 = hi ? startX + 8 : startX;  // the pixel whose lane index i is 0
+#if AXR_SETUP_TRIM & 1
+		const float fi0 = small_int_to_f32(xs - i0), fend = small_int_to_f32(xe - i0);
+#endif
 #pragma unroll 1
 		for (int py = s.Y0; py < s.Y1; ++py) {
 			const float pyc = small_int_to_f32(py) + 0.5f;
@@ -385,12 +411,19 @@ __device__ __forceinline__ bool raster_small(const FrameParams& fp, const SetupO
 					hit(px, py, r0 + s.a0 * fi, r1 + s.a1 * fi, r2 + s.a2 * fi);
 				}
 			}
+#elif AXR_SETUP_TRIM & 1
+			// the lane index itself is the loop counter (small integers are exact in binary32); the pixel column is only rebuilt for a hit
+#pragma unroll 1
+			for (float fi = fi0; fi < fend; fi += 1.0f) {
+				const float c0 = r0 + s.a0 * fi, c1 = r1 + s.a1 * fi, c2 = r2 + s.a2 * fi;
+				if (all_ge0(c0, c1, c2)) hit(i0 + f32_to_small_int(fi), py, c0, c1, c2);
+			}
 #else
 #pragma unroll 1
 			for (int px = xs; px < xe; ++px) {
 				const float fi = small_int_to_f32(px - i0);
 				const float c0 = r0 + s.a0 * fi, c1 = r1 + s.a1 * fi, c2 = r2 + s.a2 * fi;
-				if (c0 >= 0.f && c1 >= 0.f && c2 >= 0.f) hit(px, py, c0, c1, c2);
+				if (all_ge0(c0, c1, c2)) hit(px, py, c0, c1, c2);
 			}
 #endif
 		}

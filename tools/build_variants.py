@@ -19,6 +19,9 @@ VARIANTS = {
     "setup_abl1": ["AXR_SETUP_ABLATE=1"],           # loads + cull only (results are wrong by design: use --no-parity)
     "setup_abl2": ["AXR_SETUP_ABLATE=2"],           # + triangle setup
     "setup_abl3": ["AXR_SETUP_ABLATE=3"],           # + coverage loop without the reductions
+    "setup_trim1": ["AXR_SETUP_TRIM=1"],            # float lane counter in the pixel loop
+    "setup_trim2": ["AXR_SETUP_TRIM=2"],            # FMNMX3.NAN + one FSETP instead of three FSETP
+    "setup_trim3": ["AXR_SETUP_TRIM=3"],
     "tile_128x8": ["AXR_TILE_THREADS=128", "AXR_TILE_MINB=8"],
     "tile_128x6": ["AXR_TILE_THREADS=128", "AXR_TILE_MINB=6"],
     "tile_idx_pad": ["AXR_IDX_PAD=1"],
