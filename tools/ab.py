@@ -82,7 +82,7 @@ def main():
     a = ap.parse_args()
     libs = {"default": os.path.join(ROOT, "axiomr_b200", "libaxr_b200.so")}
     for p in sorted(glob.glob(os.path.join(os.environ.get("AXR_AB_DIR") or os.path.join(ROOT, "variants_tmp"), "lib_*.so"))):
-        libs[os.path.basename(p)[4:-3]] = p
+        libs.setdefault(os.path.basename(p)[4:-3], p)  # "default" is always the in-tree library
     if a.variants:
         libs = {k: libs[k] for k in a.variants}
     t0 = time.time()

@@ -22,6 +22,9 @@ VARIANTS = {
     "setup_trim1": ["AXR_SETUP_TRIM=1"],            # float lane counter in the pixel loop
     "setup_trim2": ["AXR_SETUP_TRIM=2"],            # FMNMX3.NAN + one FSETP instead of three FSETP
     "setup_trim3": ["AXR_SETUP_TRIM=3"],
+    "setup_pf0": ["AXR_SETUP_PF=0"],                # without the cross-CTA L2 prefetch of index chunks
+    "setup_pf888": ["AXR_SETUP_PF=888"],
+    "setup_pf3552": ["AXR_SETUP_PF=3552"],
     "tile_128x8": ["AXR_TILE_THREADS=128", "AXR_TILE_MINB=8"],
     "tile_128x6": ["AXR_TILE_THREADS=128", "AXR_TILE_MINB=6"],
     "tile_idx_pad": ["AXR_IDX_PAD=1"],
